@@ -1,0 +1,185 @@
+/*
+ * splatter360.h -- C-ABI of libsplatter360.so, the B200-native differentiable Gaussian-splat
+ * rasterizer (pinhole + native equirectangular).
+ *
+ * This is the drop-in boundary for the hot path of thucz/splatter360.  The reference reaches its
+ * rasterizer through a pip-installed torch C++ extension (pybind, no C header):
+ *
+ *   from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+ *       /root/reference/src/model/decoder/cuda_splatting.py:5-8
+ *   rasterizer(means3D=..., means2D=..., shs=..., colors_precomp=..., opacities=..., cov3D_precomp=...)
+ *       /root/reference/src/model/decoder/cuda_splatting.py:113-124, 192-217
+ *
+ * whose extension entry points are  _C.rasterize_gaussians / _C.rasterize_gaussians_backward /
+ * _C.mark_visible  (upstream is not vendored in the reference).  The
+ * functions below are what a binding for that path binds instead; each names the upstream entry
+ * it replaces.  INTEGRATION.md shows the ctypes stub and the reference-side import switch.
+ *
+ * Contract
+ *   - plain C types only; every pointer is a DEVICE pointer unless it says "host".
+ *   - the library never allocates, frees or keeps state: all buffers (inputs, outputs, saved state,
+ *     scratch) are caller-owned; sizes come from the s360_*_bytes() queries.
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 on success, a positive cudaError_t, or a negative S360_ERR_* code.
+ *     No C++ exceptions cross the boundary.  s360_error_string() maps codes to text.
+ *   - re-entrant; safe from several host threads on distinct streams.
+ *
+ * Data flow of one forward call (one view):
+ *   s360_forward_preprocess   K1 project/cull/cov2D/SH  -> geom state, radii, depth-ordered ids,
+ *                             per-Gaussian instance offsets, *num_rendered (device u32)
+ *   (caller sizes the instance buffers: read *num_rendered, or pass a capacity it trusts)
+ *   s360_forward_render       emit (tile,id) instances in depth order -> stable radix sort by tile
+ *                             -> tile ranges -> front-to-back compositing
+ *   s360_backward             per-tile back-to-front gradient pass + fused per-Gaussian backward
+ */
+#ifndef SPLATTER360_H
+#define SPLATTER360_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S360_ABI_VERSION 1
+
+#define S360_MODE_PINHOLE 0 /* upstream semantics                     */
+#define S360_MODE_ERP 1     /* native equirectangular splatting      */
+
+#define S360_ERR_BAD_ARGUMENT (-1)
+#define S360_ERR_WORKSPACE_OVERFLOW (-2) /* reported through S360Counters.overflow, see below */
+#define S360_ERR_UNSUPPORTED (-3)
+
+/* Mirrors GaussianRasterizationSettings (12 fields; cuda_splatting.py:99-112) plus the constants
+ * upstream hard-codes, so the oracle and the kernels can be frozen to whatever the installed fork
+ * does. */
+typedef struct S360View {
+  int32_t P;             /* number of Gaussians                                              */
+  int32_t M;             /* SH coefficients per channel stored per Gaussian (25 in splatter360) */
+  int32_t sh_degree;     /* settings.sh_degree                                               */
+  int32_t image_height;  /* settings.image_height                                            */
+  int32_t image_width;   /* settings.image_width                                             */
+  int32_t mode;          /* S360_MODE_*                                                      */
+  int32_t max_sh_degree; /* highest SH band evaluated (4; stock upstream stops at 3)         */
+  int32_t tight_bbox;    /* 1: drop tiles the alpha>=1/255 ellipse cannot reach (image-exact) */
+  float tanfovx;         /* settings.tanfovx                                                 */
+  float tanfovy;         /* settings.tanfovy                                                 */
+  float near_cull;       /* 0.2 : cull view z (pinhole) / radial distance (erp) <= this      */
+  float fov_clamp;       /* 1.3 : |x/z| clamp factor inside J (pinhole)                      */
+  float lowpass;         /* 0.3 : added to the cov2D diagonal                                */
+  float pole_eps;        /* erp : horizontal radius clamp rho >= pole_eps * r                */
+  const float* viewmatrix; /* [16] settings.viewmatrix  (p_view = [x y z 1] . V, row-major)  */
+  const float* projmatrix; /* [16] settings.projmatrix  (unused in erp mode)                 */
+  const float* campos;     /* [3]  settings.campos                                           */
+  const float* bg;         /* [3]  settings.bg                                               */
+} S360View;
+
+/* Device-side counters written by the forward pass (16 bytes). */
+typedef struct S360Counters {
+  uint32_t num_rendered; /* total (tile, Gaussian) instances N this view needs               */
+  uint32_t overflow;     /* set to 1 by s360_forward_render if N > instance_capacity         */
+  uint32_t num_visible;  /* Gaussians with radius > 0                                        */
+  uint32_t reserved;
+} S360Counters;
+
+/* ---- sizes of caller-owned buffers -------------------------------------------------------- */
+/* geometry state kept from forward to backward (per Gaussian). */
+size_t s360_geom_bytes(int32_t P);
+/* transient scratch of s360_forward_preprocess (depth sort + scan). */
+size_t s360_preprocess_scratch_bytes(int32_t P);
+/* transient scratch of s360_forward_render for `instance_capacity` instances. */
+size_t s360_binning_scratch_bytes(int64_t instance_capacity, int32_t image_height, int32_t image_width);
+/* image state kept from forward to backward (final transmittance, contributor count, tile ranges). */
+size_t s360_image_bytes(int32_t image_height, int32_t image_width);
+/* transient scratch of s360_backward (per-Gaussian screen-space gradient accumulators). */
+size_t s360_backward_scratch_bytes(int32_t P);
+
+/* ---- forward, stage 1 (replaces the first half of upstream _C.rasterize_gaussians:
+ *      preprocessCUDA + InclusiveSum) ------------------------------------------------------- */
+int s360_forward_preprocess(
+    const S360View* view,        /* host */
+    const float* means3D,        /* [P,3]                                                      */
+    const float* cov3D,          /* [P,6] (xx,xy,xz,yy,yz,zz)  cov3D_precomp                   */
+    const float* opacities,      /* [P]                                                        */
+    const float* shs,            /* [P,M,3] or NULL                                            */
+    const float* colors_precomp, /* [P,3]  or NULL (exactly one of shs/colors_precomp)         */
+    void* geom,                  /* s360_geom_bytes(P)                                         */
+    int32_t* radii,              /* [P] out                                                    */
+    uint32_t* depth_order,       /* [P] out: Gaussian ids sorted by (depth, id)                */
+    uint32_t* inst_offsets,      /* [P] out: exclusive scan of tiles touched, in depth order   */
+    S360Counters* counters,      /* out (device)                                               */
+    void* scratch,               /* s360_preprocess_scratch_bytes(P)                           */
+    void* stream);
+
+/* ---- forward, stage 2 (replaces duplicateWithKeys + SortPairs + identifyTileRanges + renderCUDA) */
+int s360_forward_render(
+    const S360View* view,        /* host */
+    const void* geom,
+    const uint32_t* depth_order, /* from stage 1 */
+    const uint32_t* inst_offsets,/* from stage 1 */
+    S360Counters* counters,      /* device; num_rendered read, overflow written                */
+    int64_t instance_capacity,   /* entries available in point_list / binning scratch          */
+    uint32_t* point_list,        /* [instance_capacity] out: Gaussian ids sorted by (tile, depth, id) */
+    void* image_state,           /* s360_image_bytes(H,W) out                                  */
+    float* out_color,            /* [3,H,W] out                                                */
+    void* scratch,               /* s360_binning_scratch_bytes(instance_capacity,H,W)          */
+    void* stream);
+
+/* ---- backward (replaces upstream _C.rasterize_gaussians_backward) ---------------------------- */
+int s360_backward(
+    const S360View* view,        /* host */
+    const float* means3D, const float* cov3D, const float* opacities,
+    const float* shs, const float* colors_precomp,
+    const void* geom, const int32_t* radii,
+    const uint32_t* point_list, const void* image_state,
+    const float* dL_dcolor,      /* [3,H,W]                                                    */
+    float* dL_dmeans3D,          /* [P,3] out                                                  */
+    float* dL_dmeans2D,          /* [P,3] out (NDC units, z = 0)  */
+    float* dL_dcov3D,            /* [P,6] out                                                  */
+    float* dL_dopacity,          /* [P]   out                                                  */
+    float* dL_dshs,              /* [P,M,3] out or NULL                                        */
+    float* dL_dcolors,           /* [P,3] out or NULL                                          */
+    void* scratch,               /* s360_backward_scratch_bytes(P)                             */
+    void* stream);
+
+/* ---- visibility mask (replaces upstream _C.mark_visible) ------------------------------------ */
+int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream);
+
+/* ---- debugging / introspection ---------------------------------------------------------------- */
+/* Unpack the geometry state for per-stage parity tests.  Any output may be NULL. */
+int s360_debug_unpack_geom(int32_t P, const void* geom, float* xy /*[P,2]*/, float* depth /*[P]*/,
+                           float* conic_opacity /*[P,4]*/, float* rgb /*[P,3]*/,
+                           uint32_t* tiles_touched /*[P]*/, uint8_t* clamped /*[P,3]*/, void* stream);
+/* Unpack the image state.  Any output may be NULL. */
+int s360_debug_unpack_image(int32_t image_height, int32_t image_width, const void* image_state,
+                            float* final_T /*[H,W]*/, uint32_t* n_contrib /*[H,W]*/,
+                            uint32_t* tile_ranges /*[tiles,2]*/, void* stream);
+
+/* ---- optional per-stage timing (CUDA events recorded on the caller's stream around each stage).
+ * Process-wide switch, off by default; used by bench.py for the roofline numbers.  The only mutable
+ * state the library holds besides the launch counter. */
+#define S360_STAGE_PREPROCESS 0
+#define S360_STAGE_DEPTH_SORT 1
+#define S360_STAGE_SCAN 2
+#define S360_STAGE_EMIT 3
+#define S360_STAGE_TILE_SORT 4
+#define S360_STAGE_TILE_RANGES 5
+#define S360_STAGE_RENDER_FWD 6
+#define S360_STAGE_RENDER_BWD 7
+#define S360_STAGE_PREPROCESS_BWD 8
+#define S360_NUM_STAGES 9
+int s360_profile_enable(int on); /* returns the previous setting */
+/* Sum of elapsed milliseconds and number of recordings per stage since the last reset.
+ * Synchronises on the recorded events.  ms / counts: host arrays of S360_NUM_STAGES, may be NULL. */
+int s360_profile_read(double* ms, uint64_t* counts, int reset);
+
+int s360_abi_version(void);
+const char* s360_error_string(int code);
+/* number of kernels launched by this library since load (for bench.py's gpu_launches). */
+uint64_t s360_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLATTER360_H */

@@ -1,0 +1,264 @@
+// common.cuh -- shared device helpers and state layouts for libsplatter360 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/splatter360.h"
+
+namespace s360 {
+
+constexpr int TILE = 16;                 // tile edge in pixels (upstream BLOCK_X = BLOCK_Y = 16)
+constexpr int TILE_PIX = TILE * TILE;    // 256 threads per tile
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_EPS = 0.0001f;
+constexpr float PI_F = 3.14159265358979323846f;
+
+// Per-Gaussian geometry record: 3 x float4 = 48 B, gathered by the render kernels.
+//   r0 = {x, y, conicA, conicB}   r1 = {conicC, opacity, hx, hy}   r2 = {r, g, b, depth}
+// hx, hy: half extents of the axis-aligned box outside which the Gaussian cannot contribute.
+constexpr int REC_F4 = 3;
+
+// Geometry state carved out of the caller's `geom` buffer.
+struct GeomState {
+  float4* rec;        // [P*3]
+  uint2* rect;        // [P] packed tile rect: x = (x0 & 0xffff) | nx << 16 ; y = y0 | ny << 16
+  uint8_t* clamped;   // [P] bits 0..2 SH clamp per channel, bit 3 = jacobian clamp x, bit 4 = clamp y
+};
+
+struct ImageState {
+  float* final_T;       // [H*W]
+  uint32_t* n_contrib;  // [H*W]
+  uint2* ranges;        // [tiles]
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline GeomState carve_geom(void* buf, int P) {
+  char* p = (char*)buf;
+  GeomState g;
+  g.rec = (float4*)p;      p += align_up((size_t)P * REC_F4 * sizeof(float4), 256);
+  g.rect = (uint2*)p;      p += align_up((size_t)P * sizeof(uint2), 256);
+  g.clamped = (uint8_t*)p; p += align_up((size_t)P, 256);
+  return g;
+}
+inline size_t geom_bytes(int P) {
+  return align_up((size_t)P * REC_F4 * sizeof(float4), 256) + align_up((size_t)P * sizeof(uint2), 256) +
+         align_up((size_t)P, 256);
+}
+inline ImageState carve_image(void* buf, int H, int W) {
+  char* p = (char*)buf;
+  ImageState s;
+  size_t npix = (size_t)H * W;
+  size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+  s.final_T = (float*)p;      p += align_up(npix * 4, 256);
+  s.n_contrib = (uint32_t*)p; p += align_up(npix * 4, 256);
+  s.ranges = (uint2*)p;       p += align_up(tiles * 8, 256);
+  return s;
+}
+inline size_t image_bytes(int H, int W) {
+  size_t npix = (size_t)H * W;
+  size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+  return align_up(npix * 4, 256) * 2 + align_up(tiles * 8, 256);
+}
+
+// launch bookkeeping (introspection only)
+void count_launch(int n = 1);
+
+// ---------------------------------------------------------------------------------------------
+// camera block loaded once per thread from the tiny device-resident matrices
+struct Cam {
+  float V[16];
+  float PM[16];
+  float cam[3];
+};
+
+__device__ __forceinline__ void load_cam(const S360View& v, Cam& c, bool need_proj) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) c.V[i] = __ldg(v.viewmatrix + i);
+  if (need_proj) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) c.PM[i] = __ldg(v.projmatrix + i);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) c.cam[i] = __ldg(v.campos + i);
+}
+
+// Screen-space geometry of one Gaussian, shared by the forward and backward preprocess kernels.
+struct Geo {
+  float t[3];       // view-space centre
+  float tc[3];      // centre used inside J (after fov / pole clamp)
+  bool clampx, clampy;
+  float J[2][3];
+  float Mm[2][3];   // J * R
+  float a, b, c;    // cov2D incl. low-pass
+};
+
+template <int MODE>
+__device__ __forceinline__ void geo_compute(const S360View& v, const float* V, float mx, float my, float mz,
+                                            const float* cov, Geo& g) {
+  // R[i][k] = V[4k + i]
+  g.t[0] = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+  g.t[1] = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+  g.t[2] = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+  const float x = g.t[0], y = g.t[1], z = g.t[2];
+  g.clampx = g.clampy = false;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) g.J[i][k] = 0.f;
+  if (MODE == S360_MODE_PINHOLE) {
+    const float fx = (float)v.image_width / (2.f * v.tanfovx), fy = (float)v.image_height / (2.f * v.tanfovy);
+    const float limx = v.fov_clamp * v.tanfovx, limy = v.fov_clamp * v.tanfovy;
+    const float txtz = x / z, tytz = y / z;
+    g.clampx = (txtz < -limx) || (txtz > limx);
+    g.clampy = (tytz < -limy) || (tytz > limy);
+    const float cx = fminf(limx, fmaxf(-limx, txtz)) * z;
+    const float cy = fminf(limy, fmaxf(-limy, tytz)) * z;
+    g.tc[0] = cx; g.tc[1] = cy; g.tc[2] = z;
+    g.J[0][0] = fx / z; g.J[0][2] = -(fx * cx) / (z * z);
+    g.J[1][1] = fy / z; g.J[1][2] = -(fy * cy) / (z * z);
+  } else {
+    const float su = -(float)v.image_width / (2.f * PI_F), sv = -(float)v.image_height / PI_F;
+    const float rho = sqrtf(x * x + z * z);
+    const float r = sqrtf(x * x + y * y + z * z);
+    const float rmin = v.pole_eps * r;
+    float xc = x, zc = z;
+    if (rho < rmin) {
+      g.clampx = true;
+      if (rho > 0.f) { const float s = rmin / rho; xc = x * s; zc = z * s; }
+      else { xc = 0.f; zc = rmin; }
+    }
+    g.tc[0] = xc; g.tc[1] = y; g.tc[2] = zc;
+    const float q = xc * xc + zc * zc, rc = sqrtf(q), r2 = q + y * y;
+    g.J[0][0] = su * zc / q;              g.J[0][2] = -su * xc / q;
+    g.J[1][0] = -sv * xc * y / (rc * r2); g.J[1][1] = sv * rc / r2; g.J[1][2] = -sv * zc * y / (rc * r2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      g.Mm[i][k] = g.J[i][0] * V[4 * k + 0] + g.J[i][1] * V[4 * k + 1] + g.J[i][2] * V[4 * k + 2];
+  const float S[3][3] = {{cov[0], cov[1], cov[2]}, {cov[1], cov[3], cov[4]}, {cov[2], cov[4], cov[5]}};
+  float Sm0[3], Sm1[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    Sm0[k] = S[k][0] * g.Mm[0][0] + S[k][1] * g.Mm[0][1] + S[k][2] * g.Mm[0][2];
+    Sm1[k] = S[k][0] * g.Mm[1][0] + S[k][1] * g.Mm[1][1] + S[k][2] * g.Mm[1][2];
+  }
+  g.a = g.Mm[0][0] * Sm0[0] + g.Mm[0][1] * Sm0[1] + g.Mm[0][2] * Sm0[2] + v.lowpass;
+  g.b = g.Mm[0][0] * Sm1[0] + g.Mm[0][1] * Sm1[1] + g.Mm[0][2] * Sm1[2];
+  g.c = g.Mm[1][0] * Sm1[0] + g.Mm[1][1] * Sm1[1] + g.Mm[1][2] * Sm1[2] + v.lowpass;
+}
+
+// ---------------------------------------------------------------------------------------------
+// real spherical harmonics, 3DGS sign convention, bands 0..4
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                       0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                       -0.5900435899266435f};
+__device__ constexpr float SH_C4[9] = {2.5033429417967046f,  -1.7701307697799304f, 0.9461746957575601f,
+                                       -0.6690465435572892f, 0.10578554691520431f, -0.6690465435572892f,
+                                       0.47308734787878004f, -1.7701307697799304f, 0.6258357354491761f};
+
+// basis values for all 25 slots (unused bands are left untouched); returns number of active coeffs
+__device__ __forceinline__ int sh_basis(int deg, float x, float y, float z, float* b) {
+  b[0] = SH_C0;
+  if (deg < 1) return 1;
+  b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+  if (deg < 2) return 4;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.f * zz - xx - yy);
+  b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
+  if (deg < 3) return 9;
+  b[9] = SH_C3[0] * y * (3.f * xx - yy);
+  b[10] = SH_C3[1] * xy * z;
+  b[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+  b[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+  b[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
+  b[14] = SH_C3[5] * z * (xx - yy);
+  b[15] = SH_C3[6] * x * (xx - 3.f * yy);
+  if (deg < 4) return 16;
+  b[16] = SH_C4[0] * xy * (xx - yy);
+  b[17] = SH_C4[1] * yz * (3.f * xx - yy);
+  b[18] = SH_C4[2] * xy * (7.f * zz - 1.f);
+  b[19] = SH_C4[3] * yz * (7.f * zz - 3.f);
+  b[20] = SH_C4[4] * (zz * (35.f * zz - 30.f) + 3.f);
+  b[21] = SH_C4[5] * xz * (7.f * zz - 3.f);
+  b[22] = SH_C4[6] * (xx - yy) * (7.f * zz - 1.f);
+  b[23] = SH_C4[7] * xz * (xx - 3.f * yy);
+  b[24] = SH_C4[8] * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+  return 25;
+}
+
+// partial derivatives of the basis polynomials w.r.t. (x, y, z) taken as independent variables
+__device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
+  bx[0] = by[0] = bz[0] = 0.f;
+  if (deg < 1) return;
+  bx[1] = 0.f; by[1] = -SH_C1; bz[1] = 0.f;
+  bx[2] = 0.f; by[2] = 0.f; bz[2] = SH_C1;
+  bx[3] = -SH_C1; by[3] = 0.f; bz[3] = 0.f;
+  if (deg < 2) return;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  bx[4] = SH_C2[0] * y; by[4] = SH_C2[0] * x; bz[4] = 0.f;
+  bx[5] = 0.f; by[5] = SH_C2[1] * z; bz[5] = SH_C2[1] * y;
+  bx[6] = SH_C2[2] * -2.f * x; by[6] = SH_C2[2] * -2.f * y; bz[6] = SH_C2[2] * 4.f * z;
+  bx[7] = SH_C2[3] * z; by[7] = 0.f; bz[7] = SH_C2[3] * x;
+  bx[8] = SH_C2[4] * 2.f * x; by[8] = SH_C2[4] * -2.f * y; bz[8] = 0.f;
+  if (deg < 3) return;
+  bx[9] = SH_C3[0] * 6.f * xy; by[9] = SH_C3[0] * (3.f * xx - 3.f * yy); bz[9] = 0.f;
+  bx[10] = SH_C3[1] * yz; by[10] = SH_C3[1] * xz; bz[10] = SH_C3[1] * xy;
+  bx[11] = SH_C3[2] * -2.f * xy; by[11] = SH_C3[2] * (4.f * zz - xx - 3.f * yy); bz[11] = SH_C3[2] * 8.f * yz;
+  bx[12] = SH_C3[3] * -6.f * xz; by[12] = SH_C3[3] * -6.f * yz; bz[12] = SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy);
+  bx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy); by[13] = SH_C3[4] * -2.f * xy; bz[13] = SH_C3[4] * 8.f * xz;
+  bx[14] = SH_C3[5] * 2.f * xz; by[14] = SH_C3[5] * -2.f * yz; bz[14] = SH_C3[5] * (xx - yy);
+  bx[15] = SH_C3[6] * (3.f * xx - 3.f * yy); by[15] = SH_C3[6] * -6.f * xy; bz[15] = 0.f;
+  if (deg < 4) return;
+  bx[16] = SH_C4[0] * (3.f * xx * y - yy * y); by[16] = SH_C4[0] * (xx * x - 3.f * x * yy); bz[16] = 0.f;
+  bx[17] = SH_C4[1] * 6.f * xy * z; by[17] = SH_C4[1] * z * (3.f * xx - 3.f * yy); bz[17] = SH_C4[1] * y * (3.f * xx - yy);
+  bx[18] = SH_C4[2] * y * (7.f * zz - 1.f); by[18] = SH_C4[2] * x * (7.f * zz - 1.f); bz[18] = SH_C4[2] * 14.f * xy * z;
+  bx[19] = 0.f; by[19] = SH_C4[3] * z * (7.f * zz - 3.f); bz[19] = SH_C4[3] * y * (21.f * zz - 3.f);
+  bx[20] = 0.f; by[20] = 0.f; bz[20] = SH_C4[4] * (140.f * zz * z - 60.f * z);
+  bx[21] = SH_C4[5] * z * (7.f * zz - 3.f); by[21] = 0.f; bz[21] = SH_C4[5] * x * (21.f * zz - 3.f);
+  bx[22] = SH_C4[6] * 2.f * x * (7.f * zz - 1.f); by[22] = SH_C4[6] * -2.f * y * (7.f * zz - 1.f);
+  bz[22] = SH_C4[6] * (xx - yy) * 14.f * z;
+  bx[23] = SH_C4[7] * z * (3.f * xx - 3.f * yy); by[23] = SH_C4[7] * -6.f * xy * z; bz[23] = SH_C4[7] * x * (xx - 3.f * yy);
+  bx[24] = SH_C4[8] * (4.f * xx * x - 12.f * x * yy); by[24] = SH_C4[8] * (-12.f * xx * y + 4.f * yy * y); bz[24] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers (defined in the .cu files, called from api.cu)
+int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
+                      const float* shs, const float* colors, GeomState g, int32_t* radii,
+                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st);
+int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* shs,
+                               GeomState g, const int32_t* radii, const float* acc, float* d_means,
+                               float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
+                               cudaStream_t st);
+int launch_mark_visible(const S360View& v, const float* means, uint8_t* present, cudaStream_t st);
+
+// radix sort of (u32 key, u32 value) pairs on bits [0, nbits); result lands in (keys_out, vals_out).
+// keys_a/vals_a hold the input; *_b are same-sized alternates.  n_dev (device u32, may be NULL)
+// overrides n with min(*n_dev, n).  Returns which buffer (0 = a, 1 = b) holds the result.
+size_t radix_scratch_bytes(int64_t n);
+int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n,
+                     const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b);
+
+int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_order, uint32_t* offsets,
+                        S360Counters* counters, uint32_t* block_sums, cudaStream_t st);
+int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, const uint32_t* offsets,
+                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, cudaStream_t st);
+int launch_tile_ranges(const S360View& v, const uint32_t* keys, const S360Counters* counters, int64_t capacity,
+                       uint2* ranges, cudaStream_t st);
+
+int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
+                          float* out_color, cudaStream_t st);
+int launch_render_backward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
+                           const float* dL_dcolor, float* acc, cudaStream_t st);
+
+constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator (9 used)
+
+}  // namespace s360

@@ -1,0 +1,344 @@
+// preprocess.cu -- per-Gaussian kernels.
+//   K1  preprocess_kernel          : world->view, pinhole / equirectangular projection, EWA cov2D,
+//                                    conic, extent, tile rect, SH -> RGB        
+//   K8+K9 preprocess_backward_kernel: dL/d(conic, mean2D, rgb, opacity) -> dL/d(cov3D, mean3D, SH)
+//   K10 mark_visible_kernel
+// Replaces upstream preprocessCUDA / computeCov2DCUDA / preprocessCUDA(bwd) / checkFrustum behind
+// /root/reference/src/model/decoder/cuda_splatting.py:113-124.
+#include "common.cuh"
+
+namespace s360 {
+
+constexpr int PRE_THREADS = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
+                  const float* __restrict__ opac, const float* __restrict__ shs,
+                  const float* __restrict__ colors, GeomState gs, int32_t* __restrict__ radii,
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, S360Counters* counters) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int P = v.P;
+  const int W = v.image_width, H = v.image_height;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  bool upstream_visible = false;
+  if (idx < P) {
+    Cam cam;
+    load_cam(v, cam, MODE == S360_MODE_PINHOLE);
+    const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
+    int radius = 0;
+    uint2 rect = make_uint2(0u, 0u);
+    uint32_t key = 0xFFFFFFFFu;
+    float cv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cv[k] = cov3D[6 * idx + k];
+    Geo g;
+    geo_compute<MODE>(v, cam.V, mx, my, mz, cv, g);
+    float sortkey;
+    bool alive;
+    if (MODE == S360_MODE_PINHOLE) { sortkey = g.t[2]; }
+    else { sortkey = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]); }
+    alive = sortkey > v.near_cull;
+    const float det = g.a * g.c - g.b * g.b;
+    alive = alive && (det != 0.f);
+    if (alive) {
+      const float det_inv = 1.f / det;
+      const float cA = g.c * det_inv, cB = -g.b * det_inv, cC = g.a * det_inv;
+      int ex, ey;
+      float px, py;
+      if (MODE == S360_MODE_PINHOLE) {
+        const float mid = 0.5f * (g.a + g.c);
+        const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
+        const float lam1 = mid + root, lam2 = mid - root;
+        ex = ey = (int)ceilf(3.f * sqrtf(fmaxf(lam1, lam2)));
+        const float* PM = cam.PM;
+        const float hx = PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12];
+        const float hy = PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13];
+        const float hw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
+        const float pw = 1.f / (hw + 0.0000001f);
+        px = ((hx * pw + 1.f) * W - 1.f) * 0.5f;
+        py = ((hy * pw + 1.f) * H - 1.f) * 0.5f;
+      } else {
+        ex = (int)ceilf(3.f * sqrtf(g.a));
+        ey = (int)ceilf(3.f * sqrtf(g.c));
+        if (ex > W / 2) ex = W / 2;
+        const float su = -(float)W / (2.f * PI_F), sv = -(float)H / PI_F;
+        px = su * atan2f(g.t[0], g.t[2]) + 0.5f * W - 0.5f;
+        py = sv * atan2f(g.t[1], sqrtf(g.t[0] * g.t[0] + g.t[2] * g.t[2])) + 0.5f * H - 0.5f;
+      }
+      // upstream tile rectangle
+      int ymin = (int)((py - ey) / TILE), ymax = (int)((py + ey + TILE - 1) / TILE);
+      ymin = min(gy, max(0, ymin)); ymax = min(gy, max(0, ymax));
+      int xmin, xmax;
+      if (MODE == S360_MODE_PINHOLE) {
+        xmin = (int)((px - ex) / TILE); xmax = (int)((px + ex + TILE - 1) / TILE);
+        xmin = min(gx, max(0, xmin)); xmax = min(gx, max(0, xmax));
+      } else {
+        // unwrapped column range; capped to one full row only after the tight-box intersection
+        xmin = (int)floorf((px - ex) / TILE); xmax = (int)floorf((px + ex + TILE - 1) / TILE);
+      }
+      upstream_visible = (xmax - xmin) * (ymax - ymin) > 0;
+      if (upstream_visible) {
+        radius = max(ex, ey);
+        const float op = opac[idx];
+        // box outside which alpha = op * exp(power) < 1/255 for certain
+        float hx = __int_as_float(0x7f800000), hy = hx;
+        if (v.tight_bbox) {
+          const float tau = logf(255.f * op);
+          if (tau > 0.f) {
+            hx = sqrtf(2.f * tau * g.a) * 1.0005f + 1e-3f;
+            hy = sqrtf(2.f * tau * g.c) * 1.0005f + 1e-3f;
+            const int ty0 = (int)floorf((py - hy) / TILE), ty1 = (int)floorf((py + hy) / TILE) + 1;
+            const int tx0 = (int)floorf((px - hx) / TILE), tx1 = (int)floorf((px + hx) / TILE) + 1;
+            ymin = max(ymin, ty0); ymax = min(ymax, ty1);
+            xmin = max(xmin, tx0); xmax = min(xmax, tx1);
+          } else if (tau <= 0.f) {   // opacity < 1/255: can never pass the alpha test (NaN falls through)
+            xmax = xmin; ymax = ymin;
+          }
+        }
+        int nx = max(0, xmax - xmin);
+        const int ny = max(0, ymax - ymin);
+        if (MODE == S360_MODE_ERP) nx = min(nx, gx);
+        if (nx * ny > 0) {
+          rect = make_uint2(((uint32_t)xmin & 0xffffu) | ((uint32_t)nx << 16), (uint32_t)ymin | ((uint32_t)ny << 16));
+          key = __float_as_uint(sortkey);
+        }
+        // colour
+        float col[3];
+        uint8_t cl = (g.clampx ? 8 : 0) | (g.clampy ? 16 : 0);
+        if (shs != nullptr) {
+          float dx = mx - cam.cam[0], dy = my - cam.cam[1], dz = mz - cam.cam[2];
+          const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+          dx *= inv; dy *= inv; dz *= inv;
+          float b[25];
+          const int deg = min(v.sh_degree, v.max_sh_degree);
+          const int n = sh_basis(deg, dx, dy, dz, b);
+          const float* sh = shs + (size_t)idx * v.M * 3;
+          float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 25; k++) {
+            if (k < n) {
+              acc[0] += b[k] * sh[3 * k];
+              acc[1] += b[k] * sh[3 * k + 1];
+              acc[2] += b[k] * sh[3 * k + 2];
+            }
+          }
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            const float r = acc[ch] + 0.5f;
+            if (r < 0.f) cl |= (1 << ch);
+            col[ch] = fmaxf(r, 0.f);
+          }
+        } else {
+          col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
+        }
+        gs.rec[3 * (size_t)idx + 0] = make_float4(px, py, cA, cB);
+        gs.rec[3 * (size_t)idx + 1] = make_float4(cC, op, hx, hy);
+        gs.rec[3 * (size_t)idx + 2] = make_float4(col[0], col[1], col[2], sortkey);
+        gs.clamped[idx] = cl;
+      }
+    }
+    radii[idx] = radius;
+    gs.rect[idx] = rect;
+    depth_keys[idx] = key;
+    ids[idx] = (uint32_t)idx;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, upstream_visible);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters->num_visible, (uint32_t)__popc(m));
+}
+
+int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
+                      const float* shs, const float* colors, GeomState g, int32_t* radii,
+                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st) {
+  if (v.P == 0) return 0;
+  const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
+  if (v.mode == S360_MODE_PINHOLE)
+    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+  else
+    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 + K9 fused.  acc[idx*12 + 0..8] = {dL/dr, dL/dg, dL/db, dL/du, dL/dv (pixel units),
+// dL/dconicA, dL/dconicB (true off-diagonal gradient), dL/dconicC, dL/dopacity}
+template <int MODE>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_backward_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
+                           const float* __restrict__ shs, GeomState gs, const int32_t* __restrict__ radii,
+                           const float* __restrict__ acc, float* __restrict__ d_means,
+                           float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
+                           float* __restrict__ d_shs, float* __restrict__ d_colors) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= v.P) return;
+  const int W = v.image_width, H = v.image_height;
+  float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dop = 0.f, dcol[3] = {0.f, 0.f, 0.f};
+  const bool vis = radii[idx] > 0;
+  if (vis) {
+    Cam cam;
+    load_cam(v, cam, MODE == S360_MODE_PINHOLE);
+    const float* V = cam.V;
+    const float4 a0 = *reinterpret_cast<const float4*>(acc + (size_t)idx * ACC_STRIDE);
+    const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)idx * ACC_STRIDE + 4);
+    const float a2 = acc[(size_t)idx * ACC_STRIDE + 8];
+    dcol[0] = a0.x; dcol[1] = a0.y; dcol[2] = a0.z;
+    const float gu = a0.w, gv = a1.x, gA = a1.y, gB = a1.z, gC = a1.w;
+    dop = a2;
+    dm2[0] = gu * 0.5f * W; dm2[1] = gv * 0.5f * H;
+    const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
+    float cv[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cv[k] = cov3D[6 * idx + k];
+    Geo g;
+    geo_compute<MODE>(v, V, mx, my, mz, cv, g);
+    const float denom = g.a * g.c - g.b * g.b;
+    const float inv2 = 1.f / (denom * denom + 0.0000001f);
+    const float da = inv2 * (-g.c * g.c * gA + g.b * g.c * gB + (denom - g.a * g.c) * gC);
+    const float dc = inv2 * (-g.a * g.a * gC + g.a * g.b * gB + (denom - g.a * g.c) * gA);
+    const float db = inv2 * (2.f * g.b * g.c * gA - (denom + 2.f * g.b * g.b) * gB + 2.f * g.a * g.b * gC);
+    const float(*Mm)[3] = g.Mm;
+    dcov[0] = Mm[0][0] * Mm[0][0] * da + Mm[0][0] * Mm[1][0] * db + Mm[1][0] * Mm[1][0] * dc;
+    dcov[3] = Mm[0][1] * Mm[0][1] * da + Mm[0][1] * Mm[1][1] * db + Mm[1][1] * Mm[1][1] * dc;
+    dcov[5] = Mm[0][2] * Mm[0][2] * da + Mm[0][2] * Mm[1][2] * db + Mm[1][2] * Mm[1][2] * dc;
+    dcov[1] = 2.f * Mm[0][0] * Mm[0][1] * da + (Mm[0][0] * Mm[1][1] + Mm[0][1] * Mm[1][0]) * db + 2.f * Mm[1][0] * Mm[1][1] * dc;
+    dcov[2] = 2.f * Mm[0][0] * Mm[0][2] * da + (Mm[0][0] * Mm[1][2] + Mm[0][2] * Mm[1][0]) * db + 2.f * Mm[1][0] * Mm[1][2] * dc;
+    dcov[4] = 2.f * Mm[0][2] * Mm[0][1] * da + (Mm[0][1] * Mm[1][2] + Mm[0][2] * Mm[1][1]) * db + 2.f * Mm[1][1] * Mm[1][2] * dc;
+    const float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
+    float dM[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float Sm0 = S[k][0] * Mm[0][0] + S[k][1] * Mm[0][1] + S[k][2] * Mm[0][2];
+      const float Sm1 = S[k][0] * Mm[1][0] + S[k][1] * Mm[1][1] + S[k][2] * Mm[1][2];
+      dM[0][k] = 2.f * da * Sm0 + db * Sm1;
+      dM[1][k] = 2.f * dc * Sm1 + db * Sm0;
+    }
+    // dJ[r][k] = sum_j R[k][j] dM[r][j],  R[k][j] = V[4j + k]
+    float dJ[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) dJ[r][k] = V[k] * dM[r][0] + V[4 + k] * dM[r][1] + V[8 + k] * dM[r][2];
+    float dt[3] = {0.f, 0.f, 0.f};
+    if (MODE == S360_MODE_PINHOLE) {
+      const float fx = (float)W / (2.f * v.tanfovx), fy = (float)H / (2.f * v.tanfovy);
+      const float tz = 1.f / g.tc[2], tz2 = tz * tz, tz3 = tz2 * tz;
+      const float xm = g.clampx ? 0.f : 1.f, ym = g.clampy ? 0.f : 1.f;
+      dt[0] = xm * -fx * tz2 * dJ[0][2];
+      dt[1] = ym * -fy * tz2 * dJ[1][2];
+      dt[2] = -fx * tz2 * dJ[0][0] - fy * tz2 * dJ[1][1] + (2.f * fx * g.tc[0]) * tz3 * dJ[0][2] +
+              (2.f * fy * g.tc[1]) * tz3 * dJ[1][2];
+      const float* PM = cam.PM;
+      const float hw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
+      const float mw = 1.f / (hw + 0.0000001f);
+      const float mul1 = (PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12]) * mw * mw;
+      const float mul2 = (PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13]) * mw * mw;
+      dm[0] = (PM[0] * mw - PM[3] * mul1) * dm2[0] + (PM[1] * mw - PM[3] * mul2) * dm2[1];
+      dm[1] = (PM[4] * mw - PM[7] * mul1) * dm2[0] + (PM[5] * mw - PM[7] * mul2) * dm2[1];
+      dm[2] = (PM[8] * mw - PM[11] * mul1) * dm2[0] + (PM[9] * mw - PM[11] * mul2) * dm2[1];
+    } else {
+      const float su = -(float)W / (2.f * PI_F), sv = -(float)H / PI_F;
+      const float x = g.tc[0], y = g.tc[1], z = g.tc[2];
+      if (!g.clampx) {
+        const float q = x * x + z * z, rho = sqrtf(q), r2 = q + y * y, q2 = q * q;
+        const float f = 1.f / (rho * r2);
+        const float dfx = -x * (r2 + 2.f * q) / (rho * q * r2 * r2);
+        const float dfz = -z * (r2 + 2.f * q) / (rho * q * r2 * r2);
+        const float dfy = -2.f * y / (rho * r2 * r2);
+        const float dJ00x = -2.f * su * x * z / q2, dJ00z = su * (x * x - z * z) / q2;
+        const float dJ02x = su * (x * x - z * z) / q2, dJ02z = 2.f * su * x * z / q2;
+        const float dJ10x = -sv * y * (f + x * dfx), dJ10y = -sv * x * (f + y * dfy), dJ10z = -sv * x * y * dfz;
+        const float dJ12x = -sv * z * y * dfx, dJ12y = -sv * z * (f + y * dfy), dJ12z = -sv * y * (f + z * dfz);
+        const float dJ11x = sv * x * (r2 - 2.f * q) / (rho * r2 * r2), dJ11z = sv * z * (r2 - 2.f * q) / (rho * r2 * r2);
+        const float dJ11y = -2.f * sv * rho * y / (r2 * r2);
+        dt[0] = dJ[0][0] * dJ00x + dJ[0][2] * dJ02x + dJ[1][0] * dJ10x + dJ[1][1] * dJ11x + dJ[1][2] * dJ12x;
+        dt[1] = dJ[1][0] * dJ10y + dJ[1][1] * dJ11y + dJ[1][2] * dJ12y;
+        dt[2] = dJ[0][0] * dJ00z + dJ[0][2] * dJ02z + dJ[1][0] * dJ10z + dJ[1][1] * dJ11z + dJ[1][2] * dJ12z;
+      }
+      dt[0] += g.J[0][0] * gu + g.J[1][0] * gv;
+      dt[1] += g.J[0][1] * gu + g.J[1][1] * gv;
+      dt[2] += g.J[0][2] * gu + g.J[1][2] * gv;
+    }
+    // mean3D <- view-space gradient: dm_k += sum_i R[i][k] dt_i,  R[i][k] = V[4k + i]
+#pragma unroll
+    for (int k = 0; k < 3; k++) dm[k] += V[4 * k] * dt[0] + V[4 * k + 1] * dt[1] + V[4 * k + 2] * dt[2];
+    if (shs != nullptr) {
+      const float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
+      const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
+      const float dx = ox * inv, dy = oy * inv, dz = oz * inv;
+      const int deg = min(v.sh_degree, v.max_sh_degree);
+      float b[25], bx[25], by[25], bz[25];
+      const int n = sh_basis(deg, dx, dy, dz, b);
+      sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
+      const uint8_t cl = gs.clamped[idx];
+      const float drgb[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
+      const float* sh = shs + (size_t)idx * v.M * 3;
+      float* dsh = d_shs + (size_t)idx * v.M * 3;
+      float ddir[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 25; k++) {
+        if (k < n) {
+          const float s = sh[3 * k] * drgb[0] + sh[3 * k + 1] * drgb[1] + sh[3 * k + 2] * drgb[2];
+          ddir[0] += bx[k] * s; ddir[1] += by[k] * s; ddir[2] += bz[k] * s;
+          dsh[3 * k] = b[k] * drgb[0]; dsh[3 * k + 1] = b[k] * drgb[1]; dsh[3 * k + 2] = b[k] * drgb[2];
+        }
+      }
+      for (int k = n; k < v.M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+      const float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
+      dm[0] += (ddir[0] - dx * dot) * inv;
+      dm[1] += (ddir[1] - dy * dot) * inv;
+      dm[2] += (ddir[2] - dz * dot) * inv;
+    }
+  } else if (shs != nullptr) {
+    float* dsh = d_shs + (size_t)idx * v.M * 3;
+    for (int k = 0; k < v.M * 3; k++) dsh[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) d_means[3 * idx + k] = dm[k];
+  d_means2D[3 * idx] = dm2[0]; d_means2D[3 * idx + 1] = dm2[1]; d_means2D[3 * idx + 2] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; k++) d_cov[6 * idx + k] = dcov[k];
+  d_opac[idx] = dop;
+  if (d_colors != nullptr) {
+    const bool pre = shs == nullptr;
+#pragma unroll
+    for (int k = 0; k < 3; k++) d_colors[3 * idx + k] = pre ? dcol[k] : 0.f;
+  }
+}
+
+int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* shs,
+                               GeomState g, const int32_t* radii, const float* acc, float* d_means,
+                               float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
+                               cudaStream_t st) {
+  if (v.P == 0) return 0;
+  const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
+  if (v.mode == S360_MODE_PINHOLE)
+    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+  else
+    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void mark_visible_kernel(const S360View v, const float* __restrict__ means, uint8_t* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= v.P) return;
+  const float* V = v.viewmatrix;
+  const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
+  const float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+  const float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+  const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+  const float d = v.mode == S360_MODE_PINHOLE ? tz : sqrtf(tx * tx + ty * ty + tz * tz);
+  present[idx] = d > v.near_cull ? 1 : 0;
+}
+
+int launch_mark_visible(const S360View& v, const float* means, uint8_t* present, cudaStream_t st) {
+  if (v.P == 0) return 0;
+  mark_visible_kernel<<<(v.P + 255) / 256, 256, 0, st>>>(v, means, present);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace s360

@@ -1,0 +1,280 @@
+"""Decoder-level entry points: same names, arguments and tensor conventions as the reference's
+``src/model/decoder/cuda_splatting.py`` and ``decoder_splatting_cuda.py``.
+
+* ``render_cuda``               <- /root/reference/src/model/decoder/cuda_splatting.py:47-127
+* ``render_cuda_orthographic``  <- cuda_splatting.py:130-220
+* ``render_depth_cuda``         <- cuda_splatting.py:226-269
+* ``DecoderSplattingCUDA``      <- /root/reference/src/model/decoder/decoder_splatting_cuda.py:19-97
+* ``render_erp`` / ``render_depth_erp`` / ``DecoderSplattingERP`` -- the native equirectangular path
+  (one rasterization per panorama instead of six cube faces + Cube2Equirec,
+  /root/reference/src/model/model_wrapper_erp.py:336-345, 395-398).
+
+The reference's per-call layout copies are folded away where the kernels can read the reference
+layout directly; results are identical.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import isqrt
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from .camera import erp_camera, get_fov, get_projection_matrix
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+
+DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
+
+
+def depth_to_relative_disparity(depth: Tensor, near: Tensor, far: Tensor, eps: float = 1e-10) -> Tensor:
+    """/root/reference/src/model/encoder/costvolume/conversions.py:17-27."""
+    disp_near = 1 / (near + eps)
+    disp_far = 1 / (far + eps)
+    disp = 1 / (depth + eps)
+    return 1 - (disp - disp_far) / (disp_near - disp_far + eps)
+
+
+def _triu6(cov: Tensor) -> Tensor:
+    row, col = torch.triu_indices(3, 3)
+    return cov[..., row, col]
+
+
+def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fov_y, image_shape, background_color,
+                     gaussian_means, gaussian_covariances, shs, gaussian_opacities, degree, use_sh, projection):
+    b = extrinsics.shape[0]
+    h, w = image_shape
+    images = []
+    for i in range(b):
+        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
+        try:
+            mean_gradients.retain_grad()
+        except Exception:
+            pass
+        settings = GaussianRasterizationSettings(
+            image_height=h, image_width=w,
+            tanfovx=float(tan_fov_x[i]), tanfovy=float(tan_fov_y[i]),
+            bg=background_color[i], scale_modifier=1.0,
+            viewmatrix=view_matrix[i], projmatrix=full_projection[i],
+            sh_degree=degree, campos=extrinsics[i, :3, 3],
+            prefiltered=False, debug=False, projection=projection)
+        image, _radii = GaussianRasterizer(settings)(
+            means3D=gaussian_means[i], means2D=mean_gradients,
+            shs=shs[i] if use_sh else None,
+            colors_precomp=None if use_sh else shs[i, :, 0, :],
+            opacities=gaussian_opacities[i, ..., None],
+            cov3D_precomp=_triu6(gaussian_covariances[i]))
+        images.append(image)
+    return torch.stack(images)
+
+
+def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
+                use_sh: bool = True) -> Tensor:
+    """Pinhole render of a batch: [b,3,h,w].  Argument meaning identical to the reference."""
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    if scale_invariant:
+        scale = 1 / near
+        extrinsics = extrinsics.clone()
+        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[:, None]
+        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
+        gaussian_means = gaussian_means * scale[:, None, None]
+        near = near * scale
+        far = far * scale
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    shs = gaussian_sh_coefficients.transpose(-1, -2).contiguous()  # b g xyz n -> b g n xyz
+    fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
+    tan_fov_x = (0.5 * fov_x).tan().tolist()
+    tan_fov_y = (0.5 * fov_y).tan().tolist()
+    projection_matrix = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
+    view_matrix = extrinsics.inverse().transpose(1, 2)
+    full_projection = view_matrix @ projection_matrix
+    return _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fov_y, image_shape,
+                            background_color, gaussian_means, gaussian_covariances, shs, gaussian_opacities,
+                            degree, use_sh, "pinhole")
+
+
+def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,
+                             image_shape: tuple[int, int], background_color: Tensor, gaussian_means: Tensor,
+                             gaussian_covariances: Tensor, gaussian_sh_coefficients: Tensor,
+                             gaussian_opacities: Tensor, fov_degrees: float = 0.1, use_sh: bool = True,
+                             dump: Optional[dict] = None) -> Tensor:
+    """Fake-orthographic render (tiny FOV, camera moved back), cuda_splatting.py:130-220."""
+    b = extrinsics.shape[0]
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    shs = gaussian_sh_coefficients.transpose(-1, -2).contiguous()
+    fov_x = torch.tensor(fov_degrees, device=extrinsics.device).deg2rad()
+    tan_fov_x = (0.5 * fov_x).tan()
+    distance_to_near = (0.5 * width) / tan_fov_x
+    tan_fov_y = 0.5 * height / distance_to_near
+    fov_y = (2 * tan_fov_y).atan()
+    near = near + distance_to_near
+    far = far + distance_to_near
+    move_back = torch.eye(4, dtype=torch.float32, device=extrinsics.device)
+    move_back = move_back.repeat(b, 1, 1)
+    move_back[:, 2, 3] = -distance_to_near
+    extrinsics = extrinsics @ move_back
+    if dump is not None:
+        dump.update(extrinsics=extrinsics, fov_x=fov_x, fov_y=fov_y, near=near, far=far)
+    projection_matrix = get_projection_matrix(near, far, fov_x.expand(b), fov_y).transpose(1, 2)
+    view_matrix = extrinsics.inverse().transpose(1, 2)
+    full_projection = view_matrix @ projection_matrix
+    return _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x.expand(b).tolist(),
+                            tan_fov_y.expand(b).tolist(), image_shape, background_color, gaussian_means,
+                            gaussian_covariances, shs, gaussian_opacities, degree, use_sh, "pinhole")
+
+
+def _depth_colors(fake_color: Tensor, near: Tensor, far: Tensor, mode: DepthRenderingMode) -> Tensor:
+    if mode == "disparity":
+        fake_color = 1 / fake_color
+    elif mode == "relative_disparity":
+        fake_color = depth_to_relative_disparity(fake_color, near[:, None], far[:, None])
+    elif mode == "log":
+        fake_color = fake_color.minimum(near[:, None]).maximum(far[:, None]).log()
+    return fake_color
+
+
+def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                      image_shape: tuple[int, int], gaussian_means: Tensor, gaussian_covariances: Tensor,
+                      gaussian_opacities: Tensor, scale_invariant: bool = True,
+                      mode: DepthRenderingMode = "depth") -> Tensor:
+    """Depth-as-colour render [b,h,w] (cuda_splatting.py:226-269)."""
+    w2c = extrinsics.inverse()
+    cam = torch.einsum("bij,bgj->bgi", w2c[:, :3, :3], gaussian_means) + w2c[:, None, :3, 3]
+    fake_color = _depth_colors(cam[..., 2], near, far, mode)
+    b = fake_color.shape[0]
+    result = render_cuda(extrinsics, intrinsics, near, far, image_shape,
+                         torch.zeros((b, 3), dtype=fake_color.dtype, device=fake_color.device),
+                         gaussian_means, gaussian_covariances,
+                         fake_color[:, :, None, None].expand(-1, -1, 3, 1), gaussian_opacities,
+                         scale_invariant=scale_invariant, use_sh=False)
+    return result.mean(dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# native equirectangular path
+def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+               background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+               gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
+               use_sh: bool = True) -> Tensor:
+    """One equirectangular render per batch item: [b,3,h,w].
+
+    ``extrinsics_sphere`` is the panorama camera-to-world in the reference's sphere-camera frame
+    (/root/reference/src/dataset/dataset_hm3d.py:282,298; utils360.py hm3d branch).  ``near`` plays the
+    role it has in ``render_cuda``: with ``scale_invariant`` the scene is rescaled by 1/near so that the
+    near-cull distance is 0.2*near.  ``far`` is accepted for signature symmetry and unused."""
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    if scale_invariant:
+        scale = 1 / near
+        extrinsics_sphere = extrinsics_sphere.clone()
+        extrinsics_sphere[..., :3, 3] = extrinsics_sphere[..., :3, 3] * scale[:, None]
+        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
+        gaussian_means = gaussian_means * scale[:, None, None]
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    shs = gaussian_sh_coefficients.transpose(-1, -2).contiguous()
+    cam = erp_camera(extrinsics_sphere)
+    b = extrinsics_sphere.shape[0]
+    ones = [1.0] * b
+    return _rasterize_batch(extrinsics_sphere, cam.view_matrix, cam.full_projection, ones, ones, image_shape,
+                            background_color, gaussian_means, gaussian_covariances, shs, gaussian_opacities,
+                            degree, use_sh, "erp")
+
+
+def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                     gaussian_means: Tensor, gaussian_covariances: Tensor, gaussian_opacities: Tensor,
+                     scale_invariant: bool = True, mode: DepthRenderingMode = "depth") -> Tensor:
+    """Radial-distance-as-colour equirectangular render [b,h,w] -- the quantity the reference converts its
+    cube-face z-depth to before stitching (/root/reference/src/model/model_wrapper_erp.py:447-457)."""
+    w2c = extrinsics_sphere.inverse()
+    cam = torch.einsum("bij,bgj->bgi", w2c[:, :3, :3], gaussian_means) + w2c[:, None, :3, 3]
+    fake_color = _depth_colors(cam.norm(dim=-1), near, far, mode)
+    b = fake_color.shape[0]
+    result = render_erp(extrinsics_sphere, near, far, image_shape,
+                        torch.zeros((b, 3), dtype=fake_color.dtype, device=fake_color.device),
+                        gaussian_means, gaussian_covariances,
+                        fake_color[:, :, None, None].expand(-1, -1, 3, 1), gaussian_opacities,
+                        scale_invariant=scale_invariant, use_sh=False)
+    return result.mean(dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Gaussians:
+    """/root/reference/src/model/types.py:7-12."""
+    means: Tensor        # [b,g,3]
+    covariances: Tensor  # [b,g,3,3]
+    harmonics: Tensor    # [b,g,3,d_sh]
+    opacities: Tensor    # [b,g]
+
+
+@dataclass
+class DecoderOutput:
+    """/root/reference/src/model/decoder/decoder.py:19-22."""
+    color: Tensor            # [b,v,3,h,w]
+    depth: Optional[Tensor]  # [b,v,h,w]
+
+
+class DecoderSplattingCUDA(nn.Module):
+    """Same forward contract as the reference decoder (decoder_splatting_cuda.py:34-97); constructed from a
+    background colour instead of the Hydra dataset config."""
+
+    def __init__(self, background_color=(0.0, 0.0, 0.0)) -> None:
+        super().__init__()
+        self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
+
+    def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
+        b, v, _, _ = extrinsics.shape
+        colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
+        bg = self.background_color[None].expand(b, 3)
+        for view_idx in range(v):
+            colors[:, view_idx] = render_cuda(
+                extrinsics[:, view_idx], intrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
+                bg, gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities)
+        depth = None if depth_mode is None else self.render_depth(gaussians, extrinsics, intrinsics, near, far,
+                                                                  image_shape, depth_mode)
+        return DecoderOutput(colors, depth)
+
+    def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
+                     image_shape: tuple[int, int], mode: DepthRenderingMode = "depth") -> Tensor:
+        b, v, _, _ = extrinsics.shape
+        depths = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device)
+        for view_idx in range(v):
+            depths[:, view_idx] = render_depth_cuda(
+                extrinsics[:, view_idx], intrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
+                gaussians.means, gaussians.covariances, gaussians.opacities, mode=mode)
+        return depths
+
+
+class DecoderSplattingERP(nn.Module):
+    """Native-panorama decoder: ``extrinsics`` are sphere-camera poses [b,v,4,4]; no intrinsics needed
+    (kept in the signature, ignored) so it can be swapped for ``DecoderSplattingCUDA`` at the call sites
+    /root/reference/src/model/model_wrapper_erp.py:221-229, 336-345."""
+
+    def __init__(self, background_color=(0.0, 0.0, 0.0)) -> None:
+        super().__init__()
+        self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
+
+    def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Optional[Tensor], near: Tensor,
+                far: Tensor, image_shape: tuple[int, int],
+                depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
+        b, v, _, _ = extrinsics.shape
+        colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
+        bg = self.background_color[None].expand(b, 3)
+        for view_idx in range(v):
+            colors[:, view_idx] = render_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
+                                             bg, gaussians.means, gaussians.covariances, gaussians.harmonics,
+                                             gaussians.opacities)
+        depth = None
+        if depth_mode is not None:
+            depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device)
+            for view_idx in range(v):
+                depth[:, view_idx] = render_depth_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx],
+                                                      image_shape, gaussians.means, gaussians.covariances,
+                                                      gaussians.opacities, mode=depth_mode)
+        return DecoderOutput(colors, depth)

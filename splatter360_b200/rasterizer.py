@@ -1,0 +1,270 @@
+"""Python surface of the rasterizer -- same names, arguments and error behaviour as the
+``diff_gaussian_rasterization`` package the reference imports
+(/root/reference/src/model/decoder/cuda_splatting.py:5-8) and calls
+(/root/reference/src/model/decoder/cuda_splatting.py:99-126, 178-219):
+
+    GaussianRasterizationSettings(image_height, image_width, tanfovx, tanfovy, bg, scale_modifier,
+                                  viewmatrix, projmatrix, sh_degree, campos, prefiltered, debug)
+    GaussianRasterizer(raster_settings)(means3D, means2D, opacities, shs=None, colors_precomp=None,
+                                        scales=None, rotations=None, cov3D_precomp=None) -> (color, radii)
+
+Everything numeric runs in libsplatter360.so (hand-written sm_100a CUDA, C-ABI in
+include/splatter360.h) on the caller's current CUDA stream.  There is no CPU path: CPU tensors or a
+missing library raise.
+
+Extensions over upstream are optional trailing settings fields with defaults, so reference code that
+constructs the settings by keyword keeps working unchanged:
+``projection`` ("pinhole" | "erp"), ``near_cull``, ``fov_clamp``, ``lowpass``, ``pole_eps``,
+``max_sh_degree``, ``tight_bbox``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import NamedTuple, Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: Tensor
+    scale_modifier: float
+    viewmatrix: Tensor
+    projmatrix: Tensor
+    sh_degree: int
+    campos: Tensor
+    prefiltered: bool
+    debug: bool
+    # ---- extensions (defaults reproduce upstream behaviour) ----
+    projection: str = "pinhole"   # "pinhole" (upstream) or "erp" (native equirectangular)
+    near_cull: float = 0.2
+    fov_clamp: float = 1.3
+    lowpass: float = 0.3
+    pole_eps: float = 1e-3
+    max_sh_degree: int = 4
+    tight_bbox: bool = True
+
+
+_MODES = {"pinhole": _lib.MODE_PINHOLE, "erp": _lib.MODE_ERP}
+
+
+def _f32c(t: Tensor, device) -> Tensor:
+    if t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None or t.numel() == 0 else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _make_view(s: GaussianRasterizationSettings, P: int, M: int, device):
+    """Build the host S360View plus the device tensors it points at (returned to keep them alive)."""
+    if s.projection not in _MODES:
+        raise ValueError(f"unknown projection {s.projection!r} (expected 'pinhole' or 'erp')")
+    if s.projection == "erp" and int(s.image_width) % 16 != 0:
+        raise ValueError("erp projection needs image_width to be a multiple of 16 (seam wrap at tile granularity)")
+    vm = _f32c(torch.as_tensor(s.viewmatrix), device)
+    pm = _f32c(torch.as_tensor(s.projmatrix), device)
+    cp = _f32c(torch.as_tensor(s.campos), device)
+    bg = _f32c(torch.as_tensor(s.bg), device)
+    if vm.numel() != 16 or pm.numel() != 16 or cp.numel() != 3 or bg.numel() != 3:
+        raise ValueError("viewmatrix/projmatrix must have 16 elements, campos/bg 3")
+    v = _lib.S360View()
+    v.P, v.M, v.sh_degree = int(P), int(M), int(s.sh_degree)
+    v.image_height, v.image_width = int(s.image_height), int(s.image_width)
+    v.mode = _MODES[s.projection]
+    v.max_sh_degree = int(s.max_sh_degree)
+    v.tight_bbox = int(bool(s.tight_bbox))
+    v.tanfovx, v.tanfovy = float(s.tanfovx), float(s.tanfovy)
+    v.near_cull, v.fov_clamp = float(s.near_cull), float(s.fov_clamp)
+    v.lowpass, v.pole_eps = float(s.lowpass), float(s.pole_eps)
+    v.viewmatrix, v.projmatrix = vm.data_ptr(), pm.data_ptr()
+    v.campos, v.bg = cp.data_ptr(), bg.data_ptr()
+    return v, (vm, pm, cp, bg)
+
+
+def build_covariance_6(scales: Tensor, rotations: Tensor, scale_modifier: float = 1.0) -> Tensor:
+    """cov3D[P,6] = R S S^T R^T from scales [P,3] and (r,x,y,z) quaternions [P,4] (upstream computeCov3D,
+    SURVEY.md sec. 2b).  Differentiable torch ops; the kernels always consume the 6-vector."""
+    s = scales * scale_modifier
+    r, x, y, z = rotations.unbind(-1)
+    R = torch.stack([
+        1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+    Mx = R * s[:, None, :]
+    cov = Mx @ Mx.transpose(1, 2)
+    return torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], -1)
+
+
+class ForwardState(NamedTuple):
+    """Buffers kept from forward to backward (all caller-owned torch tensors)."""
+    geom: Tensor
+    radii: Tensor
+    point_list: Tensor
+    image_state: Tensor
+    num_rendered: int
+    num_visible: int
+
+
+def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
+                shs: Optional[Tensor], colors: Optional[Tensor]):
+    """Run the two forward stages through the C-ABI.  Returns (color[3,H,W], ForwardState)."""
+    lib = _lib.load()
+    device = means3D.device
+    if device.type != "cuda":
+        raise RuntimeError("splatter360_b200 rasterizer needs CUDA tensors (there is no CPU path)")
+    P = means3D.shape[0]
+    M = shs.shape[1] if shs is not None else 0
+    H, W = int(settings.image_height), int(settings.image_width)
+    with torch.cuda.device(device):
+        view, keep = _make_view(settings, P, M, device)
+        u8 = dict(dtype=torch.uint8, device=device)
+        geom = torch.empty(lib.s360_geom_bytes(P), **u8)
+        pre_scratch = torch.empty(lib.s360_preprocess_scratch_bytes(P), **u8)
+        radii = torch.empty(P, dtype=torch.int32, device=device)
+        depth_order = torch.empty(max(P, 1), dtype=torch.int32, device=device)
+        offsets = torch.empty(max(P, 1), dtype=torch.int32, device=device)
+        counters = torch.empty(4, dtype=torch.int32, device=device)
+        st = _stream_ptr()
+        _lib.check(lib.s360_forward_preprocess(
+            ctypes.byref(view), _ptr(means3D), _ptr(cov6), _ptr(opacities), _ptr(shs), _ptr(colors),
+            _ptr(geom), _ptr(radii), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
+        # the instance count is data dependent: one 16-byte read sizes the instance buffers exactly
+        cnt = counters.cpu()
+        N, nvis = int(cnt[0].item()) & 0xFFFFFFFF, int(cnt[2].item()) & 0xFFFFFFFF
+        cap = max(N, 1)
+        point_list = torch.empty(cap, dtype=torch.int32, device=device)
+        bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(cap, H, W), **u8)
+        image_state = torch.empty(lib.s360_image_bytes(H, W), **u8)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        _lib.check(lib.s360_forward_render(
+            ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters),
+            ctypes.c_int64(N), _ptr(point_list), _ptr(image_state), _ptr(color), _ptr(bin_scratch), st))
+        if settings.debug:
+            torch.cuda.synchronize(device)
+    del keep
+    return color, ForwardState(geom, radii, point_list, image_state, N, nvis)
+
+
+def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
+                 shs: Optional[Tensor], colors: Optional[Tensor], state: ForwardState, grad_color: Tensor):
+    """Run the backward pass through the C-ABI.  Returns a dict of gradient tensors."""
+    lib = _lib.load()
+    device = means3D.device
+    P = means3D.shape[0]
+    M = shs.shape[1] if shs is not None else 0
+    with torch.cuda.device(device):
+        view, keep = _make_view(settings, P, M, device)
+        f32 = dict(dtype=torch.float32, device=device)
+        g_means = torch.empty((P, 3), **f32)
+        g_means2D = torch.empty((P, 3), **f32)
+        g_cov = torch.empty((P, 6), **f32)
+        g_op = torch.empty((P, 1), **f32)
+        g_sh = torch.empty((P, M, 3), **f32) if shs is not None else None
+        g_col = torch.empty((P, 3), **f32) if colors is not None else None
+        scratch = torch.empty(lib.s360_backward_scratch_bytes(P), dtype=torch.uint8, device=device)
+        grad_color = _f32c(grad_color, device)
+        _lib.check(lib.s360_backward(
+            ctypes.byref(view), _ptr(means3D), _ptr(cov6), _ptr(opacities), _ptr(shs), _ptr(colors),
+            _ptr(state.geom), _ptr(state.radii), _ptr(state.point_list), _ptr(state.image_state),
+            _ptr(grad_color), _ptr(g_means), _ptr(g_means2D), _ptr(g_cov), _ptr(g_op), _ptr(g_sh), _ptr(g_col),
+            _ptr(scratch), _stream_ptr()))
+        if settings.debug:
+            torch.cuda.synchronize(device)
+    del keep
+    return dict(means3D=g_means, means2D=g_means2D, cov3D=g_cov, opacities=g_op, shs=g_sh, colors=g_col)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """Same forward/backward signature as upstream's autograd.Function."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        device = means3D.device
+        means3D_c = _f32c(means3D, device)
+        cov6 = _f32c(cov3Ds_precomp, device)
+        op = _f32c(opacities, device).reshape(-1)
+        shs_c = _f32c(sh, device) if sh.numel() else None
+        col_c = _f32c(colors_precomp, device) if colors_precomp.numel() else None
+        P = means3D_c.shape[0]
+        if cov6.shape != (P, 6) or op.shape[0] != P:
+            raise ValueError("cov3D_precomp must be [P,6] and opacities [P,1]")
+        if shs_c is not None and (shs_c.dim() != 3 or shs_c.shape[0] != P or shs_c.shape[2] != 3):
+            raise ValueError("shs must be [P,M,3]")
+        if col_c is not None and col_c.shape != (P, 3):
+            raise ValueError("colors_precomp must be [P,3]")
+        color, state = forward_raw(raster_settings, means3D_c, cov6, op, shs_c, col_c)
+        ctx.raster_settings = raster_settings
+        ctx.state = state
+        ctx.has_sh = shs_c is not None
+        ctx.save_for_backward(means3D_c, cov6, op, shs_c if shs_c is not None else col_c)
+        ctx.mark_non_differentiable(state.radii)
+        return color, state.radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        means3D, cov6, op, feat = ctx.saved_tensors
+        shs = feat if ctx.has_sh else None
+        col = None if ctx.has_sh else feat
+        g = backward_raw(ctx.raster_settings, means3D, cov6, op, shs, col, ctx.state, grad_out_color)
+        return (g["means3D"], g["means2D"], g["shs"], g["colors"], g["opacities"], None, None, g["cov3D"], None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: Tensor) -> Tensor:
+        """Boolean mask of Gaussians in front of the near-cull distance (upstream ``mark_visible``)."""
+        lib = _lib.load()
+        s = self.raster_settings
+        with torch.no_grad():
+            pos = _f32c(positions, positions.device)
+            if pos.device.type != "cuda":
+                raise RuntimeError("markVisible needs CUDA tensors")
+            P = pos.shape[0]
+            with torch.cuda.device(pos.device):
+                view, keep = _make_view(s, P, 0, pos.device)
+                out = torch.empty(P, dtype=torch.uint8, device=pos.device)
+                _lib.check(lib.s360_mark_visible(ctypes.byref(view), _ptr(pos), _ptr(out), _stream_ptr()))
+            del keep
+            return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        s = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.empty(0, dtype=torch.float32, device=means3D.device)
+        if shs is None:
+            shs = empty
+        if colors_precomp is None:
+            colors_precomp = empty
+        if cov3D_precomp is None:
+            cov3D_precomp = build_covariance_6(scales, rotations, float(s.scale_modifier))
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, empty, empty, cov3D_precomp, s)
