@@ -17,15 +17,35 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
                   const float* __restrict__ opac, const float* __restrict__ shs,
                   const float* __restrict__ colors, GeomState gs, int32_t* __restrict__ radii,
                   uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, S360Counters* counters) {
+  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
+  __shared__ uint64_t s_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = v.P;
   const int W = v.image_width, H = v.image_height;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const int row = v.M * 3;                                   // floats per Gaussian
+  const int rows = min(PRE_THREADS, P - blockIdx.x * PRE_THREADS);
+  const float* sh_src = shs ? shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
+  const uint32_t sh_bytes = (uint32_t)rows * row * 4u;
+  const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u);
+  if (shs) {
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    // erp: every Gaussian is a candidate, start the copy before the geometry math (overlap)
+    if (MODE == S360_MODE_ERP && bulk_ok && threadIdx.x == 0) {
+      mbar_expect_tx(&s_bar, sh_bytes);
+      bulk_load(s_sh, sh_src, sh_bytes, &s_bar);
+    }
+  }
   bool upstream_visible = false;
+  bool want_color = false;
+  float px = 0.f, py = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, op = 0.f, hx = 0.f, hy = 0.f, sortkey = 0.f;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  uint8_t cl = 0;
+  Cam cam;
   if (idx < P) {
-    Cam cam;
     load_cam(v, cam, MODE == S360_MODE_PINHOLE);
-    const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
+    mx = means[3 * idx]; my = means[3 * idx + 1]; mz = means[3 * idx + 2];
     int radius = 0;
     uint2 rect = make_uint2(0u, 0u);
     uint32_t key = 0xFFFFFFFFu;
@@ -34,7 +54,6 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     for (int k = 0; k < 6; k++) cv[k] = cov3D[6 * idx + k];
     Geo g;
     geo_compute<MODE>(v, cam.V, mx, my, mz, cv, g);
-    float sortkey;
     bool alive;
     if (MODE == S360_MODE_PINHOLE) { sortkey = g.t[2]; }
     else { sortkey = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]); }
@@ -43,21 +62,20 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     alive = alive && (det != 0.f);
     if (alive) {
       const float det_inv = 1.f / det;
-      const float cA = g.c * det_inv, cB = -g.b * det_inv, cC = g.a * det_inv;
+      cA = g.c * det_inv; cB = -g.b * det_inv; cC = g.a * det_inv;
       int ex, ey;
-      float px, py;
       if (MODE == S360_MODE_PINHOLE) {
         const float mid = 0.5f * (g.a + g.c);
         const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
         const float lam1 = mid + root, lam2 = mid - root;
         ex = ey = (int)ceilf(3.f * sqrtf(fmaxf(lam1, lam2)));
         const float* PM = cam.PM;
-        const float hx = PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12];
-        const float hy = PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13];
-        const float hw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
-        const float pw = 1.f / (hw + 0.0000001f);
-        px = ((hx * pw + 1.f) * W - 1.f) * 0.5f;
-        py = ((hy * pw + 1.f) * H - 1.f) * 0.5f;
+        const float qx = PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12];
+        const float qy = PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13];
+        const float qw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
+        const float pw = 1.f / (qw + 0.0000001f);
+        px = ((qx * pw + 1.f) * W - 1.f) * 0.5f;
+        py = ((qy * pw + 1.f) * H - 1.f) * 0.5f;
       } else {
         ex = (int)ceilf(3.f * sqrtf(g.a));
         ey = (int)ceilf(3.f * sqrtf(g.c));
@@ -80,9 +98,9 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
       upstream_visible = (xmax - xmin) * (ymax - ymin) > 0;
       if (upstream_visible) {
         radius = max(ex, ey);
-        const float op = opac[idx];
+        op = opac[idx];
         // box outside which alpha = op * exp(power) < 1/255 for certain
-        float hx = __int_as_float(0x7f800000), hy = hx;
+        hx = __int_as_float(0x7f800000); hy = hx;
         if (v.tight_bbox) {
           const float tau = logf(255.f * op);
           if (tau > 0.f) {
@@ -103,39 +121,8 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
           rect = make_uint2(((uint32_t)xmin & 0xffffu) | ((uint32_t)nx << 16), (uint32_t)ymin | ((uint32_t)ny << 16));
           key = __float_as_uint(sortkey);
         }
-        // colour
-        float col[3];
-        uint8_t cl = (g.clampx ? 8 : 0) | (g.clampy ? 16 : 0);
-        if (shs != nullptr) {
-          float dx = mx - cam.cam[0], dy = my - cam.cam[1], dz = mz - cam.cam[2];
-          const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
-          dx *= inv; dy *= inv; dz *= inv;
-          float b[25];
-          const int deg = min(v.sh_degree, v.max_sh_degree);
-          const int n = sh_basis(deg, dx, dy, dz, b);
-          const float* sh = shs + (size_t)idx * v.M * 3;
-          float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-          for (int k = 0; k < 25; k++) {
-            if (k < n) {
-              acc[0] += b[k] * sh[3 * k];
-              acc[1] += b[k] * sh[3 * k + 1];
-              acc[2] += b[k] * sh[3 * k + 2];
-            }
-          }
-#pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            const float r = acc[ch] + 0.5f;
-            if (r < 0.f) cl |= (1 << ch);
-            col[ch] = fmaxf(r, 0.f);
-          }
-        } else {
-          col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
-        }
-        gs.rec[3 * (size_t)idx + 0] = make_float4(px, py, cA, cB);
-        gs.rec[3 * (size_t)idx + 1] = make_float4(cC, op, hx, hy);
-        gs.rec[3 * (size_t)idx + 2] = make_float4(col[0], col[1], col[2], sortkey);
-        gs.clamped[idx] = cl;
+        want_color = true;
+        cl = (g.clampx ? 8 : 0) | (g.clampy ? 16 : 0);
       }
     }
     radii[idx] = radius;
@@ -145,6 +132,57 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
   }
   const unsigned m = __ballot_sync(0xffffffffu, upstream_visible);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters->num_visible, (uint32_t)__popc(m));
+
+  // ---- colour: SH block staged in shared memory (TMA bulk copy; coalesced fallback for odd tails)
+  float col[3] = {0.f, 0.f, 0.f};
+  if (shs != nullptr) {
+    bool need = true;
+    if (MODE == S360_MODE_PINHOLE || !bulk_ok) need = __syncthreads_or(want_color);   // most pinhole blocks are culled
+    if (need) {
+      if (bulk_ok) {
+        if (MODE == S360_MODE_PINHOLE && threadIdx.x == 0) {
+          mbar_expect_tx(&s_bar, sh_bytes);
+          bulk_load(s_sh, sh_src, sh_bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+      } else {
+        for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];
+        __syncthreads();
+      }
+      if (want_color) {
+        float dx = mx - cam.cam[0], dy = my - cam.cam[1], dz = mz - cam.cam[2];
+        const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
+        dx *= inv; dy *= inv; dz *= inv;
+        float b[25];
+        const int deg = min(v.sh_degree, v.max_sh_degree);
+        const int n = sh_basis(deg, dx, dy, dz, b);
+        const float* sh = s_sh + threadIdx.x * row;
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 25; k++) {
+          if (k < n) {
+            acc[0] += b[k] * sh[3 * k];
+            acc[1] += b[k] * sh[3 * k + 1];
+            acc[2] += b[k] * sh[3 * k + 2];
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          const float r = acc[ch] + 0.5f;
+          if (r < 0.f) cl |= (1 << ch);
+          col[ch] = fmaxf(r, 0.f);
+        }
+      }
+    }
+  } else if (want_color) {
+    col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
+  }
+  if (want_color) {
+    gs.rec[3 * (size_t)idx + 0] = make_float4(px, py, cA, cB);
+    gs.rec[3 * (size_t)idx + 1] = make_float4(cC, op, hx, hy);
+    gs.rec[3 * (size_t)idx + 2] = make_float4(col[0], col[1], col[2], sortkey);
+    gs.clamped[idx] = cl;
+  }
 }
 
 int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
@@ -152,10 +190,15 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
                       uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
-  if (v.mode == S360_MODE_PINHOLE)
-    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
-  else
-    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+  const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
+  if (smem > 200 * 1024) return S360_ERR_UNSUPPORTED;
+  if (v.mode == S360_MODE_PINHOLE) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -170,12 +213,37 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
                            const float* __restrict__ acc, float* __restrict__ d_means,
                            float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
                            float* __restrict__ d_shs, float* __restrict__ d_colors) {
+  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
+  __shared__ uint64_t s_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= v.P) return;
+  const int P = v.P;
   const int W = v.image_width, H = v.image_height;
+  const int row = v.M * 3;
+  const int rows = min(PRE_THREADS, P - blockIdx.x * PRE_THREADS);
+  const float* sh_src = shs ? shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
+  float* dsh_dst = shs ? d_shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
+  const uint32_t sh_bytes = (uint32_t)rows * row * 4u;
+  const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u) &&
+                       ((reinterpret_cast<uintptr_t>(dsh_dst) & 15u) == 0u);
+  const bool vis = idx < P && radii[idx] > 0;
+  bool need = false;
+  if (shs) {
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    need = __syncthreads_or(vis);
+    if (need) {
+      if (bulk_ok) {
+        if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, sh_bytes); bulk_load(s_sh, sh_src, sh_bytes, &s_bar); }
+      } else {
+        for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];
+        __syncthreads();
+      }
+    } else {
+      // nothing visible in this block: the SH gradient block is all zeros
+      for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) dsh_dst[i] = 0.f;
+    }
+  }
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float dop = 0.f, dcol[3] = {0.f, 0.f, 0.f};
-  const bool vis = radii[idx] > 0;
   if (vis) {
     Cam cam;
     load_cam(v, cam, MODE == S360_MODE_PINHOLE);
@@ -273,27 +341,40 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
       sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
       const uint8_t cl = gs.clamped[idx];
       const float drgb[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
-      const float* sh = shs + (size_t)idx * v.M * 3;
-      float* dsh = d_shs + (size_t)idx * v.M * 3;
+      if (bulk_ok) mbar_wait(&s_bar, 0);
+      float* sh = s_sh + threadIdx.x * row;      // this thread's row: read SH, overwrite with dL/dSH
       float ddir[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int k = 0; k < 25; k++) {
         if (k < n) {
           const float s = sh[3 * k] * drgb[0] + sh[3 * k + 1] * drgb[1] + sh[3 * k + 2] * drgb[2];
           ddir[0] += bx[k] * s; ddir[1] += by[k] * s; ddir[2] += bz[k] * s;
-          dsh[3 * k] = b[k] * drgb[0]; dsh[3 * k + 1] = b[k] * drgb[1]; dsh[3 * k + 2] = b[k] * drgb[2];
+          sh[3 * k] = b[k] * drgb[0]; sh[3 * k + 1] = b[k] * drgb[1]; sh[3 * k + 2] = b[k] * drgb[2];
         }
       }
-      for (int k = n; k < v.M; k++) { dsh[3 * k] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f; }
+      for (int k = 3 * n; k < row; k++) sh[k] = 0.f;
       const float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
       dm[0] += (ddir[0] - dx * dot) * inv;
       dm[1] += (ddir[1] - dy * dot) * inv;
       dm[2] += (ddir[2] - dz * dot) * inv;
     }
-  } else if (shs != nullptr) {
-    float* dsh = d_shs + (size_t)idx * v.M * 3;
-    for (int k = 0; k < v.M * 3; k++) dsh[k] = 0.f;
+  } else if (shs != nullptr && need && idx < P) {
+    if (bulk_ok) mbar_wait(&s_bar, 0);
+    float* sh = s_sh + threadIdx.x * row;
+    for (int k = 0; k < row; k++) sh[k] = 0.f;
   }
+  if (shs != nullptr && need) {
+    if (bulk_ok) {
+      if (idx >= P) mbar_wait(&s_bar, 0);
+      fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) { bulk_store(dsh_dst, s_sh, sh_bytes); bulk_store_wait_read(); }
+    } else {
+      __syncthreads();
+      for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) dsh_dst[i] = s_sh[i];
+    }
+  }
+  if (idx >= P) return;
 #pragma unroll
   for (int k = 0; k < 3; k++) d_means[3 * idx + k] = dm[k];
   d_means2D[3 * idx] = dm2[0]; d_means2D[3 * idx + 1] = dm2[1]; d_means2D[3 * idx + 2] = 0.f;
@@ -313,10 +394,15 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
                                cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
-  if (v.mode == S360_MODE_PINHOLE)
-    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
-  else
-    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+  const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
+  if (smem > 200 * 1024) return S360_ERR_UNSUPPORTED;
+  if (v.mode == S360_MODE_PINHOLE) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }
