@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsplatter360.so")
+LIB_PATH = os.environ.get("S360_LIB", os.path.join(_HERE, "libsplatter360.so"))  # S360_LIB: A/B-test a variant build
 
 MODE_PINHOLE = 0
 MODE_ERP = 1

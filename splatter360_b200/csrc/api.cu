@@ -204,9 +204,9 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
                   const uint32_t* point_list, const void* image_state, const float* dL_dcolor,
                   float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs,
                   float* dL_dcolors, void* scratch, void* stream) {
-  (void)opacities; (void)colors_precomp;
+  (void)colors_precomp;
   if (!view_ok(view) || !geom || !image_state || !scratch) return S360_ERR_BAD_ARGUMENT;
-  if (view->P > 0 && (!means3D || !cov3D || !radii || !dL_dmeans3D || !dL_dmeans2D || !dL_dcov3D || !dL_dopacity)) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (!means3D || !cov3D || !opacities || !radii || !dL_dmeans3D || !dL_dmeans2D || !dL_dcov3D || !dL_dopacity)) return S360_ERR_BAD_ARGUMENT;
   if (shs && !dL_dshs) return S360_ERR_BAD_ARGUMENT;
   if (!shs && !dL_dcolors) return S360_ERR_BAD_ARGUMENT;
   if ((size_t)view->image_height * view->image_width > 0 && !dL_dcolor) return S360_ERR_BAD_ARGUMENT;
@@ -223,7 +223,7 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
     if (rc) return rc;
   }
   StageTimer t(S360_STAGE_PREPROCESS_BWD, st);
-  return launch_preprocess_backward(*view, means3D, cov3D, shs, g, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dcov3D,
+  return launch_preprocess_backward(*view, means3D, cov3D, opacities, shs, g, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dcov3D,
                                     dL_dopacity, dL_dshs, dL_dcolors, st);
 }
 

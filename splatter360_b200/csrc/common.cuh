@@ -266,7 +266,7 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
 int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
                       const float* shs, const float* colors, GeomState g, int32_t* radii,
                       uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st);
-int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* shs,
+int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* opac, const float* shs,
                                GeomState g, const int32_t* radii, const float* acc, float* d_means,
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
                                cudaStream_t st);

@@ -209,7 +209,7 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
 template <int MODE>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_backward_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
-                           const float* __restrict__ shs, GeomState gs, const int32_t* __restrict__ radii,
+                           const float* __restrict__ opac, const float* __restrict__ shs, GeomState gs, const int32_t* __restrict__ radii,
                            const float* __restrict__ acc, float* __restrict__ d_means,
                            float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
                            float* __restrict__ d_shs, float* __restrict__ d_colors) {
@@ -252,9 +252,7 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)idx * ACC_STRIDE + 4);
     const float a2 = acc[(size_t)idx * ACC_STRIDE + 8];
     dcol[0] = a0.x; dcol[1] = a0.y; dcol[2] = a0.z;
-    const float gu = a0.w, gv = a1.x, gA = a1.y, gB = a1.z, gC = a1.w;
     dop = a2;
-    dm2[0] = gu * 0.5f * W; dm2[1] = gv * 0.5f * H;
     const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
     float cv[6];
 #pragma unroll
@@ -262,6 +260,15 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     Geo g;
     geo_compute<MODE>(v, V, mx, my, mz, cv, g);
     const float denom = g.a * g.c - g.b * g.b;
+    // the render pass accumulated moments of q = G dL/dalpha:  a0.w = sum q dx, a1 = sum q {dy, dx^2, dxdy, dy^2};
+    // dL/dG = o dL/dalpha turns them into the screen-space gradients
+    const float op = opac[idx];
+    const float det_inv = 1.f / denom;
+    const float cA = g.c * det_inv, cB = -g.b * det_inv, cC = g.a * det_inv;   // conic, as in the forward pass
+    const float S1 = op * a0.w, S2 = op * a1.x;
+    const float gu = -cA * S1 - cB * S2, gv = -cC * S2 - cB * S1;
+    const float gA = -0.5f * op * a1.y, gB = -op * a1.z, gC = -0.5f * op * a1.w;
+    dm2[0] = gu * 0.5f * W; dm2[1] = gv * 0.5f * H;
     const float inv2 = 1.f / (denom * denom + 0.0000001f);
     const float da = inv2 * (-g.c * g.c * gA + g.b * g.c * gB + (denom - g.a * g.c) * gC);
     const float dc = inv2 * (-g.a * g.a * gC + g.a * g.b * gB + (denom - g.a * g.c) * gA);
@@ -388,7 +395,7 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
   }
 }
 
-int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* shs,
+int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* opac, const float* shs,
                                GeomState g, const int32_t* radii, const float* acc, float* d_means,
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
                                cudaStream_t st) {
@@ -398,10 +405,10 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
   if (smem > 200 * 1024) return S360_ERR_UNSUPPORTED;
   if (v.mode == S360_MODE_PINHOLE) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
   }
   count_launch();
   return (int)cudaGetLastError();
