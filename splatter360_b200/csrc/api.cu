@@ -52,20 +52,23 @@ static size_t pre_scratch_carve(void* buf, int P, PreScratch* out) {
   return 4 * arr + rad + sums;
 }
 
-// scratch layout of s360_forward_render: [tile keys a | tile keys b | vals b | radix]
+// scratch layout of s360_forward_render: [tile keys a | tile keys b | vals b | tile counts | radix]
 struct BinScratch {
-  uint32_t *keys_a, *keys_b, *vals_b;
+  uint32_t *keys_a, *keys_b, *vals_b, *tile_count;
   void* radix;
 };
-static size_t bin_scratch_carve(void* buf, int64_t cap, BinScratch* out) {
+static size_t bin_scratch_carve(void* buf, int64_t cap, int H, int W, BinScratch* out) {
   char* p = (char*)buf;
   const size_t arr = align_up((size_t)(cap > 0 ? cap : 1) * 4, 256);
+  const size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+  const size_t tc = align_up((tiles > 0 ? tiles : 1) * 4 * (size_t)tile_hist_copies(), 256);
   const size_t rad = radix_scratch_bytes(cap);
   if (out) {
     out->keys_a = (uint32_t*)p; out->keys_b = (uint32_t*)(p + arr); out->vals_b = (uint32_t*)(p + 2 * arr);
-    out->radix = p + 3 * arr;
+    out->tile_count = (uint32_t*)(p + 3 * arr);
+    out->radix = p + 3 * arr + tc;
   }
-  return 3 * arr + rad;
+  return 3 * arr + tc + rad;
 }
 
 static int tile_bits(int H, int W) {
@@ -124,7 +127,7 @@ const char* s360_error_string(int code) {
 
 size_t s360_geom_bytes(int32_t P) { return geom_bytes(P > 0 ? P : 1); }
 size_t s360_preprocess_scratch_bytes(int32_t P) { return pre_scratch_carve(nullptr, P, nullptr); }
-size_t s360_binning_scratch_bytes(int64_t cap, int32_t, int32_t) { return bin_scratch_carve(nullptr, cap, nullptr); }
+size_t s360_binning_scratch_bytes(int64_t cap, int32_t H, int32_t W) { return bin_scratch_carve(nullptr, cap, H, W, nullptr); }
 size_t s360_image_bytes(int32_t H, int32_t W) { return image_bytes(H, W); }
 size_t s360_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float), 256); }
 
@@ -150,7 +153,7 @@ int s360_forward_preprocess(const S360View* view, const float* means3D, const fl
   if (rc) return rc;
   int in_b = 0;
   { StageTimer t(S360_STAGE_DEPTH_SORT, st);
-    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, P, nullptr, 32, s.radix, st, &in_b);
+    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, P, nullptr, 32, s.radix, st, &in_b, false);
     if (rc) return rc;
     const uint32_t* sorted_ids = in_b ? s.ids_b : s.ids_a;
     if (P > 0) {
@@ -172,28 +175,26 @@ int s360_forward_render(const S360View* view, const void* geom, const uint32_t* 
   GeomState g = carve_geom(const_cast<void*>(geom), P > 0 ? P : 1);
   ImageState img = carve_image(image_state, H, W);
   BinScratch s;
-  bin_scratch_carve(scratch, instance_capacity, &s);
+  bin_scratch_carve(scratch, instance_capacity, H, W, &s);
   const int nbits = tile_bits(H, W);
   const int passes = (nbits + 7) / 8;
+  if (passes > 3) return S360_ERR_UNSUPPORTED;
   // the sorted ids must land in point_list: start in (keys_a, point_list) for an even number of passes,
   // in (keys_b, vals_b) for an odd number
   uint32_t *k0 = s.keys_a, *v0 = point_list, *k1 = s.keys_b, *v1 = s.vals_b;
   if (passes & 1) { k0 = s.keys_b; v0 = s.vals_b; k1 = s.keys_a; v1 = point_list; }
   int rc;
+  uint32_t* hist;
   { StageTimer t(S360_STAGE_EMIT, st);
-    rc = launch_emit(*view, g, depth_order, inst_offsets, counters, instance_capacity, k0, v0, st); }
+    hist = radix_prepare_hist(s.radix, instance_capacity, nbits, st);
+    rc = launch_emit(*view, g, depth_order, inst_offsets, counters, instance_capacity, k0, v0, s.tile_count, st); }
+  if (rc) return rc;
+  { StageTimer t(S360_STAGE_TILE_RANGES, st);
+    rc = launch_tile_scan(*view, s.tile_count, img.ranges, hist, passes > 0 ? passes : 1, st); }
   if (rc) return rc;
   int in_b = 0;
   { StageTimer t(S360_STAGE_TILE_SORT, st);
-    rc = radix_sort_pairs(k0, v0, k1, v1, instance_capacity, &counters->num_rendered, nbits, s.radix, st, &in_b); }
-  if (rc) return rc;
-  const uint32_t* sorted_keys = in_b ? k1 : k0;
-  if (passes == 0 && instance_capacity > 0 && v0 != point_list) {
-    rc = (int)cudaMemcpyAsync(point_list, v0, (size_t)instance_capacity * 4, cudaMemcpyDeviceToDevice, st);
-    if (rc) return rc;
-  }
-  { StageTimer t(S360_STAGE_TILE_RANGES, st);
-    rc = launch_tile_ranges(*view, sorted_keys, counters, instance_capacity, img.ranges, st); }
+    rc = radix_sort_pairs(k0, v0, k1, v1, instance_capacity, &counters->num_rendered, nbits, s.radix, st, &in_b, true); }
   if (rc) return rc;
   StageTimer t(S360_STAGE_RENDER_FWD, st);
   return launch_render_forward(*view, g, point_list, img, out_color, st);

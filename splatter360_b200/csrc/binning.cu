@@ -1,9 +1,13 @@
-// binning.cu -- tile binning: hand-written LSD radix sort + scan + instance emission + tile ranges.
+// binning.cu -- tile binning: hand-written onesweep radix sort + scan + instance emission + tile ranges.
 //
 // Upstream sorts N (tile<<32 | depth) 64-bit keys with CUB (6 passes over every instance).  Here the
 // order (tile, depth, id) is produced in two cheaper steps with identical result:
 //   1. sort the P Gaussians once by (depth bits, id)              -- 4 passes over P pairs
 //   2. emit instances in that order, then STABLE-sort them by tile -- ceil(log2(tiles)/8) passes over N
+// Each pass is ONE kernel (onesweep: per-block digit counts are published to a status array and the
+// exclusive prefix over preceding blocks is obtained by decoupled look-back), the digit histograms of
+// all passes come from a single read of the keys (depth) or from the per-tile instance histogram that
+// the emission kernel accumulates anyway (tiles); the tile ranges are a scan of that same histogram.
 // Replaces cub::DeviceScan::InclusiveSum, duplicateWithKeys, cub::DeviceRadixSort::SortPairs and
 // identifyTileRanges.
 #include "common.cuh"
@@ -12,9 +16,16 @@ namespace s360 {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 8;                       // keys per thread
+#ifndef S360_RS_ITEMS
+#define S360_RS_ITEMS 12
+#endif
+#ifndef S360_RS_MINB
+#define S360_RS_MINB 3
+#endif
+constexpr int RS_ITEMS = S360_RS_ITEMS;           // keys per thread
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per block
 constexpr int RS_BINS = 256;
+constexpr uint32_t ST_AGG = 1u << 30, ST_PREFIX = 2u << 30, ST_MASK = (1u << 30) - 1u;
 
 __device__ __forceinline__ int64_t effective_n(int64_t n_cap, const uint32_t* n_dev) {
   if (n_dev == nullptr) return n_cap;
@@ -22,80 +33,49 @@ __device__ __forceinline__ int64_t effective_n(int64_t n_cap, const uint32_t* n_
   return nd < n_cap ? nd : n_cap;
 }
 
-// ---- pass kernel A: per-block digit histogram, written bin-major: hist[bin * nblocks + block]
+// ---- digit histograms of up to four 8-bit passes from one read of the keys --------------------
 __global__ void __launch_bounds__(RS_THREADS)
-rs_histogram_kernel(const uint32_t* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ n_dev,
-                    int shift, uint32_t* __restrict__ hist, int nblocks) {
-  __shared__ uint32_t s_hist[RS_BINS];
-  const int64_t n = effective_n(n_cap, n_dev);
-  s_hist[threadIdx.x] = 0;
+rs_global_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int npasses, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_hist[4][RS_BINS];
+  for (int i = threadIdx.x; i < 4 * RS_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
   __syncthreads();
-  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
-    const int64_t j = base + i * RS_THREADS + threadIdx.x;
-    uint32_t d = 0x100u | lane;  // unique pseudo digit for out-of-range lanes
-    if (j < n) d = (keys[j] >> shift) & 0xffu;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
-    if (d < 0x100u && lane == (__ffs(peers) - 1)) atomicAdd(&s_hist[d], (uint32_t)__popc(peers));
+  const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
+  for (int64_t j = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; j < n; j += stride) {
+    const uint32_t k = keys[j];
+    for (int p = 0; p < npasses; p++) atomicAdd(&s_hist[p][(k >> (8 * p)) & 0xffu], 1u);
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_hist[threadIdx.x];
-}
-
-// ---- pass kernel B: one block per digit, exclusive scan over that digit's row of block counts
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scan_rows_kernel(uint32_t* __restrict__ hist, int nblocks, uint32_t* __restrict__ bin_totals) {
-  __shared__ uint32_t s_warp[RS_WARPS];
-  __shared__ uint32_t s_carry;
-  uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nblocks; base += RS_THREADS) {
-    const int i = base + threadIdx.x;
-    const uint32_t x = i < nblocks ? row[i] : 0u;
-    uint32_t incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) woff += (w < warp) ? s_warp[w] : 0u;
-    const uint32_t carry = s_carry;
-    if (i < nblocks) row[i] = carry + woff + incl - x;
-    __syncthreads();
-    if (threadIdx.x == RS_THREADS - 1) s_carry = carry + woff + incl;
-    __syncthreads();
+  for (int i = threadIdx.x; i < npasses * RS_BINS; i += RS_THREADS) {
+    const uint32_t c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(&hist[i], c);
   }
-  if (threadIdx.x == 0) bin_totals[blockIdx.x] = s_carry;
 }
 
-// ---- pass kernel C: stable rank inside the block, exchange through shared memory, coalesced scatter
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
-                  const uint32_t* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
-                  int nblocks, const uint32_t* __restrict__ bin_totals) {
+// ---- one radix pass: rank in block, look back for the cross-block prefix, exchange, scatter ---
+// hist: this pass's global digit counts [256].  status: [nblocks][256], zero on entry.
+// counter: zero on entry; hands out block ids in scheduling order so that look-back cannot deadlock.
+__global__ void __launch_bounds__(RS_THREADS, S360_RS_MINB)
+rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
+                   const uint32_t* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
+                   uint32_t* status, uint32_t* counter) {
   __shared__ uint32_t s_cnt[RS_WARPS][RS_BINS];   // per-warp digit counters -> exclusive warp prefixes
   __shared__ uint32_t s_keys[RS_TILE];
   __shared__ uint32_t s_vals[RS_TILE];
   __shared__ int64_t s_gbase[RS_BINS];            // global destination of local sorted slot 0 of each digit
   __shared__ uint32_t s_scan[RS_WARPS];
   __shared__ uint32_t s_scan2[RS_WARPS];
+  __shared__ uint32_t s_bid;
   const int64_t n = effective_n(n_cap, n_dev);
-  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-  if (base >= n) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x == 0) s_bid = atomicAdd(counter, 1u);
 #pragma unroll
   for (int w = 0; w < RS_WARPS; w++) s_cnt[w][threadIdx.x] = 0;
   __syncthreads();
+  const uint32_t bid = s_bid;
+  const int64_t base = (int64_t)bid * RS_TILE;
+  if (base >= n) return;   // every later block is out of range too: nobody will look back at this one
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   // warp w owns the contiguous items [w*256, w*256+256) of this block, 8 rounds of 32
   uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
@@ -132,9 +112,30 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
     s_cnt[w][d] = total;
     total += c;
   }
+  // publish this block's count of digit d, then look back over the preceding blocks
+  uint32_t* my_status = status + (size_t)bid * RS_BINS + d;
+  volatile uint32_t* vstatus = status;
+  if (bid == 0) {
+    *reinterpret_cast<volatile uint32_t*>(my_status) = total | ST_PREFIX;
+  } else {
+    *reinterpret_cast<volatile uint32_t*>(my_status) = total | ST_AGG;
+  }
+  uint32_t excl = 0;
+  if (bid > 0) {
+    int64_t j = (int64_t)bid - 1;
+    while (true) {
+      const uint32_t sv = vstatus[(size_t)j * RS_BINS + d];
+      const uint32_t flag = sv & ~ST_MASK;
+      if (flag == 0u) continue;          // predecessor has not published yet
+      excl += sv & ST_MASK;
+      if (flag == ST_PREFIX) break;
+      --j;
+    }
+    *reinterpret_cast<volatile uint32_t*>(my_status) = (excl + total) | ST_PREFIX;
+  }
   // block-exclusive scan of `total` over digits -> first local slot of digit d;
-  // block-exclusive scan of bin_totals over digits -> global base of digit d
-  const uint32_t bt = bin_totals[d];
+  // block-exclusive scan of the global histogram over digits -> global base of digit d
+  const uint32_t bt = hist[d];
   uint32_t incl = total, incl2 = bt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -152,8 +153,7 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
   }
   const uint32_t local_first = woff + incl - total;
   const uint32_t global_first = woff2 + incl2 - bt;
-  s_gbase[d] = (int64_t)global_first + (int64_t)hist[(size_t)d * nblocks + blockIdx.x] - (int64_t)local_first;
-  // s_cnt[w][d] += local_first, so that slot = s_cnt[warp][digit] + rank
+  s_gbase[d] = (int64_t)global_first + (int64_t)excl - (int64_t)local_first;
 #pragma unroll
   for (int w = 0; w < RS_WARPS; w++) s_cnt[w][d] += local_first;
   __syncthreads();
@@ -184,31 +184,46 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
 
 static inline int rs_blocks(int64_t n) { return (int)((n + RS_TILE - 1) / RS_TILE); }
 
+// scratch: [hist 4*256][counters 4 (padded)][status passes*nblocks*256]
+static inline size_t rs_status_words(int64_t n, int passes) { return (size_t)passes * rs_blocks(n > 0 ? n : 1) * RS_BINS; }
 size_t radix_scratch_bytes(int64_t n) {
-  const size_t nb = (size_t)rs_blocks(n > 0 ? n : 1);
-  return align_up(nb * RS_BINS * sizeof(uint32_t), 256) + align_up(RS_BINS * sizeof(uint32_t), 256);
+  return align_up(4 * RS_BINS * 4, 256) + 256 + align_up(rs_status_words(n, 4) * 4, 256);
 }
 
+// hist_ready: the caller already filled hist[pass][256] (and the scratch was zeroed before that)
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n,
-                     const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b) {
+                     const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b,
+                     bool hist_ready) {
   *result_in_b = 0;
   if (n <= 0 || nbits <= 0) return 0;
+  const int passes = (nbits + 7) / 8;
   const int nblocks = rs_blocks(n);
   uint32_t* hist = (uint32_t*)scratch;
-  uint32_t* bin_totals = (uint32_t*)((char*)scratch + align_up((size_t)nblocks * RS_BINS * sizeof(uint32_t), 256));
+  uint32_t* counters = (uint32_t*)((char*)scratch + align_up(4 * RS_BINS * 4, 256));
+  uint32_t* status = (uint32_t*)((char*)counters + 256);
+  if (!hist_ready) {
+    cudaMemsetAsync(scratch, 0, align_up(4 * RS_BINS * 4, 256) + 256 + rs_status_words(n, passes) * 4, st);
+    const int hb = nblocks < 592 ? nblocks : 592;
+    rs_global_hist_kernel<<<hb, RS_THREADS, 0, st>>>(keys_a, n, passes, hist);
+    count_launch();
+  }
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
-  int flips = 0;
-  for (int shift = 0; shift < nbits; shift += 8) {
-    rs_histogram_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, n, n_dev, shift, hist, nblocks);
-    rs_scan_rows_kernel<<<RS_BINS, RS_THREADS, 0, st>>>(hist, nblocks, bin_totals);
-    rs_scatter_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, n_dev, shift, hist, nblocks, bin_totals);
-    count_launch(3);
+  for (int p = 0; p < passes; p++) {
+    rs_onesweep_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, n_dev, 8 * p, hist + p * RS_BINS,
+                                                       status + (size_t)p * nblocks * RS_BINS, counters + p);
+    count_launch();
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
-    flips++;
   }
-  *result_in_b = flips & 1;
+  *result_in_b = passes & 1;
   return (int)cudaGetLastError();
+}
+
+// zero the radix scratch and return the histogram pointer so that a producer kernel can fill it
+uint32_t* radix_prepare_hist(void* scratch, int64_t n, int nbits, cudaStream_t st) {
+  const int passes = (nbits + 7) / 8;
+  cudaMemsetAsync(scratch, 0, align_up(4 * RS_BINS * 4, 256) + 256 + rs_status_words(n, passes > 0 ? passes : 1) * 4, st);
+  return (uint32_t*)scratch;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,83 +327,130 @@ int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_or
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: emit (tile, gaussian) instances in depth order.  One block owns 2048 consecutive Gaussians of
-// the depth order; its threads walk the block's contiguous instance range so that the writes are
-// coalesced and the work is balanced no matter how many tiles a single Gaussian covers.
-__global__ void __launch_bounds__(RS_THREADS)
-emit_instances_kernel(int P, int gx, int mode, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
+// K3: emit (tile, gaussian) instances in depth order and count instances per tile.  A warp owns 32
+// consecutive Gaussians of the depth order; their instances form one contiguous output range which the
+// 32 lanes walk together (coalesced writes, balanced no matter how many tiles one Gaussian covers).
+// The owner of output slot `pos` is found by a 5-step binary search over the lanes' start offsets.
+constexpr int EMIT_THREADS = 256;
+constexpr int TILE_HIST_COPIES = 16;   // replicated per-tile counters: spreads the L2 atomic traffic over more lines
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_instances_kernel(int P, int gx, int ntiles, int mode, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ offsets, S360Counters* counters, int64_t capacity,
-                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  __shared__ uint32_t s_off[RS_TILE];
-  __shared__ uint32_t s_gid[RS_TILE];
-  __shared__ uint2 s_rect[RS_TILE];
-  const int base = blockIdx.x * RS_TILE;
-  const int cnt = min(RS_TILE, P - base);
-  for (int i = threadIdx.x; i < cnt; i += RS_THREADS) {
-    const uint32_t gid = order[base + i];
-    s_gid[i] = gid;
-    s_rect[i] = rect[gid];
-    s_off[i] = offsets[base + i];
+                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ tile_count) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;   // position in the depth order
+  uint32_t gid = 0, off = 0xffffffffu, cnt = 0;
+  uint2 r = make_uint2(0u, 0u);
+  if (i < P) {
+    gid = order[i];
+    r = rect[gid];
+    off = offsets[i];
+    cnt = rect_tiles(r);
   }
-  __syncthreads();
-  const uint32_t begin = s_off[0];
-  const uint32_t end = s_off[cnt - 1] + rect_tiles(s_rect[cnt - 1]);
+  // [begin, end) of this warp's instances; lanes beyond P carry off = 0xffffffff and never own a slot
+  const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
+  uint32_t end = (i < P) ? off + cnt : 0u;
+  end = __reduce_max_sync(0xffffffffu, end);
+  if (begin == 0xffffffffu || end <= begin) return;
   bool overflow = false;
-  for (uint32_t j = begin + threadIdx.x; j < end; j += RS_THREADS) {
-    // last i with s_off[i] <= j
-    int lo = 0, hi = cnt;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= j) lo = mid; else hi = mid;
+  for (uint32_t p0 = begin; p0 < end; p0 += 32) {   // warp-uniform trip count: every lane joins the shuffles
+    const uint32_t pos = p0 + lane;
+    // last lane j with off_j <= pos (zero-count lanes share their successor's offset and lose the tie)
+    int lo = 0;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const uint32_t v = __shfl_sync(0xffffffffu, off, (lo + s) & 31);
+      if (lo + s < 32 && v <= pos) lo += s;
     }
-    const uint2 r = s_rect[lo];
-    const uint32_t k = j - s_off[lo];
-    const uint32_t nx = r.x >> 16;
-    const uint32_t ky = k / nx, kx = k - ky * nx;
-    int tx = (int)(int16_t)(r.x & 0xffffu) + (int)kx;
-    if (mode == S360_MODE_ERP) { tx %= gx; if (tx < 0) tx += gx; }
-    const uint32_t ty = (r.y & 0xffffu) + ky;
-    if ((int64_t)j < capacity) {
-      keys[j] = ty * (uint32_t)gx + (uint32_t)tx;
-      vals[j] = s_gid[lo];
-    } else {
-      overflow = true;
+    const uint32_t o_off = __shfl_sync(0xffffffffu, off, lo);
+    const uint32_t o_rx = __shfl_sync(0xffffffffu, r.x, lo);
+    const uint32_t o_ry = __shfl_sync(0xffffffffu, r.y, lo);
+    const uint32_t o_gid = __shfl_sync(0xffffffffu, gid, lo);
+    if (pos < end) {
+      const uint32_t k = pos - o_off;
+      const uint32_t nx = o_rx >> 16;
+      const uint32_t ky = k / nx, kx = k - ky * nx;
+      int tx = (int)(int16_t)(o_rx & 0xffffu) + (int)kx;
+      if (mode == S360_MODE_ERP) { tx %= gx; if (tx < 0) tx += gx; }
+      const uint32_t tile = ((o_ry & 0xffffu) + ky) * (uint32_t)gx + (uint32_t)tx;
+      if ((int64_t)pos < capacity) {
+        keys[pos] = tile;
+        vals[pos] = o_gid;
+        atomicAdd(&tile_count[(size_t)(blockIdx.x & (TILE_HIST_COPIES - 1)) * ntiles + tile], 1u);
+      } else {
+        overflow = true;
+      }
     }
   }
   if (overflow) counters->overflow = 1;
 }
 
+int tile_hist_copies() { return TILE_HIST_COPIES; }
+
+// One block: exclusive scan of the per-tile instance counts -> tile ranges, plus the digit histograms of
+// the (up to two) tile-sort passes, which are just partial sums of the same counts.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+                 uint32_t* __restrict__ hist, int npasses) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_hist[3][RS_BINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  for (int i = threadIdx.x; i < 3 * RS_BINS; i += 1024) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    uint32_t x = 0;
+    if (i < ntiles) {
+#pragma unroll
+      for (int c = 0; c < TILE_HIST_COPIES; c++) x += tile_count[(size_t)c * ntiles + i];
+    }
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_w[w];
+    const uint32_t carry = s_carry;
+    if (i < ntiles) {
+      const uint32_t start = carry + woff + incl - x;
+      ranges[i] = x ? make_uint2(start, start + x) : make_uint2(0u, 0u);
+      if (x) {
+        atomicAdd(&s_hist[0][i & 0xff], x);
+        if (npasses > 1) atomicAdd(&s_hist[1][(i >> 8) & 0xff], x);
+        if (npasses > 2) atomicAdd(&s_hist[2][(i >> 16) & 0xff], x);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + woff + incl;
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < npasses * RS_BINS; i += 1024) hist[i] = (&s_hist[0][0])[i];
+}
+
 int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, const uint32_t* offsets,
-                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, cudaStream_t st) {
+                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, uint32_t* tile_count,
+                cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+  cudaMemsetAsync(tile_count, 0, (size_t)gx * gy * TILE_HIST_COPIES * sizeof(uint32_t), st);
   if (v.P == 0) return 0;
-  const int gx = (v.image_width + TILE - 1) / TILE;
-  emit_instances_kernel<<<rs_blocks(v.P), RS_THREADS, 0, st>>>(v.P, gx, v.mode, g.rect, depth_order, offsets,
-                                                               counters, capacity, keys, vals);
+  emit_instances_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
+      v.P, gx, gx * gy, v.mode, g.rect, depth_order, offsets, counters, capacity, keys, vals, tile_count);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------------
-// K5: [start, end) of each tile in the sorted instance list
-__global__ void tile_ranges_kernel(const uint32_t* __restrict__ keys, const S360Counters* __restrict__ counters,
-                                   int64_t capacity, uint2* __restrict__ ranges) {
-  int64_t n = counters->num_rendered;
-  if (n > capacity) n = capacity;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t t = keys[i];
-  if (i == 0 || keys[i - 1] != t) ranges[t].x = (uint32_t)i;
-  if (i == n - 1 || keys[i + 1] != t) ranges[t].y = (uint32_t)(i + 1);
-}
-
-int launch_tile_ranges(const S360View& v, const uint32_t* keys, const S360Counters* counters, int64_t capacity,
-                       uint2* ranges, cudaStream_t st) {
+int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* hist, int npasses,
+                     cudaStream_t st) {
   const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
-  cudaMemsetAsync(ranges, 0, (size_t)gx * gy * sizeof(uint2), st);
-  if (capacity > 0) {
-    tile_ranges_kernel<<<(unsigned)((capacity + 255) / 256), 256, 0, st>>>(keys, counters, capacity, ranges);
-    count_launch();
-  }
+  tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, ranges, hist, npasses);
+  count_launch();
   return (int)cudaGetLastError();
 }
 

@@ -272,19 +272,24 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
                                cudaStream_t st);
 int launch_mark_visible(const S360View& v, const float* means, uint8_t* present, cudaStream_t st);
 
-// radix sort of (u32 key, u32 value) pairs on bits [0, nbits); result lands in (keys_out, vals_out).
-// keys_a/vals_a hold the input; *_b are same-sized alternates.  n_dev (device u32, may be NULL)
-// overrides n with min(*n_dev, n).  Returns which buffer (0 = a, 1 = b) holds the result.
+// onesweep radix sort of (u32 key, u32 value) pairs on bits [0, nbits).  keys_a/vals_a hold the input;
+// *_b are same-sized alternates; *result_in_b says where the result landed.  n_dev (device u32, may be NULL)
+// overrides n with min(*n_dev, n).  With hist_ready the caller has zeroed the scratch with
+// radix_prepare_hist() and filled the returned per-pass digit histograms itself.
 size_t radix_scratch_bytes(int64_t n);
+uint32_t* radix_prepare_hist(void* scratch, int64_t n, int nbits, cudaStream_t st);
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n,
-                     const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b);
+                     const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b,
+                     bool hist_ready);
 
 int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_order, uint32_t* offsets,
                         S360Counters* counters, uint32_t* block_sums, cudaStream_t st);
 int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, const uint32_t* offsets,
-                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, cudaStream_t st);
-int launch_tile_ranges(const S360View& v, const uint32_t* keys, const S360Counters* counters, int64_t capacity,
-                       uint2* ranges, cudaStream_t st);
+                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, uint32_t* tile_count,
+                cudaStream_t st);
+int tile_hist_copies();
+int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* hist, int npasses,
+                     cudaStream_t st);
 
 int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
                           float* out_color, cudaStream_t st);
