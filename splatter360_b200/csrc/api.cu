@@ -136,7 +136,7 @@ int s360_forward_preprocess(const S360View* view, const float* means3D, const fl
                             uint32_t* depth_order, uint32_t* inst_offsets, S360Counters* counters, void* scratch,
                             void* stream) {
   if (!view_ok(view) || !counters || !geom || !scratch) return S360_ERR_BAD_ARGUMENT;
-  if ((shs == nullptr) == (colors_precomp == nullptr)) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (shs == nullptr) == (colors_precomp == nullptr)) return S360_ERR_BAD_ARGUMENT;
   if (view->P > 0 && (!means3D || !cov3D || !opacities || !radii || !depth_order || !inst_offsets)) return S360_ERR_BAD_ARGUMENT;
   if (shs && view->M < (view->sh_degree < view->max_sh_degree ? (view->sh_degree + 1) * (view->sh_degree + 1)
                                                                 : (view->max_sh_degree + 1) * (view->max_sh_degree + 1)))
@@ -208,8 +208,8 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
   (void)colors_precomp;
   if (!view_ok(view) || !geom || !image_state || !scratch) return S360_ERR_BAD_ARGUMENT;
   if (view->P > 0 && (!means3D || !cov3D || !opacities || !radii || !dL_dmeans3D || !dL_dmeans2D || !dL_dcov3D || !dL_dopacity)) return S360_ERR_BAD_ARGUMENT;
-  if (shs && !dL_dshs) return S360_ERR_BAD_ARGUMENT;
-  if (!shs && !dL_dcolors) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && shs && !dL_dshs) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && !shs && !dL_dcolors) return S360_ERR_BAD_ARGUMENT;
   if ((size_t)view->image_height * view->image_width > 0 && !dL_dcolor) return S360_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = view->P, H = view->image_height, W = view->image_width;

@@ -1,0 +1,79 @@
+"""Multi-GPU layer: independent (batch item, view) renders are sharded across ranks, one process per GPU.
+
+The reference scales only by Lightning DDP with batch 1 per GPU (/root/reference/src/main.py:117-130,
+README.md:133) and renders the views of a batch item one after another in Python
+(/root/reference/src/model/decoder/decoder_splatting_cuda.py:44-59).  Each view render is independent
+given the Gaussians, so the path shards with NO data-path collective; the only collective is the
+all-reduce of the scalar loss / metrics (NCCL on GPUs, gloo in the CPU tests).  If one scene's views are
+split across ranks AND Gaussian gradients are needed, ``all_reduce_gradients`` sums the per-rank
+gradient blocks (85 floats per Gaussian).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_views(num_views: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> List[int]:
+    """Round-robin assignment of view indices to this rank: rank r renders views
+    r, r + world, r + 2 world, ...  Every view is rendered by exactly one rank."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    return list(range(rank, num_views, world_size))
+
+
+def all_reduce_loss(loss: Tensor, average: bool = False) -> Tensor:
+    """Sum (or mean) of a scalar loss over ranks -- the only collective on the hot path."""
+    _, ws = world()
+    if ws == 1:
+        return loss
+    out = loss.detach().clone()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    return out / ws if average else out
+
+
+def all_reduce_gradients(grads: Iterable[Optional[Tensor]]) -> None:
+    """In-place sum over ranks of per-Gaussian gradient tensors (only needed when the views of ONE scene are
+    split across ranks and the Gaussians are replicated)."""
+    _, ws = world()
+    if ws == 1:
+        return
+    for g in grads:
+        if g is not None:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+
+
+def gather_views(local: Tensor, num_views: int) -> Tensor:
+    """Reassemble the [num_views, ...] stack from the round-robin shards ``local`` [len(shard), ...] held by each
+    rank (evaluation / video paths that need every frame on every rank)."""
+    rank, ws = world()
+    if ws == 1:
+        return local
+    per = (num_views + ws - 1) // ws
+    pad = torch.zeros((per, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(parts, pad)
+    out = torch.empty((num_views, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r in range(ws):
+        idx = shard_views(num_views, r, ws)
+        out[idx] = parts[r][: len(idx)]
+    return out
+
+
+def render_views_sharded(render_one: Callable[[int], Tensor], num_views: int) -> Tuple[List[int], List[Tensor]]:
+    """Run ``render_one(view_index)`` for this rank's share of the views.  Returns (indices, images)."""
+    idx = shard_views(num_views)
+    return idx, [render_one(i) for i in idx]

@@ -1,0 +1,46 @@
+"""C-ABI checks that need no GPU: the shared library loads, exports every symbol include/splatter360.h
+declares, and its pure-host size queries behave."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "splatter360.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(s360_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from splatter360_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"libsplatter360.so does not export {n}"
+    assert set(_lib.EXPORTS) == set(names)
+
+
+def test_view_struct_layout_and_sizes():
+    from splatter360_b200 import _lib
+    lib = _lib.load()
+    assert ctypes.sizeof(_lib.S360View) == 8 * 4 + 6 * 4 + 4 * 8
+    assert lib.s360_abi_version() == 1
+    assert lib.s360_geom_bytes(1000) >= 1000 * (48 + 8 + 1)
+    assert lib.s360_image_bytes(512, 1024) >= 512 * 1024 * 8 + 2048 * 8
+    assert lib.s360_backward_scratch_bytes(10) >= 10 * 9 * 4
+    assert lib.s360_binning_scratch_bytes(1 << 20, 512, 1024) >= 3 * 4 * (1 << 20)
+    assert lib.s360_preprocess_scratch_bytes(1 << 20) >= 4 * 4 * (1 << 20)
+    assert b"bad argument" in lib.s360_error_string(-1)
+    assert lib.s360_launch_count() >= 0
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu():
+    from splatter360_b200 import _lib
+    lib = _lib.load()
+    v = _lib.S360View()
+    v.P, v.image_height, v.image_width, v.mode = 10, 16, 16, 7   # invalid mode, null matrices
+    assert lib.s360_mark_visible(ctypes.byref(v), None, None, None) == -1
+    assert lib.s360_forward_preprocess(ctypes.byref(v), *([None] * 12)) == -1

@@ -57,5 +57,6 @@ def test_stage_parity(mode, H, W, n):
     # between libm expf and ex2.approx (a handful of pixels in the larger cases)
     mism = float((c["n_contrib"] != o["n_contrib"]).mean())
     assert mism <= (0.0 if n <= 5000 else 2e-3), f"n_contrib mismatch fraction {mism}"
-    assert rel_l2(c["final_T"], o["final_T"]) < 1e-5
-    assert rel_l2(color.cpu().numpy(), o["color"]) < 1e-5
+    tol = 1e-5 if n <= 5000 else 1e-4   # a flipped threshold decision moves one pixel by up to ~1/255
+    assert rel_l2(c["final_T"], o["final_T"]) < tol
+    assert rel_l2(color.cpu().numpy(), o["color"]) < tol

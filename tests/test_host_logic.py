@@ -1,0 +1,124 @@
+"""Host-side logic on CPU: the Python surface mirrors diff_gaussian_rasterization's error behaviour, the product
+path refuses to run without CUDA (no silent fallback), and the view sharding / loss all-reduce work over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _settings(**kw):
+    from splatter360_b200.rasterizer import GaussianRasterizationSettings
+    d = dict(image_height=16, image_width=16, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3), scale_modifier=1.0,
+             viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3), prefiltered=False,
+             debug=False)
+    d.update(kw)
+    return GaussianRasterizationSettings(**d)
+
+
+def test_settings_surface_matches_upstream():
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    f = GaussianRasterizationSettings._fields
+    assert f[:12] == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix",
+                      "projmatrix", "sh_degree", "campos", "prefiltered", "debug")
+    s = _settings()
+    assert s.projection == "pinhole" and s.near_cull == 0.2 and s.fov_clamp == 1.3 and s.lowpass == 0.3
+    assert isinstance(GaussianRasterizer(s), torch.nn.Module)
+
+
+def test_exactly_one_of_errors_like_upstream():
+    from splatter360_b200.rasterizer import GaussianRasterizer
+    r = GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3); o = torch.ones(4, 1); c6 = torch.zeros(4, 6); col = torch.zeros(4, 3); sh = torch.zeros(4, 1, 3)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=m, means2D=m, opacities=o, cov3D_precomp=c6)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=m, means2D=m, opacities=o, shs=sh, colors_precomp=col, cov3D_precomp=c6)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m, means2D=m, opacities=o, colors_precomp=col)
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=m, means2D=m, opacities=o, colors_precomp=col, scales=torch.ones(4, 3), rotations=torch.ones(4, 4),
+          cov3D_precomp=c6)
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must fail loudly: the product path is CUDA only."""
+    from splatter360_b200.rasterizer import GaussianRasterizer
+    r = GaussianRasterizer(_settings())
+    m = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        r(means3D=m, means2D=m, opacities=torch.ones(4, 1), colors_precomp=torch.zeros(4, 3), cov3D_precomp=torch.zeros(4, 6))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        r.markVisible(m)
+
+
+def test_bad_projection_and_erp_width():
+    from splatter360_b200 import rasterizer
+    with pytest.raises(ValueError):
+        rasterizer._make_view(_settings(projection="fisheye"), 1, 0, torch.device("cpu"))
+    with pytest.raises(ValueError):
+        rasterizer._make_view(_settings(projection="erp", image_width=40), 1, 0, torch.device("cpu"))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under splatter360_b200/ may import it."""
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "splatter360_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_shard_views_partition():
+    from splatter360_b200.parallel import shard_views
+    for n in (0, 1, 7, 8, 32, 101):
+        for ws in (1, 2, 3, 8):
+            seen = sorted(i for r in range(ws) for i in shard_views(n, r, ws))
+            assert seen == list(range(n))
+            sizes = [len(shard_views(n, r, ws)) for r in range(ws)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_views(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, ws, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    from splatter360_b200 import parallel
+    n_views = 5
+    idx, imgs = parallel.render_views_sharded(lambda i: torch.full((3, 2, 2), float(i)), n_views)
+    local = torch.stack(imgs) if imgs else torch.zeros(0, 3, 2, 2)
+    full = parallel.gather_views(local, n_views)
+    loss = sum((img ** 2).mean() for img in imgs) if imgs else torch.zeros(())
+    total = parallel.all_reduce_loss(torch.as_tensor(loss, dtype=torch.float32))
+    g = [torch.full((4, 3), float(rank + 1)), None]
+    parallel.all_reduce_gradients(g)
+    q.put((rank, idx, full[:, 0, 0, 0].tolist(), float(total), g[0][0, 0].item()))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding_and_loss_allreduce():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]
+    for r in res:
+        assert r[2] == [0.0, 1.0, 2.0, 3.0, 4.0]          # every rank reassembles all views
+        assert abs(r[3] - (0 + 1 + 4 + 9 + 16)) < 1e-5     # loss all-reduce = single-process sum
+        assert r[4] == 3.0                                  # gradient all-reduce: 1 + 2

@@ -1,0 +1,152 @@
+"""CPU tests of the oracle itself: the plain-C restatement against the independent float64 autograd
+restatement, analytic cases, and the edge cases listed in SURVEY.md sec. 4b."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_case, oracle_kwargs, rel_l2, run_oracle
+
+
+def _torch_oracle(case, dL, **over):
+    from oracle import torch_oracle
+    kw = oracle_kwargs(case, **over)
+    m = case["means"].double().requires_grad_()
+    c = case["cov6"].double().requires_grad_()
+    o = case["opac"].double().requires_grad_()
+    s = case["shs"].double().requires_grad_()
+    col, aux = torch_oracle.render(m, c, o, shs=s, **kw)
+    (col * dL.double()).sum().backward()
+    return col.detach().numpy(), aux, dict(d_means=m.grad.numpy(), d_cov6=c.grad.numpy(), d_opac=o.grad.numpy(),
+                                           d_shs=s.grad.numpy(), d_means2D=aux["means2D"].grad.numpy())
+
+
+@pytest.mark.parametrize("mode,H,W", [("pinhole", 48, 64), ("erp", 32, 64), ("pinhole", 40, 50)])
+def test_c_oracle_matches_autograd_oracle(mode, H, W):
+    case = make_case(120, mode, H, W, seed=5)
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(2))
+    o = run_oracle(case, dL=dL)
+    col, aux, g = _torch_oracle(case, dL)
+    assert rel_l2(o["color"], col) < 2e-6
+    assert np.array_equal(o["n_contrib"].astype(np.int64), aux["n_contrib"].numpy())
+    for k, v in g.items():
+        assert rel_l2(o[k], v) < 5e-6, k
+
+
+def test_sh_basis_is_orthonormal_up_to_degree_4():
+    """Pins the 25 real-SH constants (incl. the degree-4 band the fork is assumed to evaluate)."""
+    from oracle.torch_oracle import sh_basis
+    n = 200
+    # Gauss-Legendre in cos(theta) x uniform in phi integrates degree <= 8 polynomials exactly
+    xs, ws = np.polynomial.legendre.leggauss(16)
+    phi = (np.arange(n) + 0.5) * 2 * math.pi / n
+    z = np.repeat(xs, n); w = np.repeat(ws, n) * (2 * math.pi / n)
+    r = np.sqrt(1 - z * z)
+    d = torch.tensor(np.stack([r * np.cos(np.tile(phi, 16)), r * np.sin(np.tile(phi, 16)), z], -1))
+    B = sh_basis(4, d).numpy()
+    gram = (B * w[:, None]).T @ B
+    assert np.allclose(gram, np.eye(25), atol=1e-9)
+
+
+def test_single_gaussian_analytic_peak():
+    """On-axis isotropic Gaussian: peak alpha = opacity, colour = C0*sh0 + 0.5, footprint = Sigma2D + 0.3 I
+    (recipe of /root/reference/src/scripts/test_splatter.py:38-65)."""
+    import oracle
+    H = W = 65
+    means = np.array([[0, 0, 4.0]], np.float32)
+    s2 = 0.05 ** 2
+    cov6 = np.array([[s2, 0, 0, s2, 0, s2]], np.float32)
+    sh = np.zeros((1, 25, 3), np.float32); sh[0, 0] = [1.0, 0.5, -0.2]
+    view = np.eye(4, dtype=np.float32)
+    from splatter360_b200 import camera
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None]
+    cam = camera.pinhole_camera(torch.eye(4)[None], K, torch.tensor([1.0]), torch.tensor([100.0]))
+    o = oracle.render(means, cov6, np.array([0.8], np.float32), shs=sh, H=H, W=W, view=cam.view_matrix[0].numpy(),
+                      proj=cam.full_projection[0].numpy(), campos=np.zeros(3, np.float32), tanfovx=1.0, tanfovy=1.0,
+                      sh_degree=4)
+    # centre pixel: ndc 0 -> pixel (W-1)/2 = 32
+    np.testing.assert_allclose(o["xy"][0], [32.0, 32.0], atol=1e-4)
+    rgb = 0.28209479 * sh[0, 0] + 0.5
+    np.testing.assert_allclose(o["color"][:, 32, 32], 0.8 * rgb, rtol=1e-5)
+    fx = W / 2.0
+    var = (fx / 4.0) ** 2 * s2 + 0.3
+    expect = 0.8 * math.exp(-0.5 * 1.0 / var) * rgb[0]
+    np.testing.assert_allclose(o["color"][0, 32, 33], expect, rtol=1e-4)
+    np.testing.assert_allclose(o["color"][0, 33, 32], expect, rtol=1e-4)
+
+
+def test_edge_cases_cull_and_thresholds():
+    import oracle
+    H, W = 32, 48
+    from splatter360_b200 import camera
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None]
+    cam = camera.pinhole_camera(torch.eye(4)[None], K, torch.tensor([1.0]), torch.tensor([100.0]))
+    means = np.array([[0, 0, -1.0],      # behind the camera
+                      [0, 0, 0.2],       # exactly at the near-cull plane (z <= 0.2 is culled)
+                      [0, 0, 0.2001],    # just in front of it
+                      [50, 0, 3.0],      # far off screen (rect area 0)
+                      [0, 0, 3.0]], np.float32)   # visible, but opacity below 1/255
+    cov6 = np.tile(np.array([1e-3, 0, 0, 1e-3, 0, 1e-3], np.float32), (5, 1))
+    op = np.array([0.9, 0.9, 0.9, 0.9, 0.003], np.float32)
+    col = np.ones((5, 3), np.float32)
+    kw = dict(H=H, W=W, view=cam.view_matrix[0].numpy(), proj=cam.full_projection[0].numpy(), campos=np.zeros(3, np.float32),
+              bg=(0.2, 0.3, 0.4))
+    o = oracle.render(means, cov6, op, colors=col, **kw)
+    assert list(o["radii"] > 0) == [False, False, True, False, True]
+    o2 = oracle.render(means[[0, 1, 3, 4]], cov6[:4], op[[0, 1, 3, 4]], colors=col[:4], **kw)
+    # nothing contributes: image is the background, transmittance 1, no contributors
+    assert np.allclose(o2["color"], np.array([0.2, 0.3, 0.4])[:, None, None])
+    assert (o2["n_contrib"] == 0).all() and np.allclose(o2["final_T"], 1.0)
+
+
+def test_equal_depth_ties_keep_index_order():
+    import oracle
+    from splatter360_b200 import camera
+    H = W = 32
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None]
+    cam = camera.pinhole_camera(torch.eye(4)[None], K, torch.tensor([1.0]), torch.tensor([100.0]))
+    means = np.array([[0, 0, 3.0]] * 4, np.float32)
+    cov6 = np.tile(np.array([1e-2, 0, 0, 1e-2, 0, 1e-2], np.float32), (4, 1))
+    o = oracle.render(means, cov6, np.full(4, 0.5, np.float32), colors=np.eye(4, 3, dtype=np.float32), H=H, W=W,
+                      view=cam.view_matrix[0].numpy(), proj=cam.full_projection[0].numpy(), campos=np.zeros(3, np.float32))
+    r = o["tile_ranges"]
+    for t in range(r.shape[0]):
+        ids = o["inst_gid"][r[t, 0]:r[t, 1]]
+        assert list(ids) == sorted(ids)
+
+
+def test_empty_scene():
+    import oracle
+    o = oracle.render(np.zeros((0, 3), np.float32), np.zeros((0, 6), np.float32), np.zeros(0, np.float32),
+                      colors=np.zeros((0, 3), np.float32), H=20, W=36, view=np.eye(4, dtype=np.float32),
+                      proj=np.eye(4, dtype=np.float32), campos=np.zeros(3, np.float32), bg=(1, 0, 0))
+    assert o["num_rendered"] == 0 and np.allclose(o["color"][0], 1.0) and np.allclose(o["color"][1:], 0.0)
+
+
+def test_erp_jacobian_is_derivative_of_reference_projection():
+    """Appendix B2: J of the erp mode equals autograd of the reference's point->pixel map."""
+    from splatter360_b200 import camera
+    t = torch.tensor([[0.7, -0.4, 1.3], [-2.0, 0.5, -0.3]], dtype=torch.float64, requires_grad=True)
+    H, W = 512, 1024
+    J_auto = torch.stack([torch.autograd.functional.jacobian(lambda p: camera.erp_project(p, H, W), t[i]) for i in range(2)])
+    x, y, z = t.detach().unbind(-1)
+    su, sv = -W / (2 * math.pi), -H / math.pi
+    q = x * x + z * z; rho = q.sqrt(); r2 = q + y * y
+    J = torch.stack([torch.stack([su * z / q, torch.zeros_like(x), -su * x / q], -1),
+                     torch.stack([-sv * x * y / (rho * r2), sv * rho / r2, -sv * z * y / (rho * r2)], -1)], 1)
+    assert torch.allclose(J, J_auto, atol=1e-9)
+
+
+def test_erp_seam_wrap():
+    """A Gaussian straddling theta = +-pi shows up on both image edges with periodic distance."""
+    import oracle
+    H, W = 32, 64
+    means = np.array([[0.001, 0.0, -2.0]], np.float32)   # looks backwards: u ~ -0.5 / W - 0.5
+    cov6 = np.array([[0.05, 0, 0, 0.05, 0, 0.05]], np.float32)
+    o = oracle.render(means, cov6, np.array([0.9], np.float32), colors=np.ones((1, 3), np.float32), H=H, W=W,
+                      view=np.eye(4, dtype=np.float32), proj=np.eye(4, dtype=np.float32), campos=np.zeros(3, np.float32),
+                      mode="erp")
+    row = o["color"][0, H // 2]
+    assert row[0] > 0.3 and row[W - 1] > 0.3 and row[W // 2] == 0.0
+    assert abs(row[0] - row[W - 1]) < 0.05
