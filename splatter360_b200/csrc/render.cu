@@ -121,9 +121,13 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   const float Wf = (float)W, halfW = 0.5f * (float)W;
   const uint2 range = ranges[tile];
 
-  float T0 = 1.f, T1 = 1.f, Ca0 = 0.f, Ca1 = 0.f, Ca2 = 0.f, Cb0 = 0.f, Cb1 = 0.f, Cb2 = 0.f;
+  // packed state of the lane's two pixels (.x = row py0, .y = row py0 + 4); FFMA2/FMUL2/FADD2 are Blackwell's
+  // two-wide FP32 instructions
+  float2 T = make_float2(1.f, 1.f), Cr = make_float2(0.f, 0.f), Cg = Cr, Cb = Cr;
   uint32_t last0 = 0, last1 = 0;
-  bool done0 = !in0, done1 = !in1;
+  const float INF = __int_as_float(0x7f800000);
+  float amin0 = in0 ? ALPHA_MIN : INF, amin1 = in1 ? ALPHA_MIN : INF;   // +inf once the pixel is finished
+  const float2 npy = make_float2(-pyf, -(pyf + 4.f));
 
   ChunkRegs nx;
   nx.r0 = nx.r1 = nx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -133,14 +137,14 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   uint32_t gid2 = (range.x + 32 + lane < range.y) ? point_list[range.x + 32 + lane] : 0u;
 
   for (uint32_t base = range.x; base < range.y; base += 32) {
-    if (__all_sync(0xffffffffu, done0 && done1)) break;
+    if (__all_sync(0xffffffffu, amin0 == INF && amin1 == INF)) break;
     const bool valid = base + lane < range.y;
     float4 cull, ev, col;
     stage_instance(nx.r0, nx.r1, nx.r2, cull, ev, col);
     const float thr = col.w;
     const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
     s_ev[warp][lane] = ev;
-    s_col[warp][lane] = col;
+    s_col[warp][lane] = make_float4(-col.x, -col.y, -col.z, 0.f);   // negated: the loop carries -alpha
     __syncwarp();
     // keep the pipeline full: records of the next chunk, ids of the one after
     nx.gid = gid2;
@@ -158,25 +162,27 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
       mask &= mask - 1;
       const float xs = __shfl_sync(0xffffffffu, cx, k), ys = __shfl_sync(0xffffffffu, cy, k);
       const float4 e = s_ev[warp][k];
+      const float4 c = s_col[warp][k];
       float dx = xs - pxf;
       if (MODE == S360_MODE_ERP && ((hmask >> k) & 1u)) dx = wrap_dx<MODE>(dx, Wf, halfW);
-      const float dy0 = ys - pyf, dy1 = dy0 - 4.f;
-      const float u = e.y * dx;
-      const float pb = e.x * dx * dx;                            // A'dx^2
-      const float p0 = fmaf(fmaf(e.z, dy0, u), dy0, pb);         // + C'dy^2 + B'dxdy  (= power * log2 e)
-      const float p1 = fmaf(fmaf(e.z, dy1, u), dy1, pb);
-      const float al0 = fminf(ALPHA_MAX, ex2_approx(p0 + e.w)), al1 = fminf(ALPHA_MAX, ex2_approx(p1 + e.w));
-      bool ok0 = !done0 && (p0 <= 0.f) && (al0 >= ALPHA_MIN);
-      bool ok1 = !done1 && (p1 <= 0.f) && (al1 >= ALPHA_MIN);
-      const float tt0 = T0 * (1.f - al0), tt1 = T1 * (1.f - al1);
-      if (ok0 && tt0 < T_EPS) { done0 = true; ok0 = false; }
-      if (ok1 && tt1 < T_EPS) { done1 = true; ok1 = false; }
-      if (ok0 || ok1) {
-        const float4 c = s_col[warp][k];
-        const uint32_t pos = base - range.x + (uint32_t)k + 1u;
-        if (ok0) { const float w = al0 * T0; Ca0 += c.x * w; Ca1 += c.y * w; Ca2 += c.z * w; T0 = tt0; last0 = pos; }
-        if (ok1) { const float w = al1 * T1; Cb0 += c.x * w; Cb1 += c.y * w; Cb2 += c.z * w; T1 = tt1; last1 = pos; }
-      }
+      const float2 dy = __fadd2_rn(make_float2(ys, ys), npy);
+      const float u = e.y * dx, pb = e.x * dx * dx;
+      const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
+      const float2 a = __fadd2_rn(p, make_float2(e.w, e.w));          // power * log2(e) + log2(opacity)
+      const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));   // -alpha
+      // -alpha if this pixel takes the Gaussian (power <= 0, alpha >= 1/255, pixel not finished), else 0
+      float2 nae = make_float2((p.x <= 0.f && -nal0 >= amin0) ? nal0 : 0.f, (p.y <= 0.f && -nal1 >= amin1) ? nal1 : 0.f);
+      const float2 tt = __ffma2_rn(T, nae, T);                          // T (1 - alpha); == T when not taken
+      if (tt.x < T_EPS) { nae.x = 0.f; amin0 = INF; }                   // would saturate: not blended, pixel done
+      if (tt.y < T_EPS) { nae.y = 0.f; amin1 = INF; }
+      const float2 nw = __fmul2_rn(nae, T);                             // -alpha T
+      Cr = __ffma2_rn(make_float2(c.x, c.x), nw, Cr);                   // c holds -rgb
+      Cg = __ffma2_rn(make_float2(c.y, c.y), nw, Cg);
+      Cb = __ffma2_rn(make_float2(c.z, c.z), nw, Cb);
+      T = __ffma2_rn(T, nae, T);
+      const uint32_t pos = base - range.x + (uint32_t)k + 1u;
+      if (nae.x < 0.f) last0 = pos;
+      if (nae.y < 0.f) last1 = pos;
     }
     __syncwarp();
   }
@@ -184,13 +190,13 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
   if (in0) {
     const size_t pid = (size_t)py0 * W + px;
-    final_T[pid] = T0; n_contrib[pid] = last0;
-    out_color[pid] = Ca0 + T0 * b0; out_color[plane + pid] = Ca1 + T0 * b1; out_color[2 * plane + pid] = Ca2 + T0 * b2;
+    final_T[pid] = T.x; n_contrib[pid] = last0;
+    out_color[pid] = Cr.x + T.x * b0; out_color[plane + pid] = Cg.x + T.x * b1; out_color[2 * plane + pid] = Cb.x + T.x * b2;
   }
   if (in1) {
     const size_t pid = (size_t)py1 * W + px;
-    final_T[pid] = T1; n_contrib[pid] = last1;
-    out_color[pid] = Cb0 + T1 * b0; out_color[plane + pid] = Cb1 + T1 * b1; out_color[2 * plane + pid] = Cb2 + T1 * b2;
+    final_T[pid] = T.y; n_contrib[pid] = last1;
+    out_color[pid] = Cr.y + T.y * b0; out_color[plane + pid] = Cg.y + T.y * b1; out_color[2 * plane + pid] = Cb.y + T.y * b2;
   }
 }
 
@@ -228,43 +234,36 @@ __device__ __forceinline__ float warp_reduce8(float v0, float v1, float v2, floa
 
 constexpr int NACC = 9;         // colour x3, q*dx, q*dy, q*dx^2, q*dxdy, q*dy^2, q
 
-// per-pixel running state of the back-to-front pass
-struct PixB {
-  float T, T_final, bgT;
-  float ar0, ar1, ar2, lc0, lc1, lc2, last_alpha;
-  float dp0, dp1, dp2;
-  uint32_t last_contributor;
+// running state of the lane's pixel pair in the back-to-front pass, packed for FFMA2/FMUL2/FADD2
+// (.x = row py0, .y = row py0 + 4).  nar = -accum_rec, nla = -last_alpha; the colour of the previously processed
+// instance is the same for both pixels and lives in scalar registers of the kernel.
+struct PairB {
+  float2 T, bgT;
+  float2 nar0, nar1, nar2;
+  float2 nla;
+  float2 dp0, dp1, dp2;
+  uint32_t lastc0, lastc1;
 };
 
-__device__ __forceinline__ void pix_init(PixB& p, bool inside, size_t pid, size_t plane, const float* final_T,
-                                         const uint32_t* n_contrib, const float* dL, const float* bg) {
-  p.T_final = inside ? final_T[pid] : 0.f;
-  p.last_contributor = inside ? n_contrib[pid] : 0u;
-  p.dp0 = p.dp1 = p.dp2 = 0.f;
-  if (inside) { p.dp0 = dL[pid]; p.dp1 = dL[plane + pid]; p.dp2 = dL[2 * plane + pid]; }
-  p.bgT = -p.T_final * (bg[0] * p.dp0 + bg[1] * p.dp1 + bg[2] * p.dp2);
-  p.T = p.T_final;
-  p.ar0 = p.ar1 = p.ar2 = p.lc0 = p.lc1 = p.lc2 = p.last_alpha = 0.f;
+__device__ __forceinline__ void pair_init(PairB& p, bool in0, bool in1, size_t pid0, size_t pid1, size_t plane,
+                                          const float* final_T, const uint32_t* n_contrib, const float* dL,
+                                          const float* bg) {
+  const float T0 = in0 ? final_T[pid0] : 0.f, T1 = in1 ? final_T[pid1] : 0.f;
+  p.lastc0 = in0 ? n_contrib[pid0] : 0u;
+  p.lastc1 = in1 ? n_contrib[pid1] : 0u;
+  p.dp0 = make_float2(in0 ? dL[pid0] : 0.f, in1 ? dL[pid1] : 0.f);
+  p.dp1 = make_float2(in0 ? dL[plane + pid0] : 0.f, in1 ? dL[plane + pid1] : 0.f);
+  p.dp2 = make_float2(in0 ? dL[2 * plane + pid0] : 0.f, in1 ? dL[2 * plane + pid1] : 0.f);
+  const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  p.bgT = make_float2(-T0 * (b0 * p.dp0.x + b1 * p.dp1.x + b2 * p.dp2.x), -T1 * (b0 * p.dp0.y + b1 * p.dp1.y + b2 * p.dp2.y));
+  p.T = make_float2(T0, T1);
+  p.nar0 = p.nar1 = p.nar2 = p.nla = make_float2(0.f, 0.f);
 }
 
-// one (pixel, instance) term; accumulates the nine partials into v[]
-__device__ __forceinline__ void pix_term(PixB& p, float alpha, float G, float dx, float dy, const float4& c,
-                                         float* v) {
-  const float inv1ma = __frcp_rn(1.f - alpha);
-  p.T = p.T * inv1ma;
-  const float w = alpha * p.T;
-  p.ar0 = p.last_alpha * p.lc0 + (1.f - p.last_alpha) * p.ar0;
-  p.ar1 = p.last_alpha * p.lc1 + (1.f - p.last_alpha) * p.ar1;
-  p.ar2 = p.last_alpha * p.lc2 + (1.f - p.last_alpha) * p.ar2;
-  p.lc0 = c.x; p.lc1 = c.y; p.lc2 = c.z;
-  float dL_dalpha = (c.x - p.ar0) * p.dp0 + (c.y - p.ar1) * p.dp1 + (c.z - p.ar2) * p.dp2;
-  dL_dalpha = dL_dalpha * p.T + p.bgT * inv1ma;
-  p.last_alpha = alpha;
-  const float q = G * dL_dalpha;
-  const float qx = q * dx, qy = q * dy;
-  v[0] += w * p.dp0; v[1] += w * p.dp1; v[2] += w * p.dp2;
-  v[3] += qx; v[4] += qy; v[5] += qx * dx; v[6] += qx * dy; v[7] += qy * dy;
-  v[8] += q;
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 template <int MODE>
@@ -288,11 +287,12 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   const uint2 range = ranges[tile];
   const size_t plane = (size_t)H * W;
 
-  PixB P0, P1;
-  pix_init(P0, in0, (size_t)py0 * W + px, plane, final_T, n_contrib, dL_dcolor, bg);
-  pix_init(P1, in1, (size_t)py1 * W + px, plane, final_T, n_contrib, dL_dcolor, bg);
+  PairB S;
+  pair_init(S, in0, in1, (size_t)py0 * W + px, (size_t)py1 * W + px, plane, final_T, n_contrib, dL_dcolor, bg);
+  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // colour of the previously processed instance
+  const float2 npy = make_float2(-pyf, -(pyf + 4.f));
   // instances [0, todo) of this tile's list can matter to this warp's 64 pixels
-  const uint32_t todo = __reduce_max_sync(0xffffffffu, max(P0.last_contributor, P1.last_contributor));
+  const uint32_t todo = __reduce_max_sync(0xffffffffu, max(S.lastc0, S.lastc1));
   const int nchunks = (int)((todo + 31u) >> 5);
 
   ChunkRegs nx;
@@ -334,22 +334,43 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const float4 e = s_ev[warp][k];
       float dx = xs - pxf;
       if (MODE == S360_MODE_ERP && ((hmask >> k) & 1u)) dx = wrap_dx<MODE>(dx, Wf, halfW);
-      const float dy0 = ys - pyf, dy1 = dy0 - 4.f;
-      const float u = e.y * dx;
-      const float pb = e.x * dx * dx;
-      const float p0 = fmaf(fmaf(e.z, dy0, u), dy0, pb);
-      const float p1 = fmaf(fmaf(e.z, dy1, u), dy1, pb);
-      // same expression as the forward pass, so that T / (1 - alpha) undoes exactly what it applied
-      const float al0 = fminf(ALPHA_MAX, ex2_approx(p0 + e.w)), al1 = fminf(ALPHA_MAX, ex2_approx(p1 + e.w));
-      const bool ok0 = (pos < P0.last_contributor) && (p0 <= 0.f) && (al0 >= ALPHA_MIN);
-      const bool ok1 = (pos < P1.last_contributor) && (p1 <= 0.f) && (al1 >= ALPHA_MIN);
+      const float2 dy = __fadd2_rn(make_float2(ys, ys), npy);
+      const float u = e.y * dx, pb = e.x * dx * dx;
+      const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
+      // same expressions as the forward pass, so that T / (1 - alpha) undoes exactly what it applied
+      const float2 a = __fadd2_rn(p, make_float2(e.w, e.w));
+      const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));
+      const bool ok0 = (pos < S.lastc0) && (p.x <= 0.f) && (-nal0 >= ALPHA_MIN);
+      const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
       const float4 c = s_col[warp][k];
+      // A pixel that does not take this instance runs the same recurrences with alpha = 0, which only folds the
+      // pending (last_alpha, last_color) term into accum_rec early -- bit-identical to skipping it.
+      const float2 nae = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);                  // -alpha or 0
+      const float2 om = __fadd2_rn(make_float2(1.f, 1.f), nae);                            // 1 - alpha
+      const float2 inv = make_float2(rcp_approx(om.x), rcp_approx(om.y));
+      S.T = __fmul2_rn(S.T, inv);
+      const float2 nw = __fmul2_rn(nae, S.T);                                              // -alpha T
+      // accum_rec <- last_alpha * last_color + (1 - last_alpha) * accum_rec, kept negated
+      S.nar0 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc0, lc0), S.nar0), S.nar0);
+      S.nar1 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc1, lc1), S.nar1), S.nar1);
+      S.nar2 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc2, lc2), S.nar2), S.nar2);
+      lc0 = c.x; lc1 = c.y; lc2 = c.z;
+      S.nla = nae;
+      float2 dLda = __fmul2_rn(__fadd2_rn(make_float2(c.x, c.x), S.nar0), S.dp0);
+      dLda = __ffma2_rn(__fadd2_rn(make_float2(c.y, c.y), S.nar1), S.dp1, dLda);
+      dLda = __ffma2_rn(__fadd2_rn(make_float2(c.z, c.z), S.nar2), S.dp2, dLda);
+      dLda = __ffma2_rn(dLda, S.T, __fmul2_rn(S.bgT, inv));
+      float2 q = __fmul2_rn(make_float2(ex2_approx(p.x), ex2_approx(p.y)), dLda);          // G dL/dalpha
+      q.x = ok0 ? q.x : 0.f; q.y = ok1 ? q.y : 0.f;
+      const float2 dx2 = make_float2(dx, dx);
+      const float2 qx = __fmul2_rn(q, dx2), qy = __fmul2_rn(q, dy);
+      const float2 t0 = __fmul2_rn(nw, S.dp0), t1 = __fmul2_rn(nw, S.dp1), t2 = __fmul2_rn(nw, S.dp2);
+      const float2 t5 = __fmul2_rn(qx, dx2), t6 = __fmul2_rn(qx, dy), t7 = __fmul2_rn(qy, dy);
       float v[NACC];
-#pragma unroll
-      for (int i = 0; i < NACC; i++) v[i] = 0.f;
-      if (ok1) pix_term(P1, al1, ex2_approx(p1), dx, dy1, c, v);
-      if (ok0) pix_term(P0, al0, ex2_approx(p0), dx, dy0, c, v);
+      v[0] = -(t0.x + t0.y); v[1] = -(t1.x + t1.y); v[2] = -(t2.x + t2.y);
+      v[3] = qx.x + qx.y; v[4] = qy.x + qy.y; v[5] = t5.x + t5.y; v[6] = t6.x + t6.y; v[7] = t7.x + t7.y;
+      v[8] = q.x + q.y;
       const float s8 = warp_reduce8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], lane);
       float v8 = v[8];
       v8 += __shfl_xor_sync(0xffffffffu, v8, 16);
