@@ -112,6 +112,16 @@ int s360_forward_preprocess(
     void* scratch,               /* s360_preprocess_scratch_bytes(P)                           */
     void* stream);
 
+/* The same stage in two halves, so that a host that needs the instance count can read
+ * counters->num_rendered (final after s360_forward_project) while s360_forward_order is still running:
+ *   s360_forward_project : K1 only -> geom, radii, counters (scratch keeps the unsorted depth keys)
+ *   s360_forward_order   : depth sort + scan -> depth_order, inst_offsets (same scratch, same stream) */
+int s360_forward_project(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
+                         const float* shs, const float* colors_precomp, void* geom, int32_t* radii,
+                         S360Counters* counters, void* scratch, void* stream);
+int s360_forward_order(const S360View* view, const void* geom, uint32_t* depth_order, uint32_t* inst_offsets,
+                       S360Counters* counters, void* scratch, void* stream);
+
 /* ---- forward, stage 2 (replaces duplicateWithKeys + SortPairs + identifyTileRanges + renderCUDA) */
 int s360_forward_render(
     const S360View* view,        /* host */

@@ -19,7 +19,7 @@ EXPORTS = [
     "s360_abi_version", "s360_error_string", "s360_launch_count",
     "s360_geom_bytes", "s360_preprocess_scratch_bytes", "s360_binning_scratch_bytes",
     "s360_image_bytes", "s360_backward_scratch_bytes",
-    "s360_forward_preprocess", "s360_forward_render", "s360_backward", "s360_mark_visible",
+    "s360_forward_preprocess", "s360_forward_project", "s360_forward_order", "s360_forward_render", "s360_backward", "s360_mark_visible",
     "s360_debug_unpack_geom", "s360_debug_unpack_image",
     "s360_profile_enable", "s360_profile_read",
 ]
@@ -74,6 +74,10 @@ def load() -> ctypes.CDLL:
     vp = c_void_p
     lib.s360_forward_preprocess.restype = c_int
     lib.s360_forward_preprocess.argtypes = [ctypes.POINTER(S360View)] + [vp] * 12
+    lib.s360_forward_project.restype = c_int
+    lib.s360_forward_project.argtypes = [ctypes.POINTER(S360View)] + [vp] * 10
+    lib.s360_forward_order.restype = c_int
+    lib.s360_forward_order.argtypes = [ctypes.POINTER(S360View)] + [vp] * 6
     lib.s360_forward_render.restype = c_int
     lib.s360_forward_render.argtypes = [ctypes.POINTER(S360View), vp, vp, vp, vp, c_int64, vp, vp, vp, vp, vp]
     lib.s360_backward.restype = c_int

@@ -42,7 +42,7 @@ static size_t pre_scratch_carve(void* buf, int P, PreScratch* out) {
   char* p = (char*)buf;
   const size_t arr = align_up((size_t)(P > 0 ? P : 1) * 4, 256);
   const size_t rad = radix_scratch_bytes(P);
-  const size_t sums = align_up(((size_t)(P > 0 ? P : 1) / 2048 + 2) * 4, 256);
+  const size_t sums = align_up(((size_t)(P > 0 ? P : 1) / 2048 + 4) * 4, 256);
   if (out) {
     out->keys_a = (uint32_t*)p; out->ids_a = (uint32_t*)(p + arr);
     out->keys_b = (uint32_t*)(p + 2 * arr); out->ids_b = (uint32_t*)(p + 3 * arr);
@@ -131,13 +131,12 @@ size_t s360_binning_scratch_bytes(int64_t cap, int32_t H, int32_t W) { return bi
 size_t s360_image_bytes(int32_t H, int32_t W) { return image_bytes(H, W); }
 size_t s360_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float), 256); }
 
-int s360_forward_preprocess(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
-                            const float* shs, const float* colors_precomp, void* geom, int32_t* radii,
-                            uint32_t* depth_order, uint32_t* inst_offsets, S360Counters* counters, void* scratch,
-                            void* stream) {
+int s360_forward_project(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
+                         const float* shs, const float* colors_precomp, void* geom, int32_t* radii,
+                         S360Counters* counters, void* scratch, void* stream) {
   if (!view_ok(view) || !counters || !geom || !scratch) return S360_ERR_BAD_ARGUMENT;
   if (view->P > 0 && (shs == nullptr) == (colors_precomp == nullptr)) return S360_ERR_BAD_ARGUMENT;
-  if (view->P > 0 && (!means3D || !cov3D || !opacities || !radii || !depth_order || !inst_offsets)) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (!means3D || !cov3D || !opacities || !radii)) return S360_ERR_BAD_ARGUMENT;
   if (shs && view->M < (view->sh_degree < view->max_sh_degree ? (view->sh_degree + 1) * (view->sh_degree + 1)
                                                                 : (view->max_sh_degree + 1) * (view->max_sh_degree + 1)))
     return S360_ERR_BAD_ARGUMENT;
@@ -148,20 +147,35 @@ int s360_forward_preprocess(const S360View* view, const float* means3D, const fl
   GeomState g = carve_geom(geom, P > 0 ? P : 1);
   PreScratch s;
   pre_scratch_carve(scratch, P, &s);
-  { StageTimer t(S360_STAGE_PREPROCESS, st);
-    rc = launch_preprocess(*view, means3D, cov3D, opacities, shs, colors_precomp, g, radii, s.keys_a, s.ids_a, counters, st); }
-  if (rc) return rc;
-  int in_b = 0;
+  StageTimer t(S360_STAGE_PREPROCESS, st);
+  return launch_preprocess(*view, means3D, cov3D, opacities, shs, colors_precomp, g, radii, s.keys_a, s.ids_a, counters, st);
+}
+
+int s360_forward_order(const S360View* view, const void* geom, uint32_t* depth_order, uint32_t* inst_offsets,
+                       S360Counters* counters, void* scratch, void* stream) {
+  if (!view_ok(view) || !counters || !geom || !scratch) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (!depth_order || !inst_offsets)) return S360_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = view->P;
+  GeomState g = carve_geom(const_cast<void*>(geom), P > 0 ? P : 1);
+  PreScratch s;
+  pre_scratch_carve(scratch, P, &s);
+  int rc, in_b = 0;
   { StageTimer t(S360_STAGE_DEPTH_SORT, st);
-    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, P, nullptr, 32, s.radix, st, &in_b, false);
-    if (rc) return rc;
-    const uint32_t* sorted_ids = in_b ? s.ids_b : s.ids_a;
-    if (P > 0) {
-      rc = (int)cudaMemcpyAsync(depth_order, sorted_ids, (size_t)P * 4, cudaMemcpyDeviceToDevice, st);
-      if (rc) return rc;
-    } }
+    // the last of the four passes writes the sorted ids straight into depth_order
+    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, P, nullptr, 32, s.radix, st, &in_b, false, depth_order);
+    if (rc) return rc; }
   StageTimer t(S360_STAGE_SCAN, st);
   return launch_scan_offsets(*view, g, depth_order, inst_offsets, counters, s.block_sums, st);
+}
+
+int s360_forward_preprocess(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
+                            const float* shs, const float* colors_precomp, void* geom, int32_t* radii,
+                            uint32_t* depth_order, uint32_t* inst_offsets, S360Counters* counters, void* scratch,
+                            void* stream) {
+  int rc = s360_forward_project(view, means3D, cov3D, opacities, shs, colors_precomp, geom, radii, counters, scratch, stream);
+  if (rc) return rc;
+  return s360_forward_order(view, geom, depth_order, inst_offsets, counters, scratch, stream);
 }
 
 int s360_forward_render(const S360View* view, const void* geom, const uint32_t* depth_order,

@@ -193,7 +193,7 @@ size_t radix_scratch_bytes(int64_t n) {
 // hist_ready: the caller already filled hist[pass][256] (and the scratch was zeroed before that)
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n,
                      const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b,
-                     bool hist_ready) {
+                     bool hist_ready, uint32_t* vals_final) {
   *result_in_b = 0;
   if (n <= 0 || nbits <= 0) return 0;
   const int passes = (nbits + 7) / 8;
@@ -209,7 +209,8 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   }
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   for (int p = 0; p < passes; p++) {
-    rs_onesweep_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vo, n, n_dev, 8 * p, hist + p * RS_BINS,
+    uint32_t* vdst = (vals_final != nullptr && p == passes - 1) ? vals_final : vo;   // last pass may write elsewhere
+    rs_onesweep_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vdst, n, n_dev, 8 * p, hist + p * RS_BINS,
                                                        status + (size_t)p * nblocks * RS_BINS, counters + p);
     count_launch();
     uint32_t* t = ki; ki = ko; ko = t;
@@ -230,67 +231,24 @@ uint32_t* radix_prepare_hist(void* scratch, int64_t n, int nbits, cudaStream_t s
 // exclusive scan of tiles-touched in depth order (K2).  2048 Gaussians per block.
 __device__ __forceinline__ uint32_t rect_tiles(uint2 r) { return (r.x >> 16) * (r.y >> 16); }
 
-__global__ void __launch_bounds__(RS_THREADS)
-scan_block_sums_kernel(int P, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
-                       uint32_t* __restrict__ block_sums) {
-  __shared__ uint32_t s_w[RS_WARPS];
-  uint32_t s = 0;
-  const int base = blockIdx.x * RS_TILE;
-#pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
-    const int j = base + i * RS_THREADS + threadIdx.x;
-    if (j < P) s += rect_tiles(rect[order[j]]);
-  }
-  s = __reduce_add_sync(0xffffffffu, s);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; w++) t += s_w[w];
-    block_sums[blockIdx.x] = t;
-  }
-}
+constexpr int SC_ITEMS = 8, SC_TILE = RS_THREADS * SC_ITEMS;
 
-__global__ void __launch_bounds__(1024)
-scan_sums_kernel(uint32_t* __restrict__ block_sums, int nblocks, S360Counters* counters) {
-  __shared__ uint32_t s_w[32];
-  __shared__ uint32_t s_carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  for (int base = 0; base < nblocks; base += 1024) {
-    const int i = base + threadIdx.x;
-    const uint32_t x = i < nblocks ? block_sums[i] : 0u;
-    uint32_t incl = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; w++) woff += s_w[w];
-    const uint32_t carry = s_carry;
-    if (i < nblocks) block_sums[i] = carry + woff + incl - x;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + woff + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { counters->num_rendered = s_carry; counters->overflow = 0; }
-}
-
+// Single-pass chained scan (decoupled look-back): block b publishes its sum, adds the sums of its predecessors
+// until it meets an inclusive prefix, and writes the exclusive offsets of its 2048 Gaussians.
+// status: [nblocks] zero on entry; counter: zero on entry.
 __global__ void __launch_bounds__(RS_THREADS)
-scan_write_offsets_kernel(int P, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
-                          const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ offsets) {
+scan_offsets_kernel(int P, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
+                    uint32_t* __restrict__ offsets, uint32_t* status, uint32_t* counter, S360Counters* counters) {
   __shared__ uint32_t s_w[RS_WARPS];
-  // thread t owns the 8 consecutive items [base + 8t, base + 8t + 8)
-  const int base = blockIdx.x * RS_TILE + threadIdx.x * RS_ITEMS;
-  uint32_t c[RS_ITEMS];
+  __shared__ uint32_t s_bid, s_excl;
+  if (threadIdx.x == 0) s_bid = atomicAdd(counter, 1u);
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  const int base = (int)bid * SC_TILE + threadIdx.x * SC_ITEMS;   // thread t owns 8 consecutive items
+  uint32_t c[SC_ITEMS];
   uint32_t s = 0;
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
+  for (int i = 0; i < SC_ITEMS; i++) {
     const int j = base + i;
     c[i] = j < P ? rect_tiles(rect[order[j]]) : 0u;
     s += c[i];
@@ -304,25 +262,65 @@ scan_write_offsets_kernel(int P, const uint2* __restrict__ rect, const uint32_t*
   }
   if (lane == 31) s_w[warp] = incl;
   __syncthreads();
-  uint32_t woff = 0;
+  uint32_t woff = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < RS_WARPS; w++) woff += (w < warp) ? s_w[w] : 0u;
-  uint32_t run = block_sums[blockIdx.x] + woff + incl - s;
+  for (int w = 0; w < RS_WARPS; w++) { woff += (w < warp) ? s_w[w] : 0u; total += s_w[w]; }
+  if (warp == 0) {
+    // warp-wide look-back: 32 predecessors are inspected per step
+    volatile uint32_t* vs = status;
+    uint32_t excl = 0;
+    if (bid == 0) {
+      if (lane == 0) vs[0] = total | ST_PREFIX;
+    } else {
+      if (lane == 0) vs[bid] = total | ST_AGG;
+      int64_t hi = (int64_t)bid - 1;   // nearest predecessor not yet accounted for
+      while (true) {
+        const int64_t j = hi - lane;
+        uint32_t sv = ST_PREFIX;        // lanes before block 0 behave like an empty inclusive prefix
+        if (j >= 0) sv = vs[j];
+        const uint32_t flag = sv & ~ST_MASK;
+        const unsigned notready = __ballot_sync(0xffffffffu, flag == 0u);
+        const unsigned isprefix = __ballot_sync(0xffffffffu, flag == ST_PREFIX);
+        // usable lanes: those nearer than the first not-ready lane, up to and including the first prefix
+        const int first_nr = notready ? __ffs(notready) - 1 : 32;
+        const int first_px = isprefix ? __ffs(isprefix) - 1 : 32;
+        const int upto = first_px < first_nr ? first_px + 1 : first_nr;   // number of lanes to add
+        const uint32_t add = (lane < upto) ? (sv & ST_MASK) : 0u;
+        excl += __reduce_add_sync(0xffffffffu, add);
+        if (first_px < first_nr) break;
+        hi -= upto;                     // upto == 0 just spins on the same window
+      }
+      if (lane == 0) vs[bid] = (excl + total) | ST_PREFIX;
+    }
+    if (lane == 0) {
+      s_excl = excl;
+      if ((int)bid == (P + SC_TILE - 1) / SC_TILE - 1) { counters->num_rendered = excl + total; counters->overflow = 0; }
+    }
+  }
+  __syncthreads();
+  uint32_t run = s_excl + woff + incl - s;
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
+  for (int i = 0; i < SC_ITEMS; i++) {
     const int j = base + i;
     if (j < P) offsets[j] = run;
     run += c[i];
   }
 }
 
+__global__ void scan_empty_kernel(S360Counters* counters) { counters->num_rendered = 0; counters->overflow = 0; }
+
 int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_order, uint32_t* offsets,
                         S360Counters* counters, uint32_t* block_sums, cudaStream_t st) {
-  const int nblocks = rs_blocks(v.P > 0 ? v.P : 1);
-  if (v.P > 0) scan_block_sums_kernel<<<nblocks, RS_THREADS, 0, st>>>(v.P, g.rect, depth_order, block_sums);
-  scan_sums_kernel<<<1, 1024, 0, st>>>(block_sums, v.P > 0 ? nblocks : 0, counters);
-  if (v.P > 0) scan_write_offsets_kernel<<<nblocks, RS_THREADS, 0, st>>>(v.P, g.rect, depth_order, block_sums, offsets);
-  count_launch(3);
+  // block_sums scratch: [counter][status nblocks]; instance totals stay below 2^30 (status word payload)
+  const int nblocks = (v.P + SC_TILE - 1) / SC_TILE;
+  if (v.P == 0) {
+    scan_empty_kernel<<<1, 1, 0, st>>>(counters);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  cudaMemsetAsync(block_sums, 0, (size_t)(nblocks + 1) * sizeof(uint32_t), st);
+  scan_offsets_kernel<<<nblocks, RS_THREADS, 0, st>>>(v.P, g.rect, depth_order, offsets, block_sums + 1, block_sums, counters);
+  count_launch();
   return (int)cudaGetLastError();
 }
 

@@ -280,7 +280,7 @@ size_t radix_scratch_bytes(int64_t n);
 uint32_t* radix_prepare_hist(void* scratch, int64_t n, int nbits, cudaStream_t st);
 int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n,
                      const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b,
-                     bool hist_ready);
+                     bool hist_ready, uint32_t* vals_final = nullptr);
 
 int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_order, uint32_t* offsets,
                         S360Counters* counters, uint32_t* block_sums, cudaStream_t st);

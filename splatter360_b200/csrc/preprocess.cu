@@ -39,6 +39,7 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
   }
   bool upstream_visible = false;
   bool want_color = false;
+  uint32_t my_tiles = 0;
   float px = 0.f, py = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, op = 0.f, hx = 0.f, hy = 0.f, sortkey = 0.f;
   float mx = 0.f, my = 0.f, mz = 0.f;
   uint8_t cl = 0;
@@ -120,6 +121,7 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
         if (nx * ny > 0) {
           rect = make_uint2(((uint32_t)xmin & 0xffffu) | ((uint32_t)nx << 16), (uint32_t)ymin | ((uint32_t)ny << 16));
           key = __float_as_uint(sortkey);
+          my_tiles = (uint32_t)(nx * ny);
         }
         want_color = true;
         cl = (g.clampx ? 8 : 0) | (g.clampy ? 16 : 0);
@@ -130,8 +132,24 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     depth_keys[idx] = key;
     ids[idx] = (uint32_t)idx;
   }
-  const unsigned m = __ballot_sync(0xffffffffu, upstream_visible);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters->num_visible, (uint32_t)__popc(m));
+  // block totals -> one atomic each.  The instance total is known here already (the scan only orders it), which
+  // lets the host size the instance buffers while the depth sort is still running.
+  {
+    __shared__ uint32_t s_cnt[2];
+    if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
+    __syncthreads();
+    const unsigned m = __ballot_sync(0xffffffffu, upstream_visible);
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, my_tiles);
+    if ((threadIdx.x & 31) == 0) {
+      if (m) atomicAdd(&s_cnt[0], (uint32_t)__popc(m));
+      if (wsum) atomicAdd(&s_cnt[1], wsum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_cnt[0]) atomicAdd(&counters->num_visible, s_cnt[0]);
+      if (s_cnt[1]) atomicAdd(&counters->num_rendered, s_cnt[1]);
+    }
+  }
 
   // ---- colour: SH block staged in shared memory (TMA bulk copy; coalesced fallback for odd tails)
   float col[3] = {0.f, 0.f, 0.f};

@@ -110,6 +110,19 @@ def build_covariance_6(scales: Tensor, rotations: Tensor, scale_modifier: float 
     return torch.stack([cov[:, 0, 0], cov[:, 0, 1], cov[:, 0, 2], cov[:, 1, 1], cov[:, 1, 2], cov[:, 2, 2]], -1)
 
 
+_readers = {}
+
+
+def _count_reader(device):
+    """Per-device (pinned 16-byte buffer, side stream, event) used to read S360Counters back early."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    r = _readers.get(key)
+    if r is None:
+        r = (torch.empty(4, dtype=torch.int32).pin_memory(), torch.cuda.Stream(device=device), torch.cuda.Event())
+        _readers[key] = r
+    return r
+
+
 class ForwardState(NamedTuple):
     """Buffers kept from forward to backward (all caller-owned torch tensors)."""
     geom: Tensor
@@ -140,12 +153,23 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
         offsets = torch.empty(max(P, 1), dtype=torch.int32, device=device)
         counters = torch.empty(4, dtype=torch.int32, device=device)
         st = _stream_ptr()
-        _lib.check(lib.s360_forward_preprocess(
+        # K1 fixes the instance count; it is read back over a side stream while the depth sort and scan run, so
+        # the data-dependent allocation below does not leave the GPU idle
+        _lib.check(lib.s360_forward_project(
             ctypes.byref(view), _ptr(means3D), _ptr(cov6), _ptr(opacities), _ptr(shs), _ptr(colors),
-            _ptr(geom), _ptr(radii), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
-        # the instance count is data dependent: one 16-byte read sizes the instance buffers exactly
-        cnt = counters.cpu()
-        N, nvis = int(cnt[0].item()) & 0xFFFFFFFF, int(cnt[2].item()) & 0xFFFFFFFF
+            _ptr(geom), _ptr(radii), _ptr(counters), _ptr(pre_scratch), st))
+        host_counts, side, ready = _count_reader(device)
+        ready.record(torch.cuda.current_stream())
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            host_counts.copy_(counters, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        counters.record_stream(side)
+        _lib.check(lib.s360_forward_order(
+            ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
+        done.synchronize()
+        N, nvis = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
         cap = max(N, 1)
         point_list = torch.empty(cap, dtype=torch.int32, device=device)
         bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(cap, H, W), **u8)
