@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S360_ABI_VERSION 1
+#define S360_ABI_VERSION 2
 
 #define S360_MODE_PINHOLE 0 /* upstream semantics                     */
 #define S360_MODE_ERP 1     /* native equirectangular splatting      */
@@ -69,6 +69,11 @@ typedef struct S360View {
   float fov_clamp;       /* 1.3 : |x/z| clamp factor inside J (pinhole)                      */
   float lowpass;         /* 0.3 : added to the cov2D diagonal                                */
   float pole_eps;        /* erp : horizontal radius clamp rho >= pole_eps * r                */
+  float scene_scale;     /* means *= s, cov3D *= s^2 on load (the reference's 1/near rescale,
+                            cuda_splatting.py:64-71); gradients are returned w.r.t. the unscaled inputs */
+  int32_t sh_layout;     /* 0: shs[P,M,3] (rasterizer API)   1: [P,3,M] (reference's harmonics layout) */
+  int32_t cov_layout;    /* 0: cov3D[P,6]                     1: [P,3,3] (upper triangle read / written) */
+  int32_t reserved0;
   const float* viewmatrix; /* [16] settings.viewmatrix  (p_view = [x y z 1] . V, row-major)  */
   const float* projmatrix; /* [16] settings.projmatrix  (unused in erp mode)                 */
   const float* campos;     /* [3]  settings.campos                                           */

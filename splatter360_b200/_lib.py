@@ -36,6 +36,7 @@ class S360View(ctypes.Structure):
         ("max_sh_degree", c_int32), ("tight_bbox", c_int32),
         ("tanfovx", c_float), ("tanfovy", c_float), ("near_cull", c_float),
         ("fov_clamp", c_float), ("lowpass", c_float), ("pole_eps", c_float),
+        ("scene_scale", c_float), ("sh_layout", c_int32), ("cov_layout", c_int32), ("reserved0", c_int32),
         ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p), ("bg", c_void_p),
     ]
 
@@ -92,7 +93,7 @@ def load() -> ctypes.CDLL:
     lib.s360_profile_enable.argtypes = [c_int]
     lib.s360_profile_read.restype = c_int
     lib.s360_profile_read.argtypes = [vp, vp, c_int]
-    if lib.s360_abi_version() != 1:
+    if lib.s360_abi_version() != 2:
         raise ImportError("libsplatter360.so ABI version mismatch")
     _lib = lib
     return lib

@@ -80,7 +80,8 @@ static int tile_bits(int H, int W) {
 
 static bool view_ok(const S360View* v) {
   return v && v->P >= 0 && v->image_height >= 0 && v->image_width >= 0 &&
-         (v->mode == S360_MODE_PINHOLE || v->mode == S360_MODE_ERP) && v->viewmatrix && v->campos && v->bg &&
+         (v->mode == S360_MODE_PINHOLE || v->mode == S360_MODE_ERP) && v->scene_scale > 0.f &&
+         (v->sh_layout == 0 || v->sh_layout == 1) && (v->cov_layout == 0 || v->cov_layout == 1) && v->viewmatrix && v->campos && v->bg &&
          (v->mode == S360_MODE_ERP || v->projmatrix) &&
          (v->mode != S360_MODE_ERP || v->image_width % TILE == 0) &&
          ((v->image_width + TILE - 1) / TILE) < 32768 && ((v->image_height + TILE - 1) / TILE) < 65536;

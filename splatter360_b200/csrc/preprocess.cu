@@ -11,6 +11,32 @@ namespace s360 {
 
 constexpr int PRE_THREADS = 128;
 
+// covariance in: [P,6] (xx,xy,xz,yy,yz,zz) or the reference's [P,3,3] (upper triangle is read,
+// cuda_splatting.py:115,123), multiplied by scene_scale^2
+__device__ __forceinline__ void load_cov6(const S360View& v, const float* __restrict__ cov, int idx, float* cv) {
+  const float s2 = v.scene_scale * v.scene_scale;
+  if (v.cov_layout == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) cv[k] = cov[6 * (size_t)idx + k] * s2;
+  } else {
+    const float* c = cov + 9 * (size_t)idx;
+    cv[0] = c[0] * s2; cv[1] = c[1] * s2; cv[2] = c[2] * s2; cv[3] = c[4] * s2; cv[4] = c[5] * s2; cv[5] = c[8] * s2;
+  }
+}
+// gradient out in the same layout; for [P,3,3] only the upper triangle carries gradient, exactly like autograd
+// through the reference's triu gather
+__device__ __forceinline__ void store_dcov(const S360View& v, float* __restrict__ d_cov, int idx, const float* g, float s2) {
+  if (v.cov_layout == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) d_cov[6 * (size_t)idx + k] = g[k] * s2;
+  } else {
+    float* d = d_cov + 9 * (size_t)idx;
+    d[0] = g[0] * s2; d[1] = g[1] * s2; d[2] = g[2] * s2;
+    d[3] = 0.f;       d[4] = g[3] * s2; d[5] = g[4] * s2;
+    d[6] = 0.f;       d[7] = 0.f;       d[8] = g[5] * s2;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
@@ -46,13 +72,13 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
   Cam cam;
   if (idx < P) {
     load_cam(v, cam, MODE == S360_MODE_PINHOLE);
-    mx = means[3 * idx]; my = means[3 * idx + 1]; mz = means[3 * idx + 2];
+    const float sc = v.scene_scale;   // reference's 1/near rescale (cuda_splatting.py:64-71), folded into the load
+    mx = means[3 * idx] * sc; my = means[3 * idx + 1] * sc; mz = means[3 * idx + 2] * sc;
     int radius = 0;
     uint2 rect = make_uint2(0u, 0u);
     uint32_t key = 0xFFFFFFFFu;
     float cv[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) cv[k] = cov3D[6 * idx + k];
+    load_cov6(v, cov3D, idx, cv);
     Geo g;
     geo_compute<MODE>(v, cam.V, mx, my, mz, cv, g);
     bool alive;
@@ -175,13 +201,14 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
         const int deg = min(v.sh_degree, v.max_sh_degree);
         const int n = sh_basis(deg, dx, dy, dz, b);
         const float* sh = s_sh + threadIdx.x * row;
+        const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;   // [P,M,3] or the reference's [P,3,M]
         float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < 25; k++) {
           if (k < n) {
-            acc[0] += b[k] * sh[3 * k];
-            acc[1] += b[k] * sh[3 * k + 1];
-            acc[2] += b[k] * sh[3 * k + 2];
+            acc[0] += b[k] * sh[ks * k];
+            acc[1] += b[k] * sh[ks * k + cs];
+            acc[2] += b[k] * sh[ks * k + 2 * cs];
           }
         }
 #pragma unroll
@@ -271,10 +298,10 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     const float a2 = acc[(size_t)idx * ACC_STRIDE + 8];
     dcol[0] = a0.x; dcol[1] = a0.y; dcol[2] = a0.z;
     dop = a2;
-    const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
+    const float sc = v.scene_scale;
+    const float mx = means[3 * idx] * sc, my = means[3 * idx + 1] * sc, mz = means[3 * idx + 2] * sc;
     float cv[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) cv[k] = cov3D[6 * idx + k];
+    load_cov6(v, cov3D, idx, cv);
     Geo g;
     geo_compute<MODE>(v, V, mx, my, mz, cv, g);
     const float denom = g.a * g.c - g.b * g.b;
@@ -368,16 +395,17 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
       const float drgb[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
       if (bulk_ok) mbar_wait(&s_bar, 0);
       float* sh = s_sh + threadIdx.x * row;      // this thread's row: read SH, overwrite with dL/dSH
+      const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
       float ddir[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int k = 0; k < 25; k++) {
         if (k < n) {
-          const float s = sh[3 * k] * drgb[0] + sh[3 * k + 1] * drgb[1] + sh[3 * k + 2] * drgb[2];
+          const float s = sh[ks * k] * drgb[0] + sh[ks * k + cs] * drgb[1] + sh[ks * k + 2 * cs] * drgb[2];
           ddir[0] += bx[k] * s; ddir[1] += by[k] * s; ddir[2] += bz[k] * s;
-          sh[3 * k] = b[k] * drgb[0]; sh[3 * k + 1] = b[k] * drgb[1]; sh[3 * k + 2] = b[k] * drgb[2];
+          sh[ks * k] = b[k] * drgb[0]; sh[ks * k + cs] = b[k] * drgb[1]; sh[ks * k + 2 * cs] = b[k] * drgb[2];
         }
       }
-      for (int k = 3 * n; k < row; k++) sh[k] = 0.f;
+      for (int k = n; k < v.M; k++) { sh[ks * k] = 0.f; sh[ks * k + cs] = 0.f; sh[ks * k + 2 * cs] = 0.f; }
       const float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
       dm[0] += (ddir[0] - dx * dot) * inv;
       dm[1] += (ddir[1] - dy * dot) * inv;
@@ -400,11 +428,12 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     }
   }
   if (idx >= P) return;
+  // gradients w.r.t. the caller's (unscaled) means / covariances
+  const float gsc = v.scene_scale;
 #pragma unroll
-  for (int k = 0; k < 3; k++) d_means[3 * idx + k] = dm[k];
+  for (int k = 0; k < 3; k++) d_means[3 * idx + k] = dm[k] * gsc;
   d_means2D[3 * idx] = dm2[0]; d_means2D[3 * idx + 1] = dm2[1]; d_means2D[3 * idx + 2] = 0.f;
-#pragma unroll
-  for (int k = 0; k < 6; k++) d_cov[6 * idx + k] = dcov[k];
+  store_dcov(v, d_cov, idx, dcov, gsc * gsc);
   d_opac[idx] = dop;
   if (d_colors != nullptr) {
     const bool pre = shs == nullptr;
@@ -437,7 +466,8 @@ __global__ void mark_visible_kernel(const S360View v, const float* __restrict__ 
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= v.P) return;
   const float* V = v.viewmatrix;
-  const float mx = means[3 * idx], my = means[3 * idx + 1], mz = means[3 * idx + 2];
+  const float sc = v.scene_scale;
+  const float mx = means[3 * idx] * sc, my = means[3 * idx + 1] * sc, mz = means[3 * idx + 2] * sc;
   const float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
   const float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
   const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];

@@ -41,7 +41,12 @@ def _triu6(cov: Tensor) -> Tensor:
 
 
 def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fov_y, image_shape, background_color,
-                     gaussian_means, gaussian_covariances, shs, gaussian_opacities, degree, use_sh, projection):
+                     gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
+                     projection, scene_scale):
+    """Per batch item: one rasterizer call.  The reference's per-call layout copies (SH transpose
+    cuda_splatting.py:75, triu gather :115,123) and its 1/near rescale copies (:64-71) are not materialised: the
+    kernels read harmonics [g,3,d_sh] and covariances [g,3,3] directly and apply the scale on load, and return the
+    gradients in those layouts w.r.t. the unscaled tensors -- identical values, ~1.4 KB/Gaussian less traffic per call."""
     b = extrinsics.shape[0]
     h, w = image_shape
     images = []
@@ -57,13 +62,14 @@ def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fo
             bg=background_color[i], scale_modifier=1.0,
             viewmatrix=view_matrix[i], projmatrix=full_projection[i],
             sh_degree=degree, campos=extrinsics[i, :3, 3],
-            prefiltered=False, debug=False, projection=projection)
+            prefiltered=False, debug=False, projection=projection,
+            scene_scale=float(scene_scale[i]), sh_layout=1, cov_layout=1)
         image, _radii = GaussianRasterizer(settings)(
             means3D=gaussian_means[i], means2D=mean_gradients,
-            shs=shs[i] if use_sh else None,
-            colors_precomp=None if use_sh else shs[i, :, 0, :],
+            shs=gaussian_sh_coefficients[i] if use_sh else None,
+            colors_precomp=None if use_sh else gaussian_sh_coefficients[i, :, :, 0],
             opacities=gaussian_opacities[i, ..., None],
-            cov3D_precomp=_triu6(gaussian_covariances[i]))
+            cov3D_precomp=gaussian_covariances[i])
         images.append(image)
     return torch.stack(images)
 
@@ -74,26 +80,24 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
                 use_sh: bool = True) -> Tensor:
     """Pinhole render of a batch: [b,3,h,w].  Argument meaning identical to the reference."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    b = extrinsics.shape[0]
+    scale = torch.ones_like(near)
     if scale_invariant:
         scale = 1 / near
         extrinsics = extrinsics.clone()
         extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[:, None]
-        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
-        gaussian_means = gaussian_means * scale[:, None, None]
         near = near * scale
         far = far * scale
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    shs = gaussian_sh_coefficients.transpose(-1, -2).contiguous()  # b g xyz n -> b g n xyz
     fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
-    tan_fov_x = (0.5 * fov_x).tan().tolist()
-    tan_fov_y = (0.5 * fov_y).tan().tolist()
+    host = torch.stack(((0.5 * fov_x).tan(), (0.5 * fov_y).tan(), scale)).tolist()   # one device read for all scalars
     projection_matrix = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
     view_matrix = extrinsics.inverse().transpose(1, 2)
     full_projection = view_matrix @ projection_matrix
-    return _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fov_y, image_shape,
-                            background_color, gaussian_means, gaussian_covariances, shs, gaussian_opacities,
-                            degree, use_sh, "pinhole")
+    return _rasterize_batch(extrinsics, view_matrix, full_projection, host[0], host[1], image_shape,
+                            background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
+                            gaussian_opacities, degree, use_sh, "pinhole", host[2])
 
 
 def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,
@@ -106,7 +110,6 @@ def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, 
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    shs = gaussian_sh_coefficients.transpose(-1, -2).contiguous()
     fov_x = torch.tensor(fov_degrees, device=extrinsics.device).deg2rad()
     tan_fov_x = (0.5 * fov_x).tan()
     distance_to_near = (0.5 * width) / tan_fov_x
@@ -125,7 +128,8 @@ def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, 
     full_projection = view_matrix @ projection_matrix
     return _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x.expand(b).tolist(),
                             tan_fov_y.expand(b).tolist(), image_shape, background_color, gaussian_means,
-                            gaussian_covariances, shs, gaussian_opacities, degree, use_sh, "pinhole")
+                            gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
+                            "pinhole", [1.0] * b)
 
 
 def _depth_colors(fake_color: Tensor, near: Tensor, far: Tensor, mode: DepthRenderingMode) -> Tensor:
@@ -168,21 +172,20 @@ def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape
     role it has in ``render_cuda``: with ``scale_invariant`` the scene is rescaled by 1/near so that the
     near-cull distance is 0.2*near.  ``far`` is accepted for signature symmetry and unused."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    b = extrinsics_sphere.shape[0]
+    scales = [1.0] * b
     if scale_invariant:
         scale = 1 / near
         extrinsics_sphere = extrinsics_sphere.clone()
         extrinsics_sphere[..., :3, 3] = extrinsics_sphere[..., :3, 3] * scale[:, None]
-        gaussian_covariances = gaussian_covariances * (scale[:, None, None, None] ** 2)
-        gaussian_means = gaussian_means * scale[:, None, None]
+        scales = scale.tolist()
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    shs = gaussian_sh_coefficients.transpose(-1, -2).contiguous()
     cam = erp_camera(extrinsics_sphere)
-    b = extrinsics_sphere.shape[0]
     ones = [1.0] * b
     return _rasterize_batch(extrinsics_sphere, cam.view_matrix, cam.full_projection, ones, ones, image_shape,
-                            background_color, gaussian_means, gaussian_covariances, shs, gaussian_opacities,
-                            degree, use_sh, "erp")
+                            background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
+                            gaussian_opacities, degree, use_sh, "erp", scales)
 
 
 def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],

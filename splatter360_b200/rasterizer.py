@@ -49,6 +49,9 @@ class GaussianRasterizationSettings(NamedTuple):
     pole_eps: float = 1e-3
     max_sh_degree: int = 4
     tight_bbox: bool = True
+    scene_scale: float = 1.0      # means *= s, cov3D *= s^2 inside the kernels (cuda_splatting.py:64-71), grads w.r.t. inputs
+    sh_layout: int = 0            # 0: shs [P,M,3]   1: [P,3,M] (the reference's harmonics layout, no transpose copy)
+    cov_layout: int = 0           # 0: cov3D [P,6]   1: [P,3,3] (upper triangle read; gradient in the same layout)
 
 
 _MODES = {"pinhole": _lib.MODE_PINHOLE, "erp": _lib.MODE_ERP}
@@ -91,6 +94,7 @@ def _make_view(s: GaussianRasterizationSettings, P: int, M: int, device):
     v.tanfovx, v.tanfovy = float(s.tanfovx), float(s.tanfovy)
     v.near_cull, v.fov_clamp = float(s.near_cull), float(s.fov_clamp)
     v.lowpass, v.pole_eps = float(s.lowpass), float(s.pole_eps)
+    v.scene_scale, v.sh_layout, v.cov_layout = float(s.scene_scale), int(s.sh_layout), int(s.cov_layout)
     v.viewmatrix, v.projmatrix = vm.data_ptr(), pm.data_ptr()
     v.campos, v.bg = cp.data_ptr(), bg.data_ptr()
     return v, (vm, pm, cp, bg)
@@ -141,7 +145,7 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
     if device.type != "cuda":
         raise RuntimeError("splatter360_b200 rasterizer needs CUDA tensors (there is no CPU path)")
     P = means3D.shape[0]
-    M = shs.shape[1] if shs is not None else 0
+    M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
     H, W = int(settings.image_height), int(settings.image_width)
     with torch.cuda.device(device):
         view, keep = _make_view(settings, P, M, device)
@@ -190,15 +194,15 @@ def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6:
     lib = _lib.load()
     device = means3D.device
     P = means3D.shape[0]
-    M = shs.shape[1] if shs is not None else 0
+    M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
     with torch.cuda.device(device):
         view, keep = _make_view(settings, P, M, device)
         f32 = dict(dtype=torch.float32, device=device)
         g_means = torch.empty((P, 3), **f32)
         g_means2D = torch.empty((P, 3), **f32)
-        g_cov = torch.empty((P, 6), **f32)
+        g_cov = torch.empty_like(cov6)
         g_op = torch.empty((P, 1), **f32)
-        g_sh = torch.empty((P, M, 3), **f32) if shs is not None else None
+        g_sh = torch.empty_like(shs) if shs is not None else None
         g_col = torch.empty((P, 3), **f32) if colors is not None else None
         scratch = torch.empty(lib.s360_backward_scratch_bytes(P), dtype=torch.uint8, device=device)
         grad_color = _f32c(grad_color, device)
@@ -226,10 +230,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         shs_c = _f32c(sh, device) if sh.numel() else None
         col_c = _f32c(colors_precomp, device) if colors_precomp.numel() else None
         P = means3D_c.shape[0]
-        if cov6.shape != (P, 6) or op.shape[0] != P:
-            raise ValueError("cov3D_precomp must be [P,6] and opacities [P,1]")
-        if shs_c is not None and (shs_c.dim() != 3 or shs_c.shape[0] != P or shs_c.shape[2] != 3):
-            raise ValueError("shs must be [P,M,3]")
+        if cov6.shape != ((P, 3, 3) if raster_settings.cov_layout else (P, 6)) or op.shape[0] != P:
+            raise ValueError("cov3D_precomp must be [P,6] ([P,3,3] with cov_layout=1) and opacities [P,1]")
+        if shs_c is not None and (shs_c.dim() != 3 or shs_c.shape[0] != P or shs_c.shape[1 if raster_settings.sh_layout else 2] != 3):
+            raise ValueError("shs must be [P,M,3] ([P,3,M] with sh_layout=1)")
         if col_c is not None and col_c.shape != (P, 3):
             raise ValueError("colors_precomp must be [P,3]")
         color, state = forward_raw(raster_settings, means3D_c, cov6, op, shs_c, col_c)

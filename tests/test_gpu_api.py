@@ -196,3 +196,44 @@ def test_full_size_properties():
     gp = rasterizer.backward_raw(s0, means[perm].contiguous(), cov6[perm].contiguous(), op[perm].contiguous(), shs[perm].contiguous(), None, stp, d1)
     assert float((gp["opacities"] - g1["opacities"][perm]).norm() / g1["opacities"].norm()) < 1e-4
     assert float((gp["shs"] - g1["shs"][perm]).norm() / g1["shs"].norm()) < 1e-4
+
+
+def test_decoder_layouts_and_scale_gradients_match_oracle():
+    """The decoder-level path hands the kernels the reference's raw layouts (harmonics [g,3,d_sh], covariances
+    [g,3,3]) plus the 1/near scale; gradients must equal autograd through the reference's explicit copies:
+    s * dL/dmeans, s^2 * dL/dcov6 on the upper triangle (zero below), transposed dL/dSH."""
+    import oracle
+    from splatter360_b200 import camera, decoder, synthetic
+    for proj in ("erp", "pinhole"):
+        sc = synthetic.random_cloud_scene(2500, sh_degree=4, seed=15, ref_width=64, depth_range=(0.5, 4.0))
+        pose = synthetic.target_pose(15)
+        near, far = torch.tensor([0.4]), torch.tensor([30.0])
+        H, W = (64, 128) if proj == "erp" else (64, 64)
+        dev = "cuda"
+        m = sc.means[None].to(dev).requires_grad_(); c = sc.covariances[None].to(dev).requires_grad_()
+        h = sc.harmonics[None].to(dev).requires_grad_(); o = sc.opacities[None].to(dev).requires_grad_()
+        dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(2))
+        K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None].to(dev)
+        if proj == "erp":
+            img = decoder.render_erp(pose[None].to(dev), near.to(dev), far.to(dev), (H, W), torch.zeros(1, 3, device=dev), m, c, h, o)
+        else:
+            img = decoder.render_cuda(pose[None].to(dev), K, near.to(dev), far.to(dev), (H, W), torch.zeros(1, 3, device=dev), m, c, h, o)
+        (img[0] * dL.to(dev)).sum().backward()
+        s = float(1 / near[0])
+        pose_s = pose.clone(); pose_s[:3, 3] *= s
+        if proj == "erp":
+            cam = camera.erp_camera(pose_s[None]); tan = (1.0, 1.0)
+        else:
+            cam = camera.pinhole_camera(pose_s[None], K.cpu(), near * s, far * s); tan = (float(cam.tan_fov_x[0]), float(cam.tan_fov_y[0]))
+        ref = oracle.render((sc.means * s).numpy(), synthetic.cov3x3_to_cov6(sc.covariances * s * s).numpy(), sc.opacities.numpy(),
+                            shs=sc.harmonics.permute(0, 2, 1).contiguous().numpy(), H=H, W=W, view=cam.view_matrix[0].numpy(),
+                            proj=cam.full_projection[0].numpy(), campos=cam.campos[0].numpy(), tanfovx=tan[0], tanfovy=tan[1],
+                            sh_degree=4, mode=proj, dL_dpix=dL.numpy(), stages=False)
+        assert rel_l2(img[0].detach().cpu().numpy(), ref["color"]) < TOL
+        assert rel_l2(m.grad[0].cpu().numpy(), s * ref["d_means"]) < TOL
+        assert rel_l2(o.grad[0].cpu().numpy(), ref["d_opac"]) < TOL
+        assert rel_l2(h.grad[0].cpu().numpy(), ref["d_shs"].transpose(0, 2, 1)) < TOL
+        gc = c.grad[0].cpu()
+        row, col = torch.triu_indices(3, 3)
+        assert rel_l2(gc[:, row, col].numpy(), s * s * ref["d_cov6"]) < TOL
+        assert float(gc[:, 1, 0].abs().max()) == 0 and float(gc[:, 2, 0].abs().max()) == 0 and float(gc[:, 2, 1].abs().max()) == 0
