@@ -47,6 +47,13 @@ extern "C" {
 #define S360_MODE_PINHOLE 0 /* upstream semantics                     */
 #define S360_MODE_ERP 1     /* native equirectangular splatting      */
 
+/* fused depth channel of s360_forward_render: per-Gaussian value blended like a colour
+ * (DepthRenderingMode of /root/reference/src/model/decoder/cuda_splatting.py:223-269) */
+#define S360_DEPTH_DEPTH 0               /* camera z (pinhole) / radial distance (erp), unscaled */
+#define S360_DEPTH_DISPARITY 1           /* 1 / depth                                            */
+#define S360_DEPTH_RELATIVE_DISPARITY 2  /* depth_to_relative_disparity(depth, near, far)        */
+#define S360_DEPTH_LOG 3                 /* log(max(min(depth, near), far)) as written upstream  */
+
 #define S360_ERR_BAD_ARGUMENT (-1)
 #define S360_ERR_WORKSPACE_OVERFLOW (-2) /* reported through S360Counters.overflow, see below */
 #define S360_ERR_UNSUPPORTED (-3)
@@ -138,6 +145,9 @@ int s360_forward_render(
     uint32_t* point_list,        /* [instance_capacity] out: Gaussian ids sorted by (tile, depth, id) */
     void* image_state,           /* s360_image_bytes(H,W) out                                  */
     float* out_color,            /* [3,H,W] out                                                */
+    float* out_depth,            /* [H,W] out or NULL: fused depth channel (no gradient)       */
+    int32_t depth_mode,          /* S360_DEPTH_*                                               */
+    float depth_near, float depth_far, /* unscaled near / far for relative_disparity and log   */
     void* scratch,               /* s360_binning_scratch_bytes(instance_capacity,H,W)          */
     void* stream);
 

@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("S360_LIB", os.path.join(_HERE, "libsplatter360.so")) 
 
 MODE_PINHOLE = 0
 MODE_ERP = 1
+DEPTH_MODES = {"depth": 0, "disparity": 1, "relative_disparity": 2, "log": 3}
 
 EXPORTS = [
     "s360_abi_version", "s360_error_string", "s360_launch_count",
@@ -80,7 +81,7 @@ def load() -> ctypes.CDLL:
     lib.s360_forward_order.restype = c_int
     lib.s360_forward_order.argtypes = [ctypes.POINTER(S360View)] + [vp] * 6
     lib.s360_forward_render.restype = c_int
-    lib.s360_forward_render.argtypes = [ctypes.POINTER(S360View), vp, vp, vp, vp, c_int64, vp, vp, vp, vp, vp]
+    lib.s360_forward_render.argtypes = [ctypes.POINTER(S360View), vp, vp, vp, vp, c_int64, vp, vp, vp, vp, c_int32, c_float, c_float, vp, vp]
     lib.s360_backward.restype = c_int
     lib.s360_backward.argtypes = [ctypes.POINTER(S360View)] + [vp] * 18
     lib.s360_mark_visible.restype = c_int

@@ -181,7 +181,8 @@ int s360_forward_preprocess(const S360View* view, const float* means3D, const fl
 
 int s360_forward_render(const S360View* view, const void* geom, const uint32_t* depth_order,
                         const uint32_t* inst_offsets, S360Counters* counters, int64_t instance_capacity,
-                        uint32_t* point_list, void* image_state, float* out_color, void* scratch, void* stream) {
+                        uint32_t* point_list, void* image_state, float* out_color, float* out_depth,
+                        int32_t depth_mode, float depth_near, float depth_far, void* scratch, void* stream) {
   if (!view_ok(view) || !geom || !counters || !image_state || !scratch || instance_capacity < 0) return S360_ERR_BAD_ARGUMENT;
   if (instance_capacity > 0 && !point_list) return S360_ERR_BAD_ARGUMENT;
   if ((size_t)view->image_height * view->image_width > 0 && !out_color) return S360_ERR_BAD_ARGUMENT;
@@ -212,7 +213,8 @@ int s360_forward_render(const S360View* view, const void* geom, const uint32_t* 
     rc = radix_sort_pairs(k0, v0, k1, v1, instance_capacity, &counters->num_rendered, nbits, s.radix, st, &in_b, true); }
   if (rc) return rc;
   StageTimer t(S360_STAGE_RENDER_FWD, st);
-  return launch_render_forward(*view, g, point_list, img, out_color, st);
+  if (depth_mode < S360_DEPTH_DEPTH || depth_mode > S360_DEPTH_LOG) return S360_ERR_BAD_ARGUMENT;
+  return launch_render_forward(*view, g, point_list, img, out_color, out_depth, depth_mode, depth_near, depth_far, st);
 }
 
 int s360_backward(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,

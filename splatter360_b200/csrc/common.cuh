@@ -292,7 +292,8 @@ int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* range
                      cudaStream_t st);
 
 int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
-                          float* out_color, cudaStream_t st);
+                          float* out_color, float* out_depth, int depth_mode, float depth_near, float depth_far,
+                          cudaStream_t st);
 int launch_render_backward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
                            const float* dL_dcolor, float* acc, cudaStream_t st);
 

@@ -77,6 +77,27 @@ __device__ __forceinline__ bool rect_can_contribute(const float4& q, const float
   return !(best < thr);
 }
 
+// Fused depth channel: what the reference renders in a second full pass by feeding
+// per-Gaussian depth as colour (cuda_splatting.py:226-269).  The geometry record stores the sort depth of the
+// rescaled scene (camera z for pinhole, radial distance for erp); dividing by scene_scale recovers the value the
+// reference computes from the unscaled means.
+struct DepthSpec {
+  int mode;          // S360_DEPTH_*
+  float inv_scale;   // 1 / scene_scale
+  float near, far;   // unscaled, for relative_disparity / log
+};
+__device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth) {
+  const float z = rec_depth * d.inv_scale;
+  if (d.mode == S360_DEPTH_DISPARITY) return 1.f / z;
+  if (d.mode == S360_DEPTH_RELATIVE_DISPARITY) {
+    const float eps = 1e-10f;
+    const float dn = 1.f / (d.near + eps), df = 1.f / (d.far + eps), dz = 1.f / (z + eps);
+    return 1.f - (dz - df) / (dn - df + eps);
+  }
+  if (d.mode == S360_DEPTH_LOG) return logf(fmaxf(fminf(z, d.near), d.far));   // literal: .minimum(near).maximum(far).log()
+  return z;
+}
+
 #ifndef S360_FWD_MINB
 #define S360_FWD_MINB 1
 #endif
@@ -106,7 +127,8 @@ template <int MODE>
 __global__ void __launch_bounds__(RT, S360_FWD_MINB)
 render_forward_kernel(const int W, const int H, const float* __restrict__ bg, const float4* __restrict__ rec,
                       const uint32_t* __restrict__ point_list, const uint2* __restrict__ ranges,
-                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color) {
+                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
+                      float* __restrict__ out_depth, const DepthSpec dspec) {
   __shared__ float4 s_ev[NWARPS][32];    // A', B', C' (log2-scaled conic), log2(opacity)
   __shared__ float4 s_col[NWARPS][32];   // r, g, b, -
   const int gx = (W + TILE - 1) / TILE;
@@ -123,7 +145,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
 
   // packed state of the lane's two pixels (.x = row py0, .y = row py0 + 4); FFMA2/FMUL2/FADD2 are Blackwell's
   // two-wide FP32 instructions
-  float2 T = make_float2(1.f, 1.f), Cr = make_float2(0.f, 0.f), Cg = Cr, Cb = Cr;
+  float2 T = make_float2(1.f, 1.f), Cr = make_float2(0.f, 0.f), Cg = Cr, Cb = Cr, Cd = Cr;
   uint32_t last0 = 0, last1 = 0;
   const float INF = __int_as_float(0x7f800000);
   float amin0 = in0 ? ALPHA_MIN : INF, amin1 = in1 ? ALPHA_MIN : INF;   // +inf once the pixel is finished
@@ -144,7 +166,8 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     const float thr = col.w;
     const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
     s_ev[warp][lane] = ev;
-    s_col[warp][lane] = make_float4(-col.x, -col.y, -col.z, 0.f);   // negated: the loop carries -alpha
+    // negated: the loop carries -alpha.  .w = the per-Gaussian depth value of the fused depth channel
+    s_col[warp][lane] = make_float4(-col.x, -col.y, -col.z, -depth_value(dspec, nx.r2.w));
     __syncwarp();
     // keep the pipeline full: records of the next chunk, ids of the one after
     nx.gid = gid2;
@@ -179,6 +202,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
       Cr = __ffma2_rn(make_float2(c.x, c.x), nw, Cr);                   // c holds -rgb
       Cg = __ffma2_rn(make_float2(c.y, c.y), nw, Cg);
       Cb = __ffma2_rn(make_float2(c.z, c.z), nw, Cb);
+      Cd = __ffma2_rn(make_float2(c.w, c.w), nw, Cd);
       T = __ffma2_rn(T, nae, T);
       const uint32_t pos = base - range.x + (uint32_t)k + 1u;
       if (nae.x < 0.f) last0 = pos;
@@ -192,23 +216,28 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     const size_t pid = (size_t)py0 * W + px;
     final_T[pid] = T.x; n_contrib[pid] = last0;
     out_color[pid] = Cr.x + T.x * b0; out_color[plane + pid] = Cg.x + T.x * b1; out_color[2 * plane + pid] = Cb.x + T.x * b2;
+    if (out_depth) out_depth[pid] = Cd.x;
   }
   if (in1) {
     const size_t pid = (size_t)py1 * W + px;
     final_T[pid] = T.y; n_contrib[pid] = last1;
     out_color[pid] = Cr.y + T.y * b0; out_color[plane + pid] = Cg.y + T.y * b1; out_color[2 * plane + pid] = Cb.y + T.y * b2;
+    if (out_depth) out_depth[pid] = Cd.y;
   }
 }
 
 int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
-                          float* out_color, cudaStream_t st) {
+                          float* out_color, float* out_depth, int depth_mode, float depth_near, float depth_far,
+                          cudaStream_t st) {
   const int W = v.image_width, H = v.image_height;
   const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
   if (tiles == 0) return 0;
+  DepthSpec ds;
+  ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
   if (v.mode == S360_MODE_PINHOLE)
-    render_forward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, out_color);
+    render_forward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, out_color, out_depth, ds);
   else
-    render_forward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, out_color);
+    render_forward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, out_color, out_depth, ds);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -42,14 +42,14 @@ def _triu6(cov: Tensor) -> Tensor:
 
 def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fov_y, image_shape, background_color,
                      gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
-                     projection, scene_scale):
+                     projection, scene_scale, depth=None):
     """Per batch item: one rasterizer call.  The reference's per-call layout copies (SH transpose
     cuda_splatting.py:75, triu gather :115,123) and its 1/near rescale copies (:64-71) are not materialised: the
     kernels read harmonics [g,3,d_sh] and covariances [g,3,3] directly and apply the scale on load, and return the
     gradients in those layouts w.r.t. the unscaled tensors -- identical values, ~1.4 KB/Gaussian less traffic per call."""
     b = extrinsics.shape[0]
     h, w = image_shape
-    images = []
+    images, depths = [], []
     for i in range(b):
         mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
         try:
@@ -63,24 +63,34 @@ def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fo
             viewmatrix=view_matrix[i], projmatrix=full_projection[i],
             sh_degree=degree, campos=extrinsics[i, :3, 3],
             prefiltered=False, debug=False, projection=projection,
-            scene_scale=float(scene_scale[i]), sh_layout=1, cov_layout=1)
-        image, _radii = GaussianRasterizer(settings)(
+            scene_scale=float(scene_scale[i]), sh_layout=1, cov_layout=1,
+            depth_mode=None if depth is None else depth[0],
+            depth_near=0.0 if depth is None else float(depth[1][i]), depth_far=0.0 if depth is None else float(depth[2][i]))
+        out = GaussianRasterizer(settings)(
             means3D=gaussian_means[i], means2D=mean_gradients,
             shs=gaussian_sh_coefficients[i] if use_sh else None,
             colors_precomp=None if use_sh else gaussian_sh_coefficients[i, :, :, 0],
             opacities=gaussian_opacities[i, ..., None],
             cov3D_precomp=gaussian_covariances[i])
-        images.append(image)
+        images.append(out[0])
+        if depth is not None:
+            depths.append(out[2])
+    if depth is not None:
+        return torch.stack(images), torch.stack(depths)
     return torch.stack(images)
 
 
 def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
                 background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                 gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
-                use_sh: bool = True) -> Tensor:
-    """Pinhole render of a batch: [b,3,h,w].  Argument meaning identical to the reference."""
+                use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None):
+    """Pinhole render of a batch: [b,3,h,w].  Argument meaning identical to the reference.
+
+    ``fused_depth_mode`` (extension): also return the depth image [b,h,w] that ``render_depth_cuda`` would produce,
+    accumulated as a fourth channel of the same pass (no gradient flows through it)."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b = extrinsics.shape[0]
+    depth = None if fused_depth_mode is None else (fused_depth_mode, near.tolist(), far.tolist())
     scale = torch.ones_like(near)
     if scale_invariant:
         scale = 1 / near
@@ -97,7 +107,7 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
     full_projection = view_matrix @ projection_matrix
     return _rasterize_batch(extrinsics, view_matrix, full_projection, host[0], host[1], image_shape,
                             background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
-                            gaussian_opacities, degree, use_sh, "pinhole", host[2])
+                            gaussian_opacities, degree, use_sh, "pinhole", host[2], depth)
 
 
 def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,
@@ -164,8 +174,9 @@ def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
 def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
-               use_sh: bool = True) -> Tensor:
-    """One equirectangular render per batch item: [b,3,h,w].
+               use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None):
+    """One equirectangular render per batch item: [b,3,h,w] (plus the fused radial-distance image [b,h,w] when
+    ``fused_depth_mode`` is given).
 
     ``extrinsics_sphere`` is the panorama camera-to-world in the reference's sphere-camera frame
     (/root/reference/src/dataset/dataset_hm3d.py:282,298; utils360.py hm3d branch).  ``near`` plays the
@@ -173,6 +184,7 @@ def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape
     near-cull distance is 0.2*near.  ``far`` is accepted for signature symmetry and unused."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b = extrinsics_sphere.shape[0]
+    depth = None if fused_depth_mode is None else (fused_depth_mode, near.tolist(), far.tolist())
     scales = [1.0] * b
     if scale_invariant:
         scale = 1 / near
@@ -185,7 +197,7 @@ def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape
     ones = [1.0] * b
     return _rasterize_batch(extrinsics_sphere, cam.view_matrix, cam.full_projection, ones, ones, image_shape,
                             background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
-                            gaussian_opacities, degree, use_sh, "erp", scales)
+                            gaussian_opacities, degree, use_sh, "erp", scales, depth)
 
 
 def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
@@ -235,12 +247,21 @@ class DecoderSplattingCUDA(nn.Module):
         b, v, _, _ = extrinsics.shape
         colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
         bg = self.background_color[None].expand(b, 3)
+        # Without autograd (evaluation / video, model_wrapper_erp.py:319-345) the depth image is a fourth channel of
+        # the colour pass; with autograd enabled the reference's separate differentiable depth pass is kept.
+        fused = depth_mode is not None and not torch.is_grad_enabled()
+        depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device) if fused else None
         for view_idx in range(v):
-            colors[:, view_idx] = render_cuda(
+            out = render_cuda(
                 extrinsics[:, view_idx], intrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
-                bg, gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities)
-        depth = None if depth_mode is None else self.render_depth(gaussians, extrinsics, intrinsics, near, far,
-                                                                  image_shape, depth_mode)
+                bg, gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities,
+                fused_depth_mode=depth_mode if fused else None)
+            if fused:
+                colors[:, view_idx], depth[:, view_idx] = out
+            else:
+                colors[:, view_idx] = out
+        if depth_mode is not None and not fused:
+            depth = self.render_depth(gaussians, extrinsics, intrinsics, near, far, image_shape, depth_mode)
         return DecoderOutput(colors, depth)
 
     def render_depth(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
@@ -269,12 +290,17 @@ class DecoderSplattingERP(nn.Module):
         b, v, _, _ = extrinsics.shape
         colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
         bg = self.background_color[None].expand(b, 3)
+        fused = depth_mode is not None and not torch.is_grad_enabled()
+        depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device) if fused else None
         for view_idx in range(v):
-            colors[:, view_idx] = render_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
-                                             bg, gaussians.means, gaussians.covariances, gaussians.harmonics,
-                                             gaussians.opacities)
-        depth = None
-        if depth_mode is not None:
+            out = render_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
+                             bg, gaussians.means, gaussians.covariances, gaussians.harmonics,
+                             gaussians.opacities, fused_depth_mode=depth_mode if fused else None)
+            if fused:
+                colors[:, view_idx], depth[:, view_idx] = out
+            else:
+                colors[:, view_idx] = out
+        if depth_mode is not None and not fused:
             depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device)
             for view_idx in range(v):
                 depth[:, view_idx] = render_depth_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx],

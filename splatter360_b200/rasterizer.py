@@ -52,6 +52,9 @@ class GaussianRasterizationSettings(NamedTuple):
     scene_scale: float = 1.0      # means *= s, cov3D *= s^2 inside the kernels (cuda_splatting.py:64-71), grads w.r.t. inputs
     sh_layout: int = 0            # 0: shs [P,M,3]   1: [P,3,M] (the reference's harmonics layout, no transpose copy)
     cov_layout: int = 0           # 0: cov3D [P,6]   1: [P,3,3] (upper triangle read; gradient in the same layout)
+    depth_mode: Optional[str] = None   # fused depth channel: "depth" | "disparity" | "relative_disparity" | "log"
+    depth_near: float = 0.0            # unscaled near / far used by relative_disparity and log
+    depth_far: float = 0.0
 
 
 _MODES = {"pinhole": _lib.MODE_PINHOLE, "erp": _lib.MODE_ERP}
@@ -135,6 +138,7 @@ class ForwardState(NamedTuple):
     image_state: Tensor
     num_rendered: int
     num_visible: int
+    depth: Optional[Tensor] = None   # [H,W] fused depth channel when settings.depth_mode is set
 
 
 def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
@@ -179,13 +183,22 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
         bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(cap, H, W), **u8)
         image_state = torch.empty(lib.s360_image_bytes(H, W), **u8)
         color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+        depth = None
+        dmode = 0
+        if settings.depth_mode is not None:
+            if settings.depth_mode not in _lib.DEPTH_MODES:
+                raise ValueError(f"unknown depth_mode {settings.depth_mode!r}")
+            dmode = _lib.DEPTH_MODES[settings.depth_mode]
+            depth = torch.empty((H, W), dtype=torch.float32, device=device)
         _lib.check(lib.s360_forward_render(
             ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters),
-            ctypes.c_int64(N), _ptr(point_list), _ptr(image_state), _ptr(color), _ptr(bin_scratch), st))
+            ctypes.c_int64(N), _ptr(point_list), _ptr(image_state), _ptr(color), _ptr(depth),
+            ctypes.c_int32(dmode), ctypes.c_float(settings.depth_near), ctypes.c_float(settings.depth_far),
+            _ptr(bin_scratch), st))
         if settings.debug:
             torch.cuda.synchronize(device)
     del keep
-    return color, ForwardState(geom, radii, point_list, image_state, N, nvis)
+    return color, ForwardState(geom, radii, point_list, image_state, N, nvis, depth)
 
 
 def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
@@ -242,10 +255,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.has_sh = shs_c is not None
         ctx.save_for_backward(means3D_c, cov6, op, shs_c if shs_c is not None else col_c)
         ctx.mark_non_differentiable(state.radii)
+        if state.depth is not None:
+            ctx.mark_non_differentiable(state.depth)
+            return color, state.radii, state.depth
         return color, state.radii
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_radii):
+    def backward(ctx, grad_out_color, _grad_radii, _grad_depth=None):
         means3D, cov6, op, feat = ctx.saved_tensors
         shs = feat if ctx.has_sh else None
         col = None if ctx.has_sh else feat

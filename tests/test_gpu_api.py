@@ -237,3 +237,29 @@ def test_decoder_layouts_and_scale_gradients_match_oracle():
         row, col = torch.triu_indices(3, 3)
         assert rel_l2(gc[:, row, col].numpy(), s * s * ref["d_cov6"]) < TOL
         assert float(gc[:, 1, 0].abs().max()) == 0 and float(gc[:, 2, 0].abs().max()) == 0 and float(gc[:, 2, 1].abs().max()) == 0
+
+
+@pytest.mark.parametrize("mode", ["depth", "disparity", "relative_disparity", "log"])
+def test_fused_depth_channel_equals_separate_depth_pass(mode):
+    """the depth image accumulated as a fourth channel of the colour pass equals the reference's
+    second rasterisation with depth-as-colour (cuda_splatting.py:226-269), pinhole and erp."""
+    from splatter360_b200 import decoder, synthetic
+    sc = synthetic.random_cloud_scene(3000, sh_degree=4, seed=25, ref_width=64, depth_range=(0.5, 4.0))
+    pose = synthetic.target_pose(25)
+    dev = "cuda"
+    near, far = torch.tensor([0.5], device=dev), torch.tensor([20.0], device=dev)
+    args = [t[None].to(dev) for t in (sc.means, sc.covariances, sc.harmonics, sc.opacities)]
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev)[None]
+    bg = torch.zeros(1, 3, device=dev)
+    with torch.no_grad():
+        img, d_fused = decoder.render_cuda(pose[None].to(dev), K, near, far, (64, 80), bg, *args, fused_depth_mode=mode)
+        img_ref = decoder.render_cuda(pose[None].to(dev), K, near, far, (64, 80), bg, *args)
+        d_ref = decoder.render_depth_cuda(pose[None].to(dev), K, near, far, (64, 80), args[0], args[1], args[3], mode=mode)
+        assert torch.equal(img, img_ref)
+        assert float((d_fused - d_ref).norm() / d_ref.norm()) < 1e-5
+        img, d_fused = decoder.render_erp(pose[None].to(dev), near, far, (64, 128), bg, *args, fused_depth_mode=mode)
+        d_ref = decoder.render_depth_erp(pose[None].to(dev), near, far, (64, 128), args[0], args[1], args[3], mode=mode)
+        assert float((d_fused - d_ref).norm() / d_ref.norm()) < 1e-5
+        dec = decoder.DecoderSplattingCUDA().to(dev)
+        out = dec(decoder.Gaussians(*args), pose[None, None].to(dev), K[None], near[None], far[None], (64, 80), depth_mode=mode)
+        assert float((out.depth[0, 0] - d_fused.new_tensor(0) - decoder.render_depth_cuda(pose[None].to(dev), K, near, far, (64, 80), args[0], args[1], args[3], mode=mode)[0]).norm()) < 1e-3 * float(out.depth.norm() + 1)
