@@ -1,0 +1,20 @@
+#!/bin/bash
+# compute-sanitizer over the small parity cases (SURVEY.md sec. 4b tooling row)
+mkdir -p gpurun_out
+cat > /tmp/san_case.py <<'PY'
+import sys, os, torch
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+from helpers import make_case, run_cuda
+for mode, H, W, n in (("pinhole", 64, 80, 1500), ("erp", 48, 96, 1500), ("erp", 37, 64, 300)):
+    case = make_case(n, mode, H, W, seed=7)
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1))
+    out = run_cuda(case, dL=dL)
+    case["colors"] = torch.rand(n, 3)
+    out = run_cuda(case, dL=dL, use_sh=False)
+    print(mode, "ok", float(out["color"].mean()))
+PY
+for tool in memcheck racecheck initcheck synccheck; do
+  echo "== $tool"
+  timeout -s KILL 600 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 5 python /tmp/san_case.py > gpurun_out/sanitize_$tool.log 2>&1
+  echo "exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|error|hazard" gpurun_out/sanitize_$tool.log | head -8
+done
