@@ -206,7 +206,7 @@ int s360_forward_render(const S360View* view, const void* geom, const uint32_t* 
     rc = launch_emit(*view, g, depth_order, inst_offsets, counters, instance_capacity, k0, v0, s.tile_count, st); }
   if (rc) return rc;
   { StageTimer t(S360_STAGE_TILE_RANGES, st);
-    rc = launch_tile_scan(*view, s.tile_count, img.ranges, hist, passes > 0 ? passes : 1, st); }
+    rc = launch_tile_scan(*view, s.tile_count, img.ranges, img.order, img.work, hist, passes > 0 ? passes : 1, st); }
   if (rc) return rc;
   int in_b = 0;
   { StageTimer t(S360_STAGE_TILE_SORT, st);
@@ -237,6 +237,8 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
   if (rc) return rc;
   if (P > 0) {
     StageTimer t(S360_STAGE_RENDER_BWD, st);
+    rc = launch_tile_order(*view, img.work, img.order_bwd, st);
+    if (rc) return rc;
     rc = launch_render_backward(*view, g, point_list, img, dL_dcolor, acc, st);
     if (rc) return rc;
   }

@@ -390,10 +390,12 @@ int tile_hist_copies() { return TILE_HIST_COPIES; }
 // the (up to two) tile-sort passes, which are just partial sums of the same counts.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                 uint32_t* __restrict__ hist, int npasses) {
+                 uint32_t* __restrict__ order, uint32_t* __restrict__ work, uint32_t* __restrict__ hist, int npasses) {
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_hist[3][RS_BINS];
+  __shared__ uint32_t s_bucket[1024];   // longest-first schedule: counting sort of the tiles by instances / 32
+  s_bucket[threadIdx.x] = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = 0;
   for (int i = threadIdx.x; i < 3 * RS_BINS; i += 1024) (&s_hist[0][0])[i] = 0;
@@ -419,6 +421,7 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __r
     if (i < ntiles) {
       const uint32_t start = carry + woff + incl - x;
       ranges[i] = x ? make_uint2(start, start + x) : make_uint2(0u, 0u);
+      atomicAdd(&s_bucket[1023u - min(x >> 5, 1023u)], 1u);   // bucket 0 = heaviest
       if (x) {
         atomicAdd(&s_hist[0][i & 0xff], x);
         if (npasses > 1) atomicAdd(&s_hist[1][(i >> 8) & 0xff], x);
@@ -430,6 +433,68 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __r
     __syncthreads();
   }
   for (int i = threadIdx.x; i < npasses * RS_BINS; i += 1024) hist[i] = (&s_hist[0][0])[i];
+  // exclusive scan of the 1024 buckets (one per thread), then every tile claims a slot in its bucket
+  {
+    const uint32_t x = s_bucket[threadIdx.x];
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_w[w];
+    s_bucket[threadIdx.x] = woff + incl - x;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntiles; i += 1024) {
+      uint32_t c = 0;
+#pragma unroll
+      for (int k = 0; k < TILE_HIST_COPIES; k++) c += tile_count[(size_t)k * ntiles + i];
+      const uint32_t pos = atomicAdd(&s_bucket[1023u - min(c >> 5, 1023u)], 1u);
+      order[pos] = (uint32_t)i;
+      work[i] = 0u;
+    }
+  }
+}
+
+// longest-first schedule of the backward pass from the work the forward pass measured per tile
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(int ntiles, const uint32_t* __restrict__ work, uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_bucket[1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s_bucket[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntiles; i += 1024) atomicAdd(&s_bucket[1023u - min(work[i] >> 5, 1023u)], 1u);
+  __syncthreads();
+  const uint32_t x = s_bucket[threadIdx.x];
+  uint32_t incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < warp; w++) woff += s_w[w];
+  __syncthreads();
+  s_bucket[threadIdx.x] = woff + incl - x;
+  __syncthreads();
+  for (int i = threadIdx.x; i < ntiles; i += 1024) {
+    const uint32_t pos = atomicAdd(&s_bucket[1023u - min(work[i] >> 5, 1023u)], 1u);
+    order[pos] = (uint32_t)i;
+  }
+}
+
+int launch_tile_order(const S360View& v, const uint32_t* work, uint32_t* order, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+  tile_order_kernel<<<1, 1024, 0, st>>>(gx * gy, work, order);
+  count_launch();
+  return (int)cudaGetLastError();
 }
 
 int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, const uint32_t* offsets,
@@ -444,10 +509,10 @@ int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, con
   return (int)cudaGetLastError();
 }
 
-int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* hist, int npasses,
-                     cudaStream_t st) {
+int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* order, uint32_t* work,
+                     uint32_t* hist, int npasses, cudaStream_t st) {
   const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
-  tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, ranges, hist, npasses);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, ranges, order, work, hist, npasses);
   count_launch();
   return (int)cudaGetLastError();
 }

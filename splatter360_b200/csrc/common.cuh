@@ -30,6 +30,9 @@ struct ImageState {
   float* final_T;       // [H*W]
   uint32_t* n_contrib;  // [H*W]
   uint2* ranges;        // [tiles]
+  uint32_t* order;      // [tiles] tile ids, heaviest first: the render CTAs take their tile from here
+  uint32_t* work;       // [tiles] instances the forward pass actually walked (drives the backward schedule)
+  uint32_t* order_bwd;  // [tiles]
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -54,12 +57,15 @@ inline ImageState carve_image(void* buf, int H, int W) {
   s.final_T = (float*)p;      p += align_up(npix * 4, 256);
   s.n_contrib = (uint32_t*)p; p += align_up(npix * 4, 256);
   s.ranges = (uint2*)p;       p += align_up(tiles * 8, 256);
+  s.order = (uint32_t*)p;     p += align_up(tiles * 4, 256);
+  s.work = (uint32_t*)p;      p += align_up(tiles * 4, 256);
+  s.order_bwd = (uint32_t*)p; p += align_up(tiles * 4, 256);
   return s;
 }
 inline size_t image_bytes(int H, int W) {
   size_t npix = (size_t)H * W;
   size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
-  return align_up(npix * 4, 256) * 2 + align_up(tiles * 8, 256);
+  return align_up(npix * 4, 256) * 2 + align_up(tiles * 8, 256) + 3 * align_up(tiles * 4, 256);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -288,8 +294,9 @@ int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, con
                 S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, uint32_t* tile_count,
                 cudaStream_t st);
 int tile_hist_copies();
-int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* hist, int npasses,
-                     cudaStream_t st);
+int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* order, uint32_t* work,
+                     uint32_t* hist, int npasses, cudaStream_t st);
+int launch_tile_order(const S360View& v, const uint32_t* work, uint32_t* order, cudaStream_t st);
 
 int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
                           float* out_color, float* out_depth, int depth_mode, float depth_near, float depth_far,

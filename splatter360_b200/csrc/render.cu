@@ -133,12 +133,13 @@ template <int MODE>
 __global__ void __launch_bounds__(RT, S360_FWD_MINB)
 render_forward_kernel(const int W, const int H, const float* __restrict__ bg, const float4* __restrict__ rec,
                       const uint32_t* __restrict__ point_list, const uint2* __restrict__ ranges,
+                      const uint32_t* __restrict__ order, uint32_t* __restrict__ work,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, const DepthSpec dspec) {
   __shared__ float4 s_ev[NWARPS][32];    // A', B', C' (log2-scaled conic), log2(opacity)
   __shared__ float4 s_col[NWARPS][32];   // r, g, b, -
   const int gx = (W + TILE - 1) / TILE;
-  const int tile = blockIdx.x;
+  const int tile = (int)order[blockIdx.x];   // heaviest tiles first (longest-processing-time schedule)
   const int tx = tile % gx, ty = tile / gx;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wx0 = tx * TILE + (warp & 1) * WARP_W, wy0 = ty * TILE + (warp >> 1) * WARP_H;
@@ -223,6 +224,11 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     }
     __syncwarp();
   }
+  // how far this warp had to walk: the backward pass replays at most that much of the tile's list
+  {
+    const uint32_t walked = __reduce_max_sync(0xffffffffu, max(last0, last1));
+    if (lane == 0 && walked) atomicMax(&work[tile], walked);
+  }
   const size_t plane = (size_t)H * W;
   const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
   if (in0) {
@@ -248,9 +254,9 @@ int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
   if (v.mode == S360_MODE_PINHOLE)
-    render_forward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, out_color, out_depth, ds);
+    render_forward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order, img.work, img.final_T, img.n_contrib, out_color, out_depth, ds);
   else
-    render_forward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, out_color, out_depth, ds);
+    render_forward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order, img.work, img.final_T, img.n_contrib, out_color, out_depth, ds);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -312,12 +318,13 @@ template <int MODE>
 __global__ void __launch_bounds__(RT, S360_BWD_MINB)
 render_backward_kernel(const int W, const int H, const float* __restrict__ bg, const float4* __restrict__ rec,
                        const uint32_t* __restrict__ point_list, const uint2* __restrict__ ranges,
+                       const uint32_t* __restrict__ order,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dcolor, float* __restrict__ acc) {
   __shared__ float4 s_ev[NWARPS][32];    // A', B', C', log2(opacity)
   __shared__ float4 s_col[NWARPS][32];   // r, g, b, bits of the Gaussian id
   const int gx = (W + TILE - 1) / TILE;
-  const int tile = blockIdx.x;
+  const int tile = (int)order[blockIdx.x];   // heaviest tiles first (longest-processing-time schedule)
   const int tx = tile % gx, ty = tile / gx;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wx0 = tx * TILE + (warp & 1) * WARP_W, wy0 = ty * TILE + (warp >> 1) * WARP_H;
@@ -444,9 +451,9 @@ int launch_render_backward(const S360View& v, GeomState g, const uint32_t* point
   const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
   if (tiles == 0) return 0;
   if (v.mode == S360_MODE_PINHOLE)
-    render_backward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, dL_dcolor, acc);
+    render_backward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, acc);
   else
-    render_backward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.final_T, img.n_contrib, dL_dcolor, acc);
+    render_backward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, acc);
   count_launch();
   return (int)cudaGetLastError();
 }
