@@ -249,8 +249,8 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// K8 + K9 fused.  acc[idx*12 + 0..8] = {dL/dr, dL/dg, dL/db, dL/du, dL/dv (pixel units),
-// dL/dconicA, dL/dconicB (true off-diagonal gradient), dL/dconicC, dL/dopacity}
+// K8 + K9 fused.  acc[idx*12 + 0..8] = {dL/dr, dL/dg, dL/db, and the moments sum(q dx), sum(q dy), sum(q dx^2),
+// sum(q dx dy), sum(q dy^2), sum(q)} with q = G dL/dalpha, accumulated by render_backward_kernel
 template <int MODE>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_backward_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,

@@ -1,19 +1,22 @@
 // render.cu -- per-tile compositing kernels.
 //   K6 render_forward_kernel : front-to-back alpha compositing            
 //   K7 render_backward_kernel: back-to-front gradient pass                 
-// One CTA = one 16x16 tile = 8 warps; a warp owns an 8x4 pixel block.  A batch of sorted instances
-// is gathered into shared memory once per tile; every warp first tests, one instance per lane,
-// whether the instance's alpha>=1/255 box can reach its 8x4 block (ballot) and then evaluates only
-// the survivors: centre broadcast by SHFL from the testing lane, conic broadcast from shared memory.
-// The conic is staged pre-multiplied by -0.5*log2(e) and the opacity as log2(opacity), so that
-// alpha = ex2(A'dx^2 + C'dy^2 + B'dxdy + log2 o) costs 5 FP32 ops + one MUFU.EX2.
+// One CTA = one 16x16 tile = 4 warps; a warp owns an 8x8 pixel block and a lane the two pixels (x, y) and
+// (x, y + 4), whose state is packed in float2 and advanced with Blackwell's two-wide FP32 instructions
+// (FFMA2 / FMUL2 / FADD2).  The kernels are warp-autonomous (no CTA barrier): every warp streams the tile's
+// depth-sorted instance list itself in chunks of 32 -- lane j gathers instance j (its id was prefetched one chunk
+// earlier, the 48-B record comes from L2/L1, which the four warps of the tile share) -- tests its own instance
+// against the warp's pixel rectangle with an exact "can the alpha >= 1/255 ellipse reach it" test, and only the
+// ballot survivors are evaluated: centre by SHFL from the testing lane, conic and colour broadcast from a per-warp
+// shared-memory slice.  The conic is staged pre-multiplied by -0.5*log2(e) and the opacity as log2(opacity), so that
+// alpha = ex2(A'dx^2 + C'dy^2 + B'dxdy + log2 o).  Blending is branch-free: a pixel that does not take an instance
+// runs the recurrences with alpha = 0.  The CTAs pick their tile from a longest-first schedule.
 //
-// Backward: per (pixel, instance) only the moments q, q*dx, q*dy, q*dx^2, q*dxdy, q*dy^2
-// (q = G * dL/dalpha) and the three colour terms are formed; they are summed over the warp with a
-// transposed butterfly (14 shuffles), written to a per-warp private slot in shared memory (no
-// atomics), and converted to dL/d{mean2D, conic, opacity} once per instance and tile before a
-// single global atomic per value.  Replaces upstream renderCUDA (forward.cu / backward.cu) behind
-// /root/reference/src/model/decoder/cuda_splatting.py:113-124.
+// Backward: per (pixel, instance) only the moments q, q*dx, q*dy, q*dx^2, q*dxdy, q*dy^2 (q = G * dL/dalpha) and the
+// three colour terms are formed; they are summed over the warp with a transposed butterfly (14 shuffles) and nine
+// lanes issue one fire-and-forget RED.ADD.F32 each into the per-Gaussian accumulator.  Moments are converted to
+// dL/d{mean2D, conic, opacity} once per Gaussian in preprocess_backward_kernel.  Replaces upstream renderCUDA
+// (forward.cu / backward.cu) behind /root/reference/src/model/decoder/cuda_splatting.py:113-124.
 #include "common.cuh"
 
 namespace s360 {
@@ -114,8 +117,9 @@ __device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth
 constexpr int NWARPS = RT / 32;
 
 // Warp-autonomous streaming of a tile's instance list: lane j of every warp gathers instance
-// (chunk*32 + j) itself (the four warps of a tile hit the same lines in L1), two chunks of ids and one
-// chunk of records are always in flight, and no CTA-wide barrier exists in the kernel.
+// (chunk*32 + j) itself (the four warps of a tile hit the same lines in L1); the ids of the next two chunks are
+// always in flight (S360_*_PREFETCH=1 additionally keeps the next chunk's records in registers), and no CTA-wide
+// barrier exists in the kernel.
 struct ChunkRegs {
   float4 r0, r1, r2;
   uint32_t gid;

@@ -12,7 +12,12 @@ TOL = 1e-4
 
 
 @pytest.mark.parametrize("mode,H,W,n", [("pinhole", 96, 128, 3000), ("erp", 64, 128, 3000),
-                                         ("pinhole", 50, 70, 500), ("erp", 40, 64, 500)])
+                                         ("pinhole", 50, 70, 500), ("erp", 40, 64, 500),
+                                         # 1001 Gaussians: the last CTA's SH block is not a multiple of 16 bytes, so the
+                                         # TMA bulk copy is replaced by the coalesced fallback for that CTA
+                                         ("erp", 48, 96, 1001), ("pinhole", 64, 64, 1003),
+                                         # 544 tiles: two tile-sort passes, several look-back blocks
+                                         ("erp", 272, 512, 30000)])
 def test_forward_backward_parity(mode, H, W, n):
     case = make_case(n, mode, H, W, seed=7)
     dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1))
@@ -22,3 +27,24 @@ def test_forward_backward_parity(mode, H, W, n):
     assert rel_l2(c["color"], o["color"]) < TOL
     for k in ("d_means", "d_cov6", "d_opac", "d_shs", "d_means2D"):
         assert rel_l2(c[k], o[k]) < TOL, k
+
+
+def test_unaligned_sh_pointer_takes_the_fallback_path():
+    """shs sliced from a larger tensor starts 300 bytes into an allocation: not 16-byte aligned, no bulk copy."""
+    from splatter360_b200.rasterizer import GaussianRasterizer
+    from helpers import make_settings
+    case = make_case(900, "erp", 48, 96, seed=31)
+    dL = torch.randn(3, 48, 96, generator=torch.Generator().manual_seed(1))
+    o = run_oracle(case, dL=dL)
+    dev = "cuda"
+    big = torch.zeros(901, 25, 3, device=dev)
+    big[1:] = case["shs"].to(dev)
+    shs = big[1:].detach().requires_grad_()
+    assert shs.data_ptr() % 16 != 0 and shs.is_contiguous()
+    means = case["means"].to(dev).requires_grad_()
+    img, _ = GaussianRasterizer(make_settings(case))(means3D=means, means2D=torch.zeros_like(means), shs=shs, colors_precomp=None,
+                                                     opacities=case["opac"].to(dev)[:, None], cov3D_precomp=case["cov6"].to(dev))
+    (img * dL.to(dev)).sum().backward()
+    assert rel_l2(img.detach().cpu().numpy(), o["color"]) < TOL
+    assert rel_l2(shs.grad.cpu().numpy(), o["d_shs"]) < TOL
+    assert rel_l2(means.grad.cpu().numpy(), o["d_means"]) < TOL
