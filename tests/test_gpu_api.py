@@ -263,3 +263,41 @@ def test_fused_depth_channel_equals_separate_depth_pass(mode):
         dec = decoder.DecoderSplattingCUDA().to(dev)
         out = dec(decoder.Gaussians(*args), pose[None, None].to(dev), K[None], near[None], far[None], (64, 80), depth_mode=mode)
         assert float((out.depth[0, 0] - d_fused.new_tensor(0) - decoder.render_depth_cuda(pose[None].to(dev), K, near, far, (64, 80), args[0], args[1], args[3], mode=mode)[0]).norm()) < 1e-3 * float(out.depth.norm() + 1)
+
+
+def test_native_erp_agrees_with_six_faces_plus_cube2equirec():
+    """the native erp render must show the same panorama as the reference's pipeline -- six 90-degree
+    pinhole faces (reference face poses, convert_cubemaps_mp.py:151-193), change_order, Cube2Equirec
+    (model_wrapper_erp.py:135-158, 395-398).  The two differ in pixel density and in the projection the EWA footprint
+    is linearised in, so this is a PSNR check on a band-limited scene (isotropic Gaussians of ~3 degrees); a wrong face
+    order, flip or axis convention gives 12-15 dB."""
+    from splatter360_b200 import cubemap, decoder
+    dev = "cuda"
+    H, W, Fw = 256, 512, 128
+    n = 1500
+    g = torch.Generator().manual_seed(3)
+    d = torch.randn(n, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    depth = 1.5 + 4 * torch.rand(n, generator=g)
+    means = d * depth[:, None]
+    cov = torch.diag_embed(((0.05 * depth) ** 2)[:, None].expand(n, 3))
+    sh = torch.zeros(n, 3, 1)
+    sh[:, :, 0] = (torch.rand(n, 3, generator=g) - 0.5) / 0.28209479177387814
+    op = 0.2 + 0.6 * torch.rand(n, generator=g)
+    from splatter360_b200 import synthetic
+    pose = synthetic.target_pose(41, jitter=0.2, max_yaw_deg=25.0).to(dev)
+    args = [t[None].to(dev) for t in (means, cov, sh, op)]
+    near, far = torch.tensor([1.0], device=dev), torch.tensor([100.0], device=dev)
+    bg = torch.zeros(1, 3, device=dev)
+    with torch.no_grad():
+        erp = decoder.render_erp(pose[None], near, far, (H, W), bg, *args)[0]
+        faces_c2w = cubemap.cube_face_extrinsics(pose)                        # [6,4,4], dataset order [U B L F R D]
+        K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev)[None]
+        faces = torch.stack([decoder.render_cuda(faces_c2w[k][None], K, near, far, (Fw, Fw), bg, *args)[0] for k in range(6)])
+        strip = torch.cat(list(cubemap.change_order(faces)), dim=-1)[None]   # [1,3,f,6f] in [F R B L U D]
+        pano = cubemap.Cube2Equirec(Fw, H, W).to(dev)(strip)[0]
+    psnr = 10 * np.log10(1.0 / float(((erp - pano) ** 2).mean()))
+    assert psnr > 26.0, f"native erp vs cube2equirec PSNR {psnr:.1f} dB"
+    band = slice(H // 2 - 32, H // 2 + 32)   # equator: both samplings are close to 1:1 there
+    psnr_c = 10 * np.log10(1.0 / float(((erp[:, band] - pano[:, band]) ** 2).mean()))
+    assert psnr_c > 32.0, f"centre band PSNR {psnr_c:.1f} dB"

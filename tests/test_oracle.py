@@ -150,3 +150,40 @@ def test_erp_seam_wrap():
     row = o["color"][0, H // 2]
     assert row[0] > 0.3 and row[W - 1] > 0.3 and row[W // 2] == 0.0
     assert abs(row[0] - row[W - 1]) < 0.05
+
+
+def test_oracle_erp_agrees_with_six_faces_plus_cube2equirec():
+    """CPU version of the convention cross-check: the oracle's erp mode vs the oracle's pinhole mode on the reference's six
+    face poses, stitched with the (golden-pinned) Cube2Equirec.  Same sign / order / flip conventions or ~13 dB."""
+    import oracle
+    from splatter360_b200 import camera, cubemap, synthetic
+    H, W, Fw = 64, 128, 32
+    n = 400
+    g = torch.Generator().manual_seed(3)
+    d = torch.randn(n, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    depth = 1.5 + 4 * torch.rand(n, generator=g)
+    means = (d * depth[:, None]).numpy()
+    s2 = (0.08 * depth) ** 2
+    cov6 = torch.stack([s2, 0 * s2, 0 * s2, s2, 0 * s2, s2], -1).numpy()
+    op = (0.2 + 0.6 * torch.rand(n, generator=g)).numpy()
+    col = torch.rand(n, 3, generator=g).numpy()
+    pose = synthetic.target_pose(41, jitter=0.2, max_yaw_deg=25.0)
+
+    def rend(c2w, mode, h, w):
+        if mode == "erp":
+            cam, tan = camera.erp_camera(c2w[None]), (1.0, 1.0)
+        else:
+            K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None]
+            cam = camera.pinhole_camera(c2w[None], K, torch.tensor([1.0]), torch.tensor([100.0]))
+            tan = (float(cam.tan_fov_x[0]), float(cam.tan_fov_y[0]))
+        o = oracle.render(means, cov6, op, colors=col, H=h, W=w, view=cam.view_matrix[0].numpy(), proj=cam.full_projection[0].numpy(),
+                          campos=cam.campos[0].numpy(), tanfovx=tan[0], tanfovy=tan[1], mode=mode, stages=False)
+        return torch.from_numpy(o["color"])
+
+    erp = rend(pose, "erp", H, W)
+    fc = cubemap.cube_face_extrinsics(pose)
+    faces = torch.stack([rend(fc[k], "pinhole", Fw, Fw) for k in range(6)])
+    pano = cubemap.Cube2Equirec(Fw, H, W)(torch.cat(list(cubemap.change_order(faces)), dim=-1)[None])[0]
+    psnr = 10 * math.log10(1.0 / float(((erp - pano) ** 2).mean()))
+    assert psnr > 24.0, psnr
