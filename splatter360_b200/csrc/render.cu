@@ -160,7 +160,10 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   uint32_t last0 = 0, last1 = 0;
   const float INF = __int_as_float(0x7f800000);
   float amin0 = in0 ? ALPHA_MIN : INF, amin1 = in1 ? ALPHA_MIN : INF;   // +inf once the pixel is finished
-  const float2 npy = make_float2(-pyf, -(pyf + 4.f));
+  // pixel offsets from the warp-block centre: instance centres are broadcast relative to that centre, which keeps
+  // dx, dy accurate to an ulp of the (small) distance even at coordinates in the thousands
+  const float offx = pxf - wcx;
+  const float2 npy = make_float2(-(pyf - wcy), -(pyf + 4.f - wcy));
 
   ChunkRegs nx;
   nx.r0 = nx.r1 = nx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -194,8 +197,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
 
     const float ddx = wrap_dx<MODE>(cull.x - wcx, Wf, halfW), ddy = cull.y - wcy;
     const bool hit = valid && (huge || rect_can_contribute(cull, ev, thr, ddx, ddy));
-    const float cx = MODE == S360_MODE_ERP ? wcx + ddx : cull.x;   // nearest periodic copy w.r.t. this warp
-    const float cy = cull.y;
+    const float cx = ddx, cy = ddy;   // centre relative to this warp's block centre (erp: nearest periodic copy)
     unsigned mask = __ballot_sync(0xffffffffu, hit);
     const unsigned hmask = MODE == S360_MODE_ERP ? __ballot_sync(0xffffffffu, hit && huge) : 0u;
     while (mask) {
@@ -204,7 +206,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
       const float xs = __shfl_sync(0xffffffffu, cx, k), ys = __shfl_sync(0xffffffffu, cy, k);
       const float4 e = s_ev[warp][k];
       const float4 c = s_col[warp][k];
-      float dx = xs - pxf;
+      float dx = xs - offx;
       if (MODE == S360_MODE_ERP && ((hmask >> k) & 1u)) dx = wrap_dx<MODE>(dx, Wf, halfW);
       const float2 dy = __fadd2_rn(make_float2(ys, ys), npy);
       const float u = e.y * dx, pb = e.x * dx * dx;
@@ -343,7 +345,10 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   PairB S;
   pair_init(S, in0, in1, (size_t)py0 * W + px, (size_t)py1 * W + px, plane, final_T, n_contrib, dL_dcolor, bg);
   float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // colour of the previously processed instance
-  const float2 npy = make_float2(-pyf, -(pyf + 4.f));
+  // pixel offsets from the warp-block centre: instance centres are broadcast relative to that centre, which keeps
+  // dx, dy accurate to an ulp of the (small) distance even at coordinates in the thousands
+  const float offx = pxf - wcx;
+  const float2 npy = make_float2(-(pyf - wcy), -(pyf + 4.f - wcy));
   // instances [0, todo) of this tile's list can matter to this warp's 64 pixels
   const uint32_t todo = __reduce_max_sync(0xffffffffu, max(S.lastc0, S.lastc1));
   const int nchunks = (int)((todo + 31u) >> 5);
@@ -382,8 +387,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
 
     const float ddx = wrap_dx<MODE>(cull.x - wcx, Wf, halfW), ddy = cull.y - wcy;
     const bool hit = valid && (huge || rect_can_contribute(cull, ev, thr, ddx, ddy));
-    const float cx = MODE == S360_MODE_ERP ? wcx + ddx : cull.x;
-    const float cy = cull.y;
+    const float cx = ddx, cy = ddy;
     unsigned mask = __ballot_sync(0xffffffffu, hit);
     const unsigned hmask = MODE == S360_MODE_ERP ? __ballot_sync(0xffffffffu, hit && huge) : 0u;
     while (mask) {
@@ -392,7 +396,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const uint32_t pos = pos0 + (uint32_t)k;
       const float xs = __shfl_sync(0xffffffffu, cx, k), ys = __shfl_sync(0xffffffffu, cy, k);
       const float4 e = s_ev[warp][k];
-      float dx = xs - pxf;
+      float dx = xs - offx;
       if (MODE == S360_MODE_ERP && ((hmask >> k) & 1u)) dx = wrap_dx<MODE>(dx, Wf, halfW);
       const float2 dy = __fadd2_rn(make_float2(ys, ys), npy);
       const float u = e.y * dx, pb = e.x * dx * dx;

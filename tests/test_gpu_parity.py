@@ -17,7 +17,9 @@ TOL = 1e-4
                                          # TMA bulk copy is replaced by the coalesced fallback for that CTA
                                          ("erp", 48, 96, 1001), ("pinhole", 64, 64, 1003),
                                          # 544 tiles: two tile-sort passes, several look-back blocks
-                                         ("erp", 272, 512, 30000)])
+                                         ("erp", 272, 512, 30000),
+                                         # the video path's resolution: 8192 tiles (13-bit tile ids)
+                                         ("erp", 1024, 2048, 40000), ("pinhole", 512, 512, 60000)])
 def test_forward_backward_parity(mode, H, W, n):
     case = make_case(n, mode, H, W, seed=7)
     dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(1))
@@ -26,7 +28,22 @@ def test_forward_backward_parity(mode, H, W, n):
     assert np.array_equal(o["radii"], c["radii"])
     assert rel_l2(c["color"], o["color"]) < TOL
     for k in ("d_means", "d_cov6", "d_opac", "d_shs", "d_means2D"):
-        assert rel_l2(c[k], o[k]) < TOL, k
+        e = rel_l2(c[k], o[k])
+        if H * W < 1_000_000:
+            assert e < TOL, (k, e)
+        else:
+            # Megapixel images with sub-pixel Gaussians: a handful of (pixel, Gaussian) pairs sit within float rounding of
+            # the alpha >= 1/255 or T < 1e-4 decisions; libm expf (oracle) and ex2.approx (GPU) decide a few of them
+            # differently, and for a Gaussian that covers three or four pixels one flipped pixel is a 5-10 % change of ITS
+            # gradient.  The image stays at ~2e-5; for the gradients require the norm to agree to 5e-4, at most 1.5 % of the Gaussians to differ by more than 1e-3
+            # (measured: 0.06-0.8 %, median per-Gaussian error 3e-6) and the remaining ones to agree to 1e-4 (measured 3e-5).
+            a = c[k].reshape(n, -1).astype(np.float64)
+            b = o[k].reshape(n, -1).astype(np.float64)
+            per = np.linalg.norm(a - b, axis=1) / (np.linalg.norm(b, axis=1) + 1e-12 * np.linalg.norm(b))
+            assert e < 5e-4, (k, e)
+            assert np.mean(per > 1e-3) < 1.5e-2 and np.mean(per > 1e-2) < 2e-3, (k, float(np.mean(per > 1e-3)))
+            keep = per <= 1e-3
+            assert rel_l2(a[keep], b[keep]) < TOL, k
 
 
 def test_unaligned_sh_pointer_takes_the_fallback_path():
