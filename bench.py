@@ -138,6 +138,7 @@ def run_ours(args):
     import torch.distributed as dist
     from splatter360_b200 import _lib, camera, synthetic
     from splatter360_b200.decoder import render_erp
+    from splatter360_b200.loss import mse_loss
     from splatter360_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +179,7 @@ def run_ours(args):
             t.grad = None
         color, _ = GaussianRasterizer(s)(means3D=means, means2D=m2d, shs=shs, colors_precomp=None,
                                          opacities=opac, cov3D_precomp=cov6)
-        loss = ((color - target) ** 2).mean()
+        loss = mse_loss(color, target)          # fused loss + seed gradient (reference: loss_mse.py:30-31)
         loss.backward()
         loss_buf.copy_(loss.detach().reshape(1))
         if world > 1:
@@ -251,7 +252,7 @@ def run_ours(args):
             m, c, sh, o = (d[k].requires_grad_() for k in ("means", "cov", "sh", "op"))
             img = render_erp(d["pose"], near, far, (H, W), bg[None], m[None], c[None], sh[None], o[None],
                              scale_invariant=False)
-            loss = ((img[0] - d["target"]) ** 2).mean()
+            loss = mse_loss(img[0], d["target"])
             loss.backward()
             if world > 1:
                 l = loss.detach().reshape(1).clone()

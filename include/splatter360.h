@@ -171,6 +171,12 @@ int s360_backward(
 /* ---- visibility mask (replaces upstream _C.mark_visible) ------------------------------------ */
 int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream);
 
+/* ---- fused photometric loss: loss = weight * mean((color - target)^2), grad = d loss / d color.
+ * Replaces the elementwise/reduction chain of /root/reference/src/loss/loss_mse.py:22-31 on the rendered image and
+ * yields the seed gradient of s360_backward in the same pass.  n = number of floats. */
+int s360_mse_loss_grad(const float* color, const float* target, int64_t n, float weight, float* loss /* [1] out */,
+                       float* grad /* [n] out */, void* stream);
+
 /* ---- debugging / introspection ---------------------------------------------------------------- */
 /* Unpack the geometry state for per-stage parity tests.  Any output may be NULL. */
 int s360_debug_unpack_geom(int32_t P, const void* geom, float* xy /*[P,2]*/, float* depth /*[P]*/,

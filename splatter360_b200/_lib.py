@@ -22,7 +22,7 @@ EXPORTS = [
     "s360_image_bytes", "s360_backward_scratch_bytes",
     "s360_forward_preprocess", "s360_forward_project", "s360_forward_order", "s360_forward_render", "s360_backward", "s360_mark_visible",
     "s360_debug_unpack_geom", "s360_debug_unpack_image",
-    "s360_profile_enable", "s360_profile_read",
+    "s360_profile_enable", "s360_profile_read", "s360_mse_loss_grad",
 ]
 
 STAGES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
@@ -90,6 +90,8 @@ def load() -> ctypes.CDLL:
     lib.s360_debug_unpack_geom.argtypes = [c_int32] + [vp] * 8
     lib.s360_debug_unpack_image.restype = c_int
     lib.s360_debug_unpack_image.argtypes = [c_int32, c_int32] + [vp] * 5
+    lib.s360_mse_loss_grad.restype = c_int
+    lib.s360_mse_loss_grad.argtypes = [vp, vp, c_int64, c_float, vp, vp, vp]
     lib.s360_profile_enable.restype = c_int
     lib.s360_profile_enable.argtypes = [c_int]
     lib.s360_profile_read.restype = c_int

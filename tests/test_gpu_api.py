@@ -301,3 +301,16 @@ def test_native_erp_agrees_with_six_faces_plus_cube2equirec():
     band = slice(H // 2 - 32, H // 2 + 32)   # equator: both samplings are close to 1:1 there
     psnr_c = 10 * np.log10(1.0 / float(((erp[:, band] - pano[:, band]) ** 2).mean()))
     assert psnr_c > 32.0, f"centre band PSNR {psnr_c:.1f} dB"
+
+
+def test_fused_mse_loss_matches_torch():
+    from splatter360_b200.loss import mse_loss
+    g = torch.Generator().manual_seed(0)
+    for shape in ((3, 64, 128), (3, 37, 53), (5,)):
+        a = torch.rand(*shape, generator=g).cuda().requires_grad_()
+        b = torch.rand(*shape, generator=g).cuda()
+        a2 = a.detach().clone().requires_grad_()
+        l1 = mse_loss(a, b, 0.7); (l1 * 3.0).backward()
+        l2 = 0.7 * ((a2 - b) ** 2).mean(); (l2 * 3.0).backward()
+        assert abs(l1.item() - l2.item()) < 1e-6 * max(1.0, abs(l2.item()))
+        assert torch.allclose(a.grad, a2.grad, rtol=1e-5, atol=1e-8)
