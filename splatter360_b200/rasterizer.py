@@ -20,6 +20,7 @@ constructs the settings by keyword keeps working unchanged:
 from __future__ import annotations
 
 import ctypes
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -118,15 +119,19 @@ def build_covariance_6(scales: Tensor, rotations: Tensor, scale_modifier: float 
 
 
 _readers = {}
+_readers_lock = threading.Lock()
 
 
 def _count_reader(device):
-    """Per-device (pinned 16-byte buffer, side stream, event) used to read S360Counters back early."""
+    """Per-device (pinned 16-byte buffer, side stream, event, lock) used to read S360Counters back early.  The lock
+    serialises the read-back of concurrent forward calls on the same device (host threads share the pinned buffer)."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    r = _readers.get(key)
-    if r is None:
-        r = (torch.empty(4, dtype=torch.int32).pin_memory(), torch.cuda.Stream(device=device), torch.cuda.Event())
-        _readers[key] = r
+    with _readers_lock:
+        r = _readers.get(key)
+        if r is None:
+            r = (torch.empty(4, dtype=torch.int32).pin_memory(), torch.cuda.Stream(device=device), torch.cuda.Event(),
+                 threading.Lock())
+            _readers[key] = r
     return r
 
 
@@ -166,18 +171,19 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
         _lib.check(lib.s360_forward_project(
             ctypes.byref(view), _ptr(means3D), _ptr(cov6), _ptr(opacities), _ptr(shs), _ptr(colors),
             _ptr(geom), _ptr(radii), _ptr(counters), _ptr(pre_scratch), st))
-        host_counts, side, ready = _count_reader(device)
-        ready.record(torch.cuda.current_stream())
-        side.wait_event(ready)
-        with torch.cuda.stream(side):
-            host_counts.copy_(counters, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(side)
-        counters.record_stream(side)
-        _lib.check(lib.s360_forward_order(
-            ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
-        done.synchronize()
-        N, nvis = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
+        host_counts, side, ready, lock = _count_reader(device)
+        with lock:
+            ready.record(torch.cuda.current_stream())
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                host_counts.copy_(counters, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(side)
+            counters.record_stream(side)
+            _lib.check(lib.s360_forward_order(
+                ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
+            done.synchronize()
+            N, nvis = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
         cap = max(N, 1)
         point_list = torch.empty(cap, dtype=torch.int32, device=device)
         bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(cap, H, W), **u8)

@@ -187,3 +187,26 @@ def test_oracle_erp_agrees_with_six_faces_plus_cube2equirec():
     pano = cubemap.Cube2Equirec(Fw, H, W)(torch.cat(list(cubemap.change_order(faces)), dim=-1)[None])[0]
     psnr = 10 * math.log10(1.0 / float(((erp - pano) ** 2).mean()))
     assert psnr > 24.0, psnr
+
+
+@pytest.mark.parametrize("mode", ["pinhole", "erp"])
+def test_oracle_size_independent_properties(mode):
+    """Properties the GPU tests use at full size, checked on the oracle itself: permutation invariance, background
+    linearity  image(bg) = image(0) + T_final * bg,  and linearity of the backward pass in dL/dcolor."""
+    H, W = (48, 64) if mode == "pinhole" else (32, 64)
+    case = make_case(300, mode, H, W, seed=9)
+    base = run_oracle(case, bg=(0.0, 0.0, 0.0))
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(300, generator=g)
+    pc = dict(case)
+    for k in ("means", "cov6", "opac", "shs"):
+        pc[k] = case[k][perm].contiguous()
+    p = run_oracle(pc, bg=(0.0, 0.0, 0.0))
+    assert rel_l2(p["color"], base["color"]) < 1e-6
+    bg = np.array([0.3, 0.6, 0.9], np.float32)
+    withbg = run_oracle(case, bg=bg)
+    assert np.allclose(withbg["color"], base["color"] + base["final_T"][None] * bg[:, None, None], atol=2e-6)
+    d1 = torch.randn(3, H, W, generator=g); d2 = torch.randn(3, H, W, generator=g)
+    g1, g2, g12 = (run_oracle(case, dL=d, stages=False) for d in (d1, d2, 2.0 * d1 - 0.5 * d2))
+    for k in ("d_means", "d_cov6", "d_opac", "d_shs"):
+        assert rel_l2(g12[k], 2.0 * g1[k] - 0.5 * g2[k]) < 2e-5, k
