@@ -53,6 +53,9 @@ class GaussianRasterizationSettings(NamedTuple):
     scene_scale: float = 1.0      # means *= s, cov3D *= s^2 inside the kernels (cuda_splatting.py:64-71), grads w.r.t. inputs
     sh_layout: int = 0            # 0: shs [P,M,3]   1: [P,3,M] (the reference's harmonics layout, no transpose copy)
     cov_layout: int = 0           # 0: cov3D [P,6]   1: [P,3,3] (upper triangle read; gradient in the same layout)
+    instance_capacity: Optional[int] = None   # None: read the instance count back (exact buffers, one small host read);
+    #                                           int: trust this capacity -> no host read at all (CUDA-graph capturable); the
+    #                                           device-side overflow flag is in ForwardState.counters, see overflowed()
     depth_mode: Optional[str] = None   # fused depth channel: "depth" | "disparity" | "relative_disparity" | "log"
     depth_near: float = 0.0            # unscaled near / far used by relative_disparity and log
     depth_far: float = 0.0
@@ -144,6 +147,7 @@ class ForwardState(NamedTuple):
     num_rendered: int
     num_visible: int
     depth: Optional[Tensor] = None   # [H,W] fused depth channel when settings.depth_mode is set
+    counters: Optional[Tensor] = None   # device int32[4]: num_rendered, overflow, num_visible, -
 
 
 def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
@@ -171,19 +175,25 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
         _lib.check(lib.s360_forward_project(
             ctypes.byref(view), _ptr(means3D), _ptr(cov6), _ptr(opacities), _ptr(shs), _ptr(colors),
             _ptr(geom), _ptr(radii), _ptr(counters), _ptr(pre_scratch), st))
-        host_counts, side, ready, lock = _count_reader(device)
-        with lock:
-            ready.record(torch.cuda.current_stream())
-            side.wait_event(ready)
-            with torch.cuda.stream(side):
-                host_counts.copy_(counters, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(side)
-            counters.record_stream(side)
+        if settings.instance_capacity is not None:
+            # sync-free path: nothing is read back; num_rendered / num_visible stay on the device
             _lib.check(lib.s360_forward_order(
                 ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
-            done.synchronize()
-            N, nvis = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
+            N, nvis = int(settings.instance_capacity), -1
+        else:
+            host_counts, side, ready, lock = _count_reader(device)
+            with lock:
+                ready.record(torch.cuda.current_stream())
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    host_counts.copy_(counters, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                counters.record_stream(side)
+                _lib.check(lib.s360_forward_order(
+                    ctypes.byref(view), _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
+                done.synchronize()
+                N, nvis = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
         cap = max(N, 1)
         point_list = torch.empty(cap, dtype=torch.int32, device=device)
         bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(cap, H, W), **u8)
@@ -204,7 +214,19 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
         if settings.debug:
             torch.cuda.synchronize(device)
     del keep
-    return color, ForwardState(geom, radii, point_list, image_state, N, nvis, depth)
+    return color, ForwardState(geom, radii, point_list, image_state, N if settings.instance_capacity is None else -1, nvis,
+                               depth, counters)
+
+
+def overflowed(state: ForwardState) -> bool:
+    """True if a forward call made with ``instance_capacity`` needed more instances than it was given (its image and
+    gradients are then incomplete).  Synchronises on the device."""
+    return state.counters is not None and bool(int(state.counters[1].item()) != 0)
+
+
+def instances_needed(state: ForwardState) -> int:
+    """Number of (tile, Gaussian) instances the view needed (synchronises); use it to pick ``instance_capacity``."""
+    return int(state.counters[0].item()) & 0xFFFFFFFF
 
 
 def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
