@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S360_ABI_VERSION 2
+#define S360_ABI_VERSION 3
 
 #define S360_MODE_PINHOLE 0 /* upstream semantics                     */
 #define S360_MODE_ERP 1     /* native equirectangular splatting      */
@@ -90,8 +90,9 @@ typedef struct S360View {
 /* Device-side counters written by the forward pass (16 bytes). */
 typedef struct S360Counters {
   uint32_t num_rendered; /* total (tile, Gaussian) instances N this view needs               */
-  uint32_t overflow;     /* set to 1 by s360_forward_render if N > instance_capacity         */
-  uint32_t num_visible;  /* Gaussians with radius > 0                                        */
+  uint32_t overflow;     /* bit 0: s360_forward_render needed N > instance_capacity;
+                            bit 1: the batched path needed more pairs than pair_capacity      */
+  uint32_t num_visible;  /* Gaussians with radius > 0; batched path: (view, Gaussian) pairs needed */
   uint32_t reserved;
 } S360Counters;
 
@@ -168,6 +169,50 @@ int s360_backward(
     void* scratch,               /* s360_backward_scratch_bytes(P)                             */
     void* stream);
 
+/* ---- batched multi-view path ------------------------------------------
+ * Renders V views of the SAME Gaussians in one pass.  The reference loops the views and calls the rasterizer once
+ * per view and batch item (/root/reference/src/model/decoder/decoder_splatting_cuda.py:44-59,
+ * cuda_splatting.py:91-126) -- six 90-degree cube faces per panorama (model_wrapper_erp.py:336-345) -- so every
+ * call re-reads all P Gaussians.  Here each Gaussian is read once and projected into all V views; every
+ * (view, Gaussian) pair that touches a tile gets a slot in pair-indexed geometry buffers (in Gaussian-major order,
+ * so equal depths keep index order exactly as V separate calls would), and the sort / emission / compositing /
+ * backward stages run ONCE over the pairs on a virtual image of V stacked views.  Results are those of V
+ * separate s360_forward_* calls; gradients are the sum over the views (what autograd produces in the reference).
+ *
+ * `view` carries the settings common to all views (P, M, image size, mode, tanfov, scene_scale, layouts, bg);
+ * its viewmatrix / projmatrix / campos point at V consecutive [16] / [16] / [3] blocks.  1 <= V <= S360_MAX_VIEWS.
+ * pair_capacity: slots in the pair buffers; V * P can never overflow, a tighter value saves memory and is
+ * reported through counters->overflow bit 1 / counters->num_visible (pairs needed) when too small.
+ * dL_dmeans2D is not produced by the batched path. */
+#define S360_MAX_VIEWS 32
+size_t s360_multi_geom_bytes(int32_t P, int64_t pair_capacity);
+size_t s360_multi_preprocess_scratch_bytes(int32_t P, int64_t pair_capacity);
+size_t s360_multi_binning_scratch_bytes(int64_t instance_capacity, int32_t V, int32_t image_height, int32_t image_width);
+size_t s360_multi_image_bytes(int32_t V, int32_t image_height, int32_t image_width);
+size_t s360_multi_backward_scratch_bytes(int64_t pair_capacity);
+/* K1 for all views -> pair geometry, radii [V,P] (may be NULL), counters (num_rendered final, num_visible = pairs) */
+int s360_multi_forward_project(const S360View* view, int32_t V, int64_t pair_capacity, const float* means3D,
+                               const float* cov3D, const float* opacities, const float* shs,
+                               const float* colors_precomp, void* geom, int32_t* radii, S360Counters* counters,
+                               void* scratch, void* stream);
+/* depth sort + scan over the pairs -> depth_order [pair_capacity], inst_offsets [pair_capacity] */
+int s360_multi_forward_order(const S360View* view, int32_t V, int64_t pair_capacity, const void* geom,
+                             uint32_t* depth_order, uint32_t* inst_offsets, S360Counters* counters, void* scratch,
+                             void* stream);
+/* emission + tile sort + compositing of all views: out_color [V,3,H,W], out_depth [V,H,W] or NULL;
+ * point_list holds pair slots sorted by (view, tile, depth, Gaussian) */
+int s360_multi_forward_render(const S360View* view, int32_t V, int64_t pair_capacity, const void* geom,
+                              const uint32_t* depth_order, const uint32_t* inst_offsets, S360Counters* counters,
+                              int64_t instance_capacity, uint32_t* point_list, void* image_state, float* out_color,
+                              float* out_depth, int32_t depth_mode, float depth_near, float depth_far, void* scratch,
+                              void* stream);
+/* dL_dcolor [V,3,H,W] -> gradients summed over the views */
+int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, const float* means3D,
+                        const float* cov3D, const float* opacities, const float* shs, const float* colors_precomp,
+                        const void* geom, const uint32_t* point_list, const void* image_state, const float* dL_dcolor,
+                        float* dL_dmeans3D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs, float* dL_dcolors,
+                        void* scratch, void* stream);
+
 /* ---- visibility mask (replaces upstream _C.mark_visible) ------------------------------------ */
 int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream);
 
@@ -176,6 +221,20 @@ int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* prese
  * yields the seed gradient of s360_backward in the same pass.  n = number of floats. */
 int s360_mse_loss_grad(const float* color, const float* target, int64_t n, float weight, float* loss /* [1] out */,
                        float* grad /* [n] out */, void* stream);
+
+/* ---- cube faces -> equirectangular panorama.  Replaces change_order
+ * (/root/reference/src/model/model_wrapper_erp.py:135-158) + the strip torch.cat (:395-398) + Cube2Equirec.forward
+ * (/root/reference/src/geometry/layers.py:108-116, a 5-D F.grid_sample) with one gather kernel; the backward is the
+ * matching scatter.  grid [H,W,3] is the reference module's sample grid (u, v in [-1,1], z = face / 2.5 - 1, faces
+ * in the order [F R B L U D]); bilinear, align_corners, border clamp.
+ *   layout 0: faces [B,C,f,6f]   the strip the reference module takes
+ *   layout 1: faces [B,6,C,f,f]  rasterizer output in the dataset face order [U B L F R D]; the reorder and the
+ *                                180-degree turn of U and D are applied by index arithmetic */
+int s360_cube2equirec_forward(const float* faces, const float* grid, int32_t layout, int32_t B, int32_t C,
+                              int32_t face_w, int32_t H, int32_t W, float* out /*[B,C,H,W]*/, void* stream);
+int s360_cube2equirec_backward(const float* dL_dout /*[B,C,H,W]*/, const float* grid, int32_t layout, int32_t B,
+                               int32_t C, int32_t face_w, int32_t H, int32_t W,
+                               float* dL_dfaces /* out, same layout as faces; zeroed by the call */, void* stream);
 
 /* ---- debugging / introspection ---------------------------------------------------------------- */
 /* Unpack the geometry state for per-stage parity tests.  Any output may be NULL. */
@@ -186,6 +245,12 @@ int s360_debug_unpack_geom(int32_t P, const void* geom, float* xy /*[P,2]*/, flo
 int s360_debug_unpack_image(int32_t image_height, int32_t image_width, const void* image_state,
                             float* final_T /*[H,W]*/, uint32_t* n_contrib /*[H,W]*/,
                             uint32_t* tile_ranges /*[tiles,2]*/, void* stream);
+
+/* Batched path: per-Gaussian pair bookkeeping (the pair of view v is slot pair_base + popcount(view_mask & ((1 << v) - 1)))
+ * and the number of pairs stored.  Pair slots index the pair geometry: s360_debug_unpack_geom(pair_capacity, geom, ...)
+ * unpacks it (tile rows there count from the top of the stacked image).  Any output may be NULL. */
+int s360_debug_unpack_pairs(int32_t P, int64_t pair_capacity, const void* geom, uint32_t* pair_base /*[P]*/,
+                            uint32_t* view_mask /*[P]*/, uint32_t* num_pairs /*[1]*/, void* stream);
 
 /* ---- optional per-stage timing (CUDA events recorded on the caller's stream around each stage).
  * Process-wide switch, off by default; used by bench.py for the roofline numbers.  The only mutable

@@ -23,7 +23,13 @@ EXPORTS = [
     "s360_forward_preprocess", "s360_forward_project", "s360_forward_order", "s360_forward_render", "s360_backward", "s360_mark_visible",
     "s360_debug_unpack_geom", "s360_debug_unpack_image",
     "s360_profile_enable", "s360_profile_read", "s360_mse_loss_grad",
+    "s360_multi_geom_bytes", "s360_multi_preprocess_scratch_bytes", "s360_multi_binning_scratch_bytes",
+    "s360_multi_image_bytes", "s360_multi_backward_scratch_bytes",
+    "s360_multi_forward_project", "s360_multi_forward_order", "s360_multi_forward_render", "s360_multi_backward",
+    "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward",
 ]
+ABI_VERSION = 3
+MAX_VIEWS = 32
 
 STAGES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
           "preprocess_bwd"]
@@ -96,7 +102,32 @@ def load() -> ctypes.CDLL:
     lib.s360_profile_enable.argtypes = [c_int]
     lib.s360_profile_read.restype = c_int
     lib.s360_profile_read.argtypes = [vp, vp, c_int]
-    if lib.s360_abi_version() != 2:
+    # batched multi-view path
+    lib.s360_multi_geom_bytes.restype = c_size_t
+    lib.s360_multi_geom_bytes.argtypes = [c_int32, c_int64]
+    lib.s360_multi_preprocess_scratch_bytes.restype = c_size_t
+    lib.s360_multi_preprocess_scratch_bytes.argtypes = [c_int32, c_int64]
+    lib.s360_multi_binning_scratch_bytes.restype = c_size_t
+    lib.s360_multi_binning_scratch_bytes.argtypes = [c_int64, c_int32, c_int32, c_int32]
+    lib.s360_multi_image_bytes.restype = c_size_t
+    lib.s360_multi_image_bytes.argtypes = [c_int32, c_int32, c_int32]
+    lib.s360_multi_backward_scratch_bytes.restype = c_size_t
+    lib.s360_multi_backward_scratch_bytes.argtypes = [c_int64]
+    head = [ctypes.POINTER(S360View), c_int32, c_int64]
+    lib.s360_multi_forward_project.restype = c_int
+    lib.s360_multi_forward_project.argtypes = head + [vp] * 10
+    lib.s360_multi_forward_order.restype = c_int
+    lib.s360_multi_forward_order.argtypes = head + [vp] * 6
+    lib.s360_multi_forward_render.restype = c_int
+    lib.s360_multi_forward_render.argtypes = head + [vp, vp, vp, vp, c_int64, vp, vp, vp, vp, c_int32, c_float, c_float, vp, vp]
+    lib.s360_multi_backward.restype = c_int
+    lib.s360_multi_backward.argtypes = head + [vp] * 16
+    for n in ("s360_cube2equirec_forward", "s360_cube2equirec_backward"):
+        getattr(lib, n).restype = c_int
+        getattr(lib, n).argtypes = [vp, vp] + [c_int32] * 6 + [vp, vp]
+    lib.s360_debug_unpack_pairs.restype = c_int
+    lib.s360_debug_unpack_pairs.argtypes = [c_int32, c_int64] + [vp] * 5
+    if lib.s360_abi_version() != ABI_VERSION:
         raise ImportError("libsplatter360.so ABI version mismatch")
     _lib = lib
     return lib

@@ -37,19 +37,23 @@ struct PreScratch {
   uint32_t *keys_a, *ids_a, *keys_b, *ids_b;
   void* radix;
   uint32_t* block_sums;
+  uint32_t* k1_status;   // batched path: [ticket][status per K1 block]
 };
-static size_t pre_scratch_carve(void* buf, int P, PreScratch* out) {
+// n = items sorted (P Gaussians, or the pair capacity of the batched path); P_status = Gaussians of the batched K1
+static size_t pre_scratch_carve(void* buf, int64_t n, PreScratch* out, int P_status = 0) {
   char* p = (char*)buf;
-  const size_t arr = align_up((size_t)(P > 0 ? P : 1) * 4, 256);
-  const size_t rad = radix_scratch_bytes(P);
-  const size_t sums = align_up(((size_t)(P > 0 ? P : 1) / 2048 + 4) * 4, 256);
+  const size_t arr = align_up((size_t)(n > 0 ? n : 1) * 4, 256);
+  const size_t rad = radix_scratch_bytes(n);
+  const size_t sums = align_up(((size_t)(n > 0 ? n : 1) / 2048 + 4) * 4, 256);
+  const size_t k1 = P_status > 0 ? align_up(((size_t)P_status / 128 + 4) * 4, 256) : 0;
   if (out) {
     out->keys_a = (uint32_t*)p; out->ids_a = (uint32_t*)(p + arr);
     out->keys_b = (uint32_t*)(p + 2 * arr); out->ids_b = (uint32_t*)(p + 3 * arr);
     out->radix = p + 4 * arr;
     out->block_sums = (uint32_t*)(p + 4 * arr + rad);
+    out->k1_status = (uint32_t*)(p + 4 * arr + rad + sums);
   }
-  return 4 * arr + rad + sums;
+  return 4 * arr + rad + sums + k1;
 }
 
 // scratch layout of s360_forward_render: [tile keys a | tile keys b | vals b | tile counts | radix]
@@ -57,10 +61,10 @@ struct BinScratch {
   uint32_t *keys_a, *keys_b, *vals_b, *tile_count;
   void* radix;
 };
-static size_t bin_scratch_carve(void* buf, int64_t cap, int H, int W, BinScratch* out) {
+static size_t bin_scratch_carve(void* buf, int64_t cap, int H, int W, BinScratch* out, int V = 1) {
   char* p = (char*)buf;
   const size_t arr = align_up((size_t)(cap > 0 ? cap : 1) * 4, 256);
-  const size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+  const size_t tiles = (size_t)V * ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
   const size_t tc = align_up((tiles > 0 ? tiles : 1) * 4 * (size_t)tile_hist_copies(), 256);
   const size_t rad = radix_scratch_bytes(cap);
   if (out) {
@@ -71,8 +75,8 @@ static size_t bin_scratch_carve(void* buf, int64_t cap, int H, int W, BinScratch
   return 3 * arr + tc + rad;
 }
 
-static int tile_bits(int H, int W) {
-  const int tiles = ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+static int tile_bits(int H, int W, int V = 1) {
+  const int tiles = V * ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
   int b = 0;
   while ((1 << b) < tiles) b++;
   return b;
@@ -85,6 +89,58 @@ static bool view_ok(const S360View* v) {
          (v->mode == S360_MODE_ERP || v->projmatrix) &&
          (v->mode != S360_MODE_ERP || v->image_width % TILE == 0) &&
          ((v->image_width + TILE - 1) / TILE) < 32768 && ((v->image_height + TILE - 1) / TILE) < 65536;
+}
+static bool batch_ok(const S360View* v, int V, int64_t pair_capacity) {
+  return view_ok(v) && V >= 1 && V <= S360_MAX_VIEWS && pair_capacity >= 0 && pair_capacity < (1ll << 30) &&
+         (int64_t)V * ((v->image_height + TILE - 1) / TILE) < 65536 &&
+         (int64_t)V * ((v->image_height + TILE - 1) / TILE) * ((v->image_width + TILE - 1) / TILE) < (1ll << 24);
+}
+
+// ---- stage bodies shared by the single-view and the batched entry points -----------------------------------
+// n_items entries of the (Gaussian- or pair-indexed) geometry state; n_dev optionally overrides the count on device
+static int order_impl(int64_t n_items, const uint32_t* n_dev, GeomState g, const PreScratch& s, uint32_t* depth_order,
+                      uint32_t* inst_offsets, S360Counters* counters, cudaStream_t st) {
+  int rc, in_b = 0;
+  { StageTimer t(S360_STAGE_DEPTH_SORT, st);
+    // the last of the four passes writes the sorted ids straight into depth_order
+    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, n_items, n_dev, 32, s.radix, st, &in_b, false, depth_order);
+    if (rc) return rc; }
+  StageTimer t(S360_STAGE_SCAN, st);
+  return launch_scan_offsets(n_items, n_dev, g, depth_order, inst_offsets, counters, s.block_sums, st);
+}
+
+static int render_impl(const S360View* view, int V, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                       const uint32_t* depth_order, const uint32_t* inst_offsets, S360Counters* counters,
+                       int64_t instance_capacity, uint32_t* point_list, void* image_state, float* out_color,
+                       float* out_depth, int32_t depth_mode, float depth_near, float depth_far, void* scratch,
+                       cudaStream_t st) {
+  const int H = view->image_height, W = view->image_width;
+  if (depth_mode < S360_DEPTH_DEPTH || depth_mode > S360_DEPTH_LOG) return S360_ERR_BAD_ARGUMENT;
+  ImageState img = carve_image(image_state, H, W, V);
+  BinScratch s;
+  bin_scratch_carve(scratch, instance_capacity, H, W, &s, V);
+  const int nbits = tile_bits(H, W, V);
+  const int passes = (nbits + 7) / 8;
+  if (passes > 3) return S360_ERR_UNSUPPORTED;
+  // the sorted ids must land in point_list: start in (keys_a, point_list) for an even number of passes,
+  // in (keys_b, vals_b) for an odd number
+  uint32_t *k0 = s.keys_a, *v0 = point_list, *k1 = s.keys_b, *v1 = s.vals_b;
+  if (passes & 1) { k0 = s.keys_b; v0 = s.vals_b; k1 = s.keys_a; v1 = point_list; }
+  int rc;
+  uint32_t* hist;
+  { StageTimer t(S360_STAGE_EMIT, st);
+    hist = radix_prepare_hist(s.radix, instance_capacity, nbits, st);
+    rc = launch_emit(*view, V, n_items, n_dev, g, depth_order, inst_offsets, counters, instance_capacity, k0, v0, s.tile_count, st); }
+  if (rc) return rc;
+  { StageTimer t(S360_STAGE_TILE_RANGES, st);
+    rc = launch_tile_scan(*view, V, s.tile_count, img.ranges, img.order, img.work, hist, passes > 0 ? passes : 1, st); }
+  if (rc) return rc;
+  int in_b = 0;
+  { StageTimer t(S360_STAGE_TILE_SORT, st);
+    rc = radix_sort_pairs(k0, v0, k1, v1, instance_capacity, &counters->num_rendered, nbits, s.radix, st, &in_b, true); }
+  if (rc) return rc;
+  StageTimer t(S360_STAGE_RENDER_FWD, st);
+  return launch_render_forward(*view, V, g, point_list, img, out_color, out_depth, depth_mode, depth_near, depth_far, st);
 }
 }  // namespace s360
 
@@ -161,13 +217,7 @@ int s360_forward_order(const S360View* view, const void* geom, uint32_t* depth_o
   GeomState g = carve_geom(const_cast<void*>(geom), P > 0 ? P : 1);
   PreScratch s;
   pre_scratch_carve(scratch, P, &s);
-  int rc, in_b = 0;
-  { StageTimer t(S360_STAGE_DEPTH_SORT, st);
-    // the last of the four passes writes the sorted ids straight into depth_order
-    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, P, nullptr, 32, s.radix, st, &in_b, false, depth_order);
-    if (rc) return rc; }
-  StageTimer t(S360_STAGE_SCAN, st);
-  return launch_scan_offsets(*view, g, depth_order, inst_offsets, counters, s.block_sums, st);
+  return order_impl(P, nullptr, g, s, depth_order, inst_offsets, counters, st);
 }
 
 int s360_forward_preprocess(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
@@ -187,34 +237,10 @@ int s360_forward_render(const S360View* view, const void* geom, const uint32_t* 
   if (instance_capacity > 0 && !point_list) return S360_ERR_BAD_ARGUMENT;
   if ((size_t)view->image_height * view->image_width > 0 && !out_color) return S360_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
-  const int P = view->P, H = view->image_height, W = view->image_width;
+  const int P = view->P;
   GeomState g = carve_geom(const_cast<void*>(geom), P > 0 ? P : 1);
-  ImageState img = carve_image(image_state, H, W);
-  BinScratch s;
-  bin_scratch_carve(scratch, instance_capacity, H, W, &s);
-  const int nbits = tile_bits(H, W);
-  const int passes = (nbits + 7) / 8;
-  if (passes > 3) return S360_ERR_UNSUPPORTED;
-  // the sorted ids must land in point_list: start in (keys_a, point_list) for an even number of passes,
-  // in (keys_b, vals_b) for an odd number
-  uint32_t *k0 = s.keys_a, *v0 = point_list, *k1 = s.keys_b, *v1 = s.vals_b;
-  if (passes & 1) { k0 = s.keys_b; v0 = s.vals_b; k1 = s.keys_a; v1 = point_list; }
-  int rc;
-  uint32_t* hist;
-  { StageTimer t(S360_STAGE_EMIT, st);
-    hist = radix_prepare_hist(s.radix, instance_capacity, nbits, st);
-    rc = launch_emit(*view, g, depth_order, inst_offsets, counters, instance_capacity, k0, v0, s.tile_count, st); }
-  if (rc) return rc;
-  { StageTimer t(S360_STAGE_TILE_RANGES, st);
-    rc = launch_tile_scan(*view, s.tile_count, img.ranges, img.order, img.work, hist, passes > 0 ? passes : 1, st); }
-  if (rc) return rc;
-  int in_b = 0;
-  { StageTimer t(S360_STAGE_TILE_SORT, st);
-    rc = radix_sort_pairs(k0, v0, k1, v1, instance_capacity, &counters->num_rendered, nbits, s.radix, st, &in_b, true); }
-  if (rc) return rc;
-  StageTimer t(S360_STAGE_RENDER_FWD, st);
-  if (depth_mode < S360_DEPTH_DEPTH || depth_mode > S360_DEPTH_LOG) return S360_ERR_BAD_ARGUMENT;
-  return launch_render_forward(*view, g, point_list, img, out_color, out_depth, depth_mode, depth_near, depth_far, st);
+  return render_impl(view, 1, P, nullptr, g, depth_order, inst_offsets, counters, instance_capacity, point_list, image_state,
+                     out_color, out_depth, depth_mode, depth_near, depth_far, scratch, st);
 }
 
 int s360_backward(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
@@ -237,14 +263,107 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
   if (rc) return rc;
   if (P > 0) {
     StageTimer t(S360_STAGE_RENDER_BWD, st);
-    rc = launch_tile_order(*view, img.work, img.order_bwd, st);
+    rc = launch_tile_order(*view, 1, img.work, img.order_bwd, st);
     if (rc) return rc;
-    rc = launch_render_backward(*view, g, point_list, img, dL_dcolor, acc, st);
+    rc = launch_render_backward(*view, 1, g, point_list, img, dL_dcolor, acc, st);
     if (rc) return rc;
   }
   StageTimer t(S360_STAGE_PREPROCESS_BWD, st);
   return launch_preprocess_backward(*view, means3D, cov3D, opacities, shs, g, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dcov3D,
                                     dL_dopacity, dL_dshs, dL_dcolors, st);
+}
+
+// ---- batched multi-view path ---------------------------------------------------------------------------------
+size_t s360_multi_geom_bytes(int32_t P, int64_t pair_capacity) { return geom_multi_bytes(P > 0 ? P : 1, pair_capacity > 0 ? pair_capacity : 1); }
+size_t s360_multi_preprocess_scratch_bytes(int32_t P, int64_t pair_capacity) { return pre_scratch_carve(nullptr, pair_capacity, nullptr, P > 0 ? P : 1); }
+size_t s360_multi_binning_scratch_bytes(int64_t cap, int32_t V, int32_t H, int32_t W) { return bin_scratch_carve(nullptr, cap, H, W, nullptr, V > 0 ? V : 1); }
+size_t s360_multi_image_bytes(int32_t V, int32_t H, int32_t W) { return image_bytes(H, W, V > 0 ? V : 1); }
+size_t s360_multi_backward_scratch_bytes(int64_t pair_capacity) { return align_up((size_t)(pair_capacity > 0 ? pair_capacity : 1) * ACC_STRIDE * sizeof(float), 256); }
+
+int s360_multi_forward_project(const S360View* view, int32_t V, int64_t pair_capacity, const float* means3D,
+                               const float* cov3D, const float* opacities, const float* shs,
+                               const float* colors_precomp, void* geom, int32_t* radii, S360Counters* counters,
+                               void* scratch, void* stream) {
+  if (!batch_ok(view, V, pair_capacity) || !counters || !geom || !scratch) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (shs == nullptr) == (colors_precomp == nullptr)) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (!means3D || !cov3D || !opacities)) return S360_ERR_BAD_ARGUMENT;
+  if (shs && view->M < (view->sh_degree < view->max_sh_degree ? (view->sh_degree + 1) * (view->sh_degree + 1)
+                                                                : (view->max_sh_degree + 1) * (view->max_sh_degree + 1)))
+    return S360_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = view->P;
+  const int64_t cap = pair_capacity > 0 ? pair_capacity : 1;
+  int rc = (int)cudaMemsetAsync(counters, 0, sizeof(S360Counters), st);
+  if (rc) return rc;
+  PairState ps;
+  GeomState g = carve_geom_multi(geom, P > 0 ? P : 1, cap, &ps);
+  PreScratch s;
+  pre_scratch_carve(scratch, pair_capacity, &s, P > 0 ? P : 1);
+  StageTimer t(S360_STAGE_PREPROCESS, st);
+  return launch_preprocess_multi(*view, V, pair_capacity, means3D, cov3D, opacities, shs, colors_precomp, g, ps, radii,
+                                 s.keys_a, s.ids_a, counters, s.k1_status, st);
+}
+
+int s360_multi_forward_order(const S360View* view, int32_t V, int64_t pair_capacity, const void* geom,
+                             uint32_t* depth_order, uint32_t* inst_offsets, S360Counters* counters, void* scratch,
+                             void* stream) {
+  if (!batch_ok(view, V, pair_capacity) || !counters || !geom || !scratch) return S360_ERR_BAD_ARGUMENT;
+  if (pair_capacity > 0 && (!depth_order || !inst_offsets)) return S360_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = view->P;
+  PairState ps;
+  GeomState g = carve_geom_multi(const_cast<void*>(geom), P > 0 ? P : 1, pair_capacity > 0 ? pair_capacity : 1, &ps);
+  PreScratch s;
+  pre_scratch_carve(scratch, pair_capacity, &s, P > 0 ? P : 1);
+  return order_impl(pair_capacity, &counters->num_visible, g, s, depth_order, inst_offsets, counters, st);
+}
+
+int s360_multi_forward_render(const S360View* view, int32_t V, int64_t pair_capacity, const void* geom,
+                              const uint32_t* depth_order, const uint32_t* inst_offsets, S360Counters* counters,
+                              int64_t instance_capacity, uint32_t* point_list, void* image_state, float* out_color,
+                              float* out_depth, int32_t depth_mode, float depth_near, float depth_far, void* scratch,
+                              void* stream) {
+  if (!batch_ok(view, V, pair_capacity) || !geom || !counters || !image_state || !scratch || instance_capacity < 0) return S360_ERR_BAD_ARGUMENT;
+  if (instance_capacity > 0 && !point_list) return S360_ERR_BAD_ARGUMENT;
+  if ((size_t)view->image_height * view->image_width > 0 && !out_color) return S360_ERR_BAD_ARGUMENT;
+  const int P = view->P;
+  PairState ps;
+  GeomState g = carve_geom_multi(const_cast<void*>(geom), P > 0 ? P : 1, pair_capacity > 0 ? pair_capacity : 1, &ps);
+  return render_impl(view, V, pair_capacity, &counters->num_visible, g, depth_order, inst_offsets, counters, instance_capacity,
+                     point_list, image_state, out_color, out_depth, depth_mode, depth_near, depth_far, scratch, (cudaStream_t)stream);
+}
+
+int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, const float* means3D,
+                        const float* cov3D, const float* opacities, const float* shs, const float* colors_precomp,
+                        const void* geom, const uint32_t* point_list, const void* image_state, const float* dL_dcolor,
+                        float* dL_dmeans3D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs, float* dL_dcolors,
+                        void* scratch, void* stream) {
+  (void)colors_precomp;
+  if (!batch_ok(view, V, pair_capacity) || !geom || !image_state || !scratch) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && (!means3D || !cov3D || !opacities || !dL_dmeans3D || !dL_dcov3D || !dL_dopacity)) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && shs && !dL_dshs) return S360_ERR_BAD_ARGUMENT;
+  if (view->P > 0 && !shs && !dL_dcolors) return S360_ERR_BAD_ARGUMENT;
+  if ((size_t)view->image_height * view->image_width > 0 && !dL_dcolor) return S360_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = view->P, H = view->image_height, W = view->image_width;
+  const int64_t cap = pair_capacity > 0 ? pair_capacity : 1;
+  PairState ps;
+  GeomState g = carve_geom_multi(const_cast<void*>(geom), P > 0 ? P : 1, cap, &ps);
+  ImageState img = carve_image(const_cast<void*>(image_state), H, W, V);
+  float* acc = (float*)scratch;
+  int rc = 0;
+  if (P > 0) {
+    StageTimer t(S360_STAGE_RENDER_BWD, st);
+    rc = launch_zero_acc(acc, ps.count, cap, st);
+    if (rc) return rc;
+    rc = launch_tile_order(*view, V, img.work, img.order_bwd, st);
+    if (rc) return rc;
+    rc = launch_render_backward(*view, V, g, point_list, img, dL_dcolor, acc, st);
+    if (rc) return rc;
+  }
+  StageTimer t(S360_STAGE_PREPROCESS_BWD, st);
+  return launch_preprocess_multi_backward(*view, V, means3D, cov3D, opacities, shs, g, ps, acc, dL_dmeans3D, dL_dcov3D,
+                                          dL_dopacity, dL_dshs, dL_dcolors, st);
 }
 
 int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream) {
@@ -274,6 +393,19 @@ int s360_debug_unpack_geom(int32_t P, const void* geom, float* xy, float* depth,
   GeomState g = carve_geom(const_cast<void*>(geom), P);
   unpack_geom_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(P, g, xy, depth, conic_opacity, rgb, tiles_touched, clamped);
   return (int)cudaGetLastError();
+}
+
+int s360_debug_unpack_pairs(int32_t P, int64_t pair_capacity, const void* geom, uint32_t* pair_base, uint32_t* view_mask,
+                            uint32_t* num_pairs, void* stream) {
+  if (P <= 0 || !geom) return 0;
+  PairState ps;
+  carve_geom_multi(const_cast<void*>(geom), P, pair_capacity > 0 ? pair_capacity : 1, &ps);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = 0;
+  if (pair_base) rc = (int)cudaMemcpyAsync(pair_base, ps.base, (size_t)P * 4, cudaMemcpyDeviceToDevice, st);
+  if (!rc && view_mask) rc = (int)cudaMemcpyAsync(view_mask, ps.mask, (size_t)P * 4, cudaMemcpyDeviceToDevice, st);
+  if (!rc && num_pairs) rc = (int)cudaMemcpyAsync(num_pairs, ps.count, 4, cudaMemcpyDeviceToDevice, st);
+  return rc;
 }
 
 int s360_debug_unpack_image(int32_t H, int32_t W, const void* image_state, float* final_T, uint32_t* n_contrib,

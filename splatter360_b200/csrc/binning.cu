@@ -35,8 +35,10 @@ __device__ __forceinline__ int64_t effective_n(int64_t n_cap, const uint32_t* n_
 
 // ---- digit histograms of up to four 8-bit passes from one read of the keys --------------------
 __global__ void __launch_bounds__(RS_THREADS)
-rs_global_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int npasses, uint32_t* __restrict__ hist) {
+rs_global_hist_kernel(const uint32_t* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ n_dev, int npasses,
+                      uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_hist[4][RS_BINS];
+  const int64_t n = effective_n(n_cap, n_dev);
   for (int i = threadIdx.x; i < 4 * RS_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
@@ -204,7 +206,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   if (!hist_ready) {
     cudaMemsetAsync(scratch, 0, align_up(4 * RS_BINS * 4, 256) + 256 + rs_status_words(n, passes) * 4, st);
     const int hb = nblocks < 592 ? nblocks : 592;
-    rs_global_hist_kernel<<<hb, RS_THREADS, 0, st>>>(keys_a, n, passes, hist);
+    rs_global_hist_kernel<<<hb, RS_THREADS, 0, st>>>(keys_a, n, n_dev, passes, hist);
     count_launch();
   }
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
@@ -237,10 +239,12 @@ constexpr int SC_ITEMS = 8, SC_TILE = RS_THREADS * SC_ITEMS;
 // until it meets an inclusive prefix, and writes the exclusive offsets of its 2048 Gaussians.
 // status: [nblocks] zero on entry; counter: zero on entry.
 __global__ void __launch_bounds__(RS_THREADS)
-scan_offsets_kernel(int P, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
-                    uint32_t* __restrict__ offsets, uint32_t* status, uint32_t* counter, S360Counters* counters) {
+scan_offsets_kernel(int P_cap, const uint32_t* __restrict__ n_dev, const uint2* __restrict__ rect,
+                    const uint32_t* __restrict__ order, uint32_t* __restrict__ offsets, uint32_t* status,
+                    uint32_t* counter, S360Counters* counters) {
   __shared__ uint32_t s_w[RS_WARPS];
   __shared__ uint32_t s_bid, s_excl;
+  const int P = (int)effective_n(P_cap, n_dev);
   if (threadIdx.x == 0) s_bid = atomicAdd(counter, 1u);
   __syncthreads();
   const uint32_t bid = s_bid;
@@ -294,7 +298,9 @@ scan_offsets_kernel(int P, const uint2* __restrict__ rect, const uint32_t* __res
     }
     if (lane == 0) {
       s_excl = excl;
-      if ((int)bid == (P + SC_TILE - 1) / SC_TILE - 1) { counters->num_rendered = excl + total; counters->overflow = 0; }
+      // the block holding the last item publishes the total (block 0 when there is nothing); bit 1 of overflow
+      // (pair buffers of the batched path) is not this stage's to clear
+      if ((int)bid == max((P + SC_TILE - 1) / SC_TILE - 1, 0)) { counters->num_rendered = excl + total; counters->overflow &= 2u; }
     }
   }
   __syncthreads();
@@ -307,19 +313,19 @@ scan_offsets_kernel(int P, const uint2* __restrict__ rect, const uint32_t* __res
   }
 }
 
-__global__ void scan_empty_kernel(S360Counters* counters) { counters->num_rendered = 0; counters->overflow = 0; }
+__global__ void scan_empty_kernel(S360Counters* counters) { counters->num_rendered = 0; counters->overflow &= 2u; }
 
-int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_order, uint32_t* offsets,
-                        S360Counters* counters, uint32_t* block_sums, cudaStream_t st) {
+int launch_scan_offsets(int64_t n_items, const uint32_t* n_dev, GeomState g, const uint32_t* depth_order,
+                        uint32_t* offsets, S360Counters* counters, uint32_t* block_sums, cudaStream_t st) {
   // block_sums scratch: [counter][status nblocks]; instance totals stay below 2^30 (status word payload)
-  const int nblocks = (v.P + SC_TILE - 1) / SC_TILE;
-  if (v.P == 0) {
+  const int nblocks = (int)((n_items + SC_TILE - 1) / SC_TILE);
+  if (n_items == 0) {
     scan_empty_kernel<<<1, 1, 0, st>>>(counters);
     count_launch();
     return (int)cudaGetLastError();
   }
   cudaMemsetAsync(block_sums, 0, (size_t)(nblocks + 1) * sizeof(uint32_t), st);
-  scan_offsets_kernel<<<nblocks, RS_THREADS, 0, st>>>(v.P, g.rect, depth_order, offsets, block_sums + 1, block_sums, counters);
+  scan_offsets_kernel<<<nblocks, RS_THREADS, 0, st>>>((int)n_items, n_dev, g.rect, depth_order, offsets, block_sums + 1, block_sums, counters);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -333,9 +339,11 @@ constexpr int EMIT_THREADS = 256;
 constexpr int TILE_HIST_COPIES = 16;   // replicated per-tile counters: spreads the L2 atomic traffic over more lines
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, int gx, int ntiles, int mode, const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
+emit_instances_kernel(int P_cap, const uint32_t* __restrict__ n_dev, int gx, int ntiles, int mode,
+                      const uint2* __restrict__ rect, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ offsets, S360Counters* counters, int64_t capacity,
                       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ tile_count) {
+  const int P = (int)effective_n(P_cap, n_dev);
   const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * EMIT_THREADS + threadIdx.x;   // position in the depth order
   uint32_t gid = 0, off = 0xffffffffu, cnt = 0;
@@ -381,7 +389,7 @@ emit_instances_kernel(int P, int gx, int ntiles, int mode, const uint2* __restri
       }
     }
   }
-  if (overflow) counters->overflow = 1;
+  if (overflow) atomicOr(&counters->overflow, 1u);
 }
 
 int tile_hist_copies() { return TILE_HIST_COPIES; }
@@ -490,28 +498,28 @@ tile_order_kernel(int ntiles, const uint32_t* __restrict__ work, uint32_t* __res
   }
 }
 
-int launch_tile_order(const S360View& v, const uint32_t* work, uint32_t* order, cudaStream_t st) {
-  const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+int launch_tile_order(const S360View& v, int NV, const uint32_t* work, uint32_t* order, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
   tile_order_kernel<<<1, 1024, 0, st>>>(gx * gy, work, order);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, const uint32_t* offsets,
-                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, uint32_t* tile_count,
-                cudaStream_t st) {
-  const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+int launch_emit(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                const uint32_t* depth_order, const uint32_t* offsets, S360Counters* counters, int64_t capacity,
+                uint32_t* keys, uint32_t* vals, uint32_t* tile_count, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
   cudaMemsetAsync(tile_count, 0, (size_t)gx * gy * TILE_HIST_COPIES * sizeof(uint32_t), st);
-  if (v.P == 0) return 0;
-  emit_instances_kernel<<<(v.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
-      v.P, gx, gx * gy, v.mode, g.rect, depth_order, offsets, counters, capacity, keys, vals, tile_count);
+  if (n_items == 0) return 0;
+  emit_instances_kernel<<<(int)((n_items + EMIT_THREADS - 1) / EMIT_THREADS), EMIT_THREADS, 0, st>>>(
+      (int)n_items, n_dev, gx, gx * gy, v.mode, g.rect, depth_order, offsets, counters, capacity, keys, vals, tile_count);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* order, uint32_t* work,
-                     uint32_t* hist, int npasses, cudaStream_t st) {
-  const int gx = (v.image_width + TILE - 1) / TILE, gy = (v.image_height + TILE - 1) / TILE;
+int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, uint2* ranges, uint32_t* order,
+                     uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
   tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, ranges, order, work, hist, npasses);
   count_launch();
   return (int)cudaGetLastError();

@@ -49,11 +49,30 @@ inline size_t geom_bytes(int P) {
   return align_up((size_t)P * REC_F4 * sizeof(float4), 256) + align_up((size_t)P * sizeof(uint2), 256) +
          align_up((size_t)P, 256);
 }
-inline ImageState carve_image(void* buf, int H, int W) {
+// Per-Gaussian bookkeeping of the batched multi-view path: which views the Gaussian has a pair in, and where its
+// pairs start in the compacted pair buffers (pair of view v = base + popc(mask & ((1 << v) - 1))).
+struct PairState {
+  uint32_t* base;   // [P]
+  uint32_t* mask;   // [P]
+  uint32_t* count;  // [1] pairs stored = min(pairs needed, pair capacity)
+};
+// geometry state of the batched path: pair-indexed GeomState for `cap` pairs followed by the per-Gaussian PairState
+inline GeomState carve_geom_multi(void* buf, int P, int64_t cap, PairState* ps) {
+  GeomState g = carve_geom(buf, (int)cap);
+  char* p = (char*)buf + geom_bytes((int)cap);
+  ps->base = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
+  ps->mask = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
+  ps->count = (uint32_t*)p;
+  return g;
+}
+inline size_t geom_multi_bytes(int P, int64_t cap) { return geom_bytes((int)cap) + 2 * align_up((size_t)P * 4, 256) + 256; }
+
+// V views are laid out as one stacked image: pixel state [V][H][W], tiles [V][gy][gx] (V = 1: the single view)
+inline ImageState carve_image(void* buf, int H, int W, int V = 1) {
   char* p = (char*)buf;
   ImageState s;
-  size_t npix = (size_t)H * W;
-  size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+  size_t npix = (size_t)V * H * W;
+  size_t tiles = (size_t)V * ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
   s.final_T = (float*)p;      p += align_up(npix * 4, 256);
   s.n_contrib = (uint32_t*)p; p += align_up(npix * 4, 256);
   s.ranges = (uint2*)p;       p += align_up(tiles * 8, 256);
@@ -62,9 +81,9 @@ inline ImageState carve_image(void* buf, int H, int W) {
   s.order_bwd = (uint32_t*)p; p += align_up(tiles * 4, 256);
   return s;
 }
-inline size_t image_bytes(int H, int W) {
-  size_t npix = (size_t)H * W;
-  size_t tiles = (size_t)((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+inline size_t image_bytes(int H, int W, int V = 1) {
+  size_t npix = (size_t)V * H * W;
+  size_t tiles = (size_t)V * ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
   return align_up(npix * 4, 256) * 2 + align_up(tiles * 8, 256) + 3 * align_up(tiles * 4, 256);
 }
 
@@ -277,6 +296,15 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
                                cudaStream_t st);
 int launch_mark_visible(const S360View& v, const float* means, uint8_t* present, cudaStream_t st);
+// batched multi-view K1 / K8+K9 (v.viewmatrix / projmatrix / campos point at NV consecutive cameras)
+int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
+                            const float* opac, const float* shs, const float* colors, GeomState g, PairState ps,
+                            int32_t* radii, uint32_t* depth_keys, uint32_t* ids, S360Counters* counters,
+                            uint32_t* status, cudaStream_t st);
+int launch_zero_acc(float* acc, const uint32_t* n_dev, int64_t cap, cudaStream_t st);
+int launch_preprocess_multi_backward(const S360View& v, int NV, const float* means, const float* cov, const float* opac,
+                                     const float* shs, GeomState g, PairState ps, const float* acc, float* d_means,
+                                     float* d_cov, float* d_opac, float* d_shs, float* d_colors, cudaStream_t st);
 
 // onesweep radix sort of (u32 key, u32 value) pairs on bits [0, nbits).  keys_a/vals_a hold the input;
 // *_b are same-sized alternates; *result_in_b says where the result landed.  n_dev (device u32, may be NULL)
@@ -288,20 +316,23 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
                      const uint32_t* n_dev, int nbits, void* scratch, cudaStream_t st, int* result_in_b,
                      bool hist_ready, uint32_t* vals_final = nullptr);
 
-int launch_scan_offsets(const S360View& v, GeomState g, const uint32_t* depth_order, uint32_t* offsets,
-                        S360Counters* counters, uint32_t* block_sums, cudaStream_t st);
-int launch_emit(const S360View& v, GeomState g, const uint32_t* depth_order, const uint32_t* offsets,
-                S360Counters* counters, int64_t capacity, uint32_t* keys, uint32_t* vals, uint32_t* tile_count,
-                cudaStream_t st);
+// n_items: entries of the geometry state the stage walks (P Gaussians, or the pair capacity of the batched path);
+// n_dev (device u32, may be NULL) overrides it with min(*n_dev, n_items); NV: views stacked on the virtual image.
+int launch_scan_offsets(int64_t n_items, const uint32_t* n_dev, GeomState g, const uint32_t* depth_order,
+                        uint32_t* offsets, S360Counters* counters, uint32_t* block_sums, cudaStream_t st);
+int launch_emit(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                const uint32_t* depth_order, const uint32_t* offsets, S360Counters* counters, int64_t capacity,
+                uint32_t* keys, uint32_t* vals, uint32_t* tile_count, cudaStream_t st);
 int tile_hist_copies();
-int launch_tile_scan(const S360View& v, const uint32_t* tile_count, uint2* ranges, uint32_t* order, uint32_t* work,
-                     uint32_t* hist, int npasses, cudaStream_t st);
-int launch_tile_order(const S360View& v, const uint32_t* work, uint32_t* order, cudaStream_t st);
+int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, uint2* ranges, uint32_t* order,
+                     uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st);
+int launch_tile_order(const S360View& v, int NV, const uint32_t* work, uint32_t* order, cudaStream_t st);
 
-int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
+// out_color [NV,3,H,W], out_depth [NV,H,W], dL_dcolor [NV,3,H,W]
+int launch_render_forward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
                           float* out_color, float* out_depth, int depth_mode, float depth_near, float depth_far,
                           cudaStream_t st);
-int launch_render_backward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
+int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
                            const float* dL_dcolor, float* acc, cudaStream_t st);
 
 constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator (9 used)

@@ -142,9 +142,10 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
                       float* __restrict__ out_depth, const DepthSpec dspec) {
   __shared__ float4 s_ev[NWARPS][32];    // A', B', C' (log2-scaled conic), log2(opacity)
   __shared__ float4 s_col[NWARPS][32];   // r, g, b, -
-  const int gx = (W + TILE - 1) / TILE;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int tile = (int)order[blockIdx.x];   // heaviest tiles first (longest-processing-time schedule)
-  const int tx = tile % gx, ty = tile / gx;
+  // batched path: the views are stacked on a virtual image, tile row = view * gy + ty (one view: view = 0)
+  const int tx = tile % gx, tyv = tile / gx, view = tyv / gy, ty = tyv - view * gy;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wx0 = tx * TILE + (warp & 1) * WARP_W, wy0 = ty * TILE + (warp >> 1) * WARP_H;
   const int px = wx0 + (lane & 7), py0 = wy0 + (lane >> 3), py1 = py0 + 4;
@@ -237,6 +238,9 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   }
   const size_t plane = (size_t)H * W;
   const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+  final_T += (size_t)view * plane; n_contrib += (size_t)view * plane;   // pixel state and outputs of this view
+  out_color += (size_t)view * 3 * plane;
+  if (out_depth) out_depth += (size_t)view * plane;
   if (in0) {
     const size_t pid = (size_t)py0 * W + px;
     final_T[pid] = T.x; n_contrib[pid] = last0;
@@ -251,11 +255,11 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   }
 }
 
-int launch_render_forward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
+int launch_render_forward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
                           float* out_color, float* out_depth, int depth_mode, float depth_near, float depth_far,
                           cudaStream_t st) {
   const int W = v.image_width, H = v.image_height;
-  const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  const int tiles = NV * ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
   if (tiles == 0) return 0;
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
@@ -329,9 +333,10 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
                        const float* __restrict__ dL_dcolor, float* __restrict__ acc) {
   __shared__ float4 s_ev[NWARPS][32];    // A', B', C', log2(opacity)
   __shared__ float4 s_col[NWARPS][32];   // r, g, b, bits of the Gaussian id
-  const int gx = (W + TILE - 1) / TILE;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int tile = (int)order[blockIdx.x];   // heaviest tiles first (longest-processing-time schedule)
-  const int tx = tile % gx, ty = tile / gx;
+  // batched path: the views are stacked on a virtual image, tile row = view * gy + ty (one view: view = 0)
+  const int tx = tile % gx, tyv = tile / gx, view = tyv / gy, ty = tyv - view * gy;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wx0 = tx * TILE + (warp & 1) * WARP_W, wy0 = ty * TILE + (warp >> 1) * WARP_H;
   const int px = wx0 + (lane & 7), py0 = wy0 + (lane >> 3), py1 = py0 + 4;
@@ -343,7 +348,8 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   const size_t plane = (size_t)H * W;
 
   PairB S;
-  pair_init(S, in0, in1, (size_t)py0 * W + px, (size_t)py1 * W + px, plane, final_T, n_contrib, dL_dcolor, bg);
+  pair_init(S, in0, in1, (size_t)py0 * W + px, (size_t)py1 * W + px, plane, final_T + (size_t)view * plane,
+            n_contrib + (size_t)view * plane, dL_dcolor + (size_t)view * 3 * plane, bg);
   float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // colour of the previously processed instance
   // pixel offsets from the warp-block centre: instance centres are broadcast relative to that centre, which keeps
   // dx, dy accurate to an ulp of the (small) distance even at coordinates in the thousands
@@ -453,10 +459,10 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   }
 }
 
-int launch_render_backward(const S360View& v, GeomState g, const uint32_t* point_list, ImageState img,
+int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
                            const float* dL_dcolor, float* acc, cudaStream_t st) {
   const int W = v.image_width, H = v.image_height;
-  const int tiles = ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  const int tiles = NV * ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
   if (tiles == 0) return 0;
   if (v.mode == S360_MODE_PINHOLE)
     render_backward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, acc);

@@ -88,9 +88,60 @@ class Cube2Equirec(nn.Module):
         grid = torch.stack([u.clamp(-0.5, 0.5) * 2, v.clamp(-0.5, 0.5) * 2, tp.float() / 2.5 - 1], dim=-1)
         self.register_buffer("sample_grid", grid.view(1, 1, H, W, 3), persistent=False)
 
-    def forward(self, cube_feat: Tensor) -> Tensor:
+    def forward_reference(self, cube_feat: Tensor) -> Tensor:
+        """The reference's own formulation (5-D ``F.grid_sample``, layers.py:108-116), pinned against the reference's
+        output in tests/test_golden.py; the checker of the CUDA kernel, not the product path."""
         bs, ch, h, w = cube_feat.shape
         assert h == self.face_w and w == 6 * self.face_w
         faces = cube_feat.view(bs, ch, h, 6, self.face_w).permute(0, 1, 3, 2, 4)      # [b, c, 6, f, f]
         grid = self.sample_grid.expand(bs, -1, -1, -1, -1)
         return F.grid_sample(faces, grid, padding_mode="border", align_corners=True).squeeze(2)
+
+    def forward(self, cube_feat: Tensor) -> Tensor:
+        """Strip [b, c, f, 6f] in the order [F R B L U D] -> panorama [b, c, H, W] (libsplatter360 gather kernel)."""
+        bs, ch, h, w = cube_feat.shape
+        assert h == self.face_w and w == 6 * self.face_w
+        return _Cube2EquirecFn.apply(cube_feat, self.sample_grid, 0, self.face_w, self.equ_h, self.equ_w)
+
+    def from_faces(self, faces: Tensor) -> Tensor:
+        """Rasterizer output [b, 6, c, f, f] in the dataset face order [U B L F R D] -> panorama [b, c, H, W]:
+        ``change_order`` + strip concatenation + stitch in one kernel."""
+        assert faces.dim() == 5 and faces.shape[1] == 6 and faces.shape[-1] == faces.shape[-2] == self.face_w
+        return _Cube2EquirecFn.apply(faces, self.sample_grid, 1, self.face_w, self.equ_h, self.equ_w)
+
+
+class _Cube2EquirecFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, faces, grid, layout, face_w, H, W):
+        import ctypes
+        from . import _lib
+        if faces.device.type != "cuda":
+            raise RuntimeError("Cube2Equirec needs CUDA tensors (use forward_reference for the torch formulation)")
+        lib = _lib.load()
+        faces_c = faces.float().contiguous()
+        grid_c = grid.to(faces.device).float().contiguous().view(H, W, 3)
+        B = faces_c.shape[0]
+        C = faces_c.shape[1] if layout == 0 else faces_c.shape[2]
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=faces.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(faces.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.s360_cube2equirec_forward(p(faces_c), p(grid_c), layout, B, C, face_w, H, W, p(out), st))
+        ctx.save_for_backward(grid_c)
+        ctx.meta = (layout, face_w, H, W, B, C, faces_c.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        (grid_c,) = ctx.saved_tensors
+        layout, face_w, H, W, B, C, shape = ctx.meta
+        g = grad_out.float().contiguous()
+        d_faces = torch.empty(shape, dtype=torch.float32, device=g.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        with torch.cuda.device(g.device):
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(lib.s360_cube2equirec_backward(p(g), p(grid_c), layout, B, C, face_w, H, W, p(d_faces), st))
+        return d_faces, None, None, None, None, None

@@ -22,7 +22,7 @@ import torch
 from torch import Tensor, nn
 
 from .camera import erp_camera, get_fov, get_projection_matrix
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
 
@@ -218,6 +218,100 @@ def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image
 
 
 # ------------------------------------------------------------------------------------------------
+# batched multi-view path: every view of a batch item in ONE rasterizer pass
+MAX_VIEWS_PER_PASS = 12   # two sets of cube faces; the pair buffers grow with views x Gaussians
+
+
+def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
+                     gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh, projection,
+                     depth_mode, max_views):
+    """cam_ext / view_matrix / full_projection: [b,v,4,4]; host: per (b,v) tuples (tanx, tany, scale, near, far) on the
+    host.  Consecutive views of one batch item that share those scalars go through one ``rasterize_views`` pass."""
+    b, v = view_matrix.shape[:2]
+    h, w = image_shape
+    colors = torch.empty((b, v, 3, h, w), dtype=torch.float32, device=view_matrix.device)
+    depths = torch.empty((b, v, h, w), dtype=torch.float32, device=view_matrix.device) if depth_mode is not None else None
+    for i in range(b):
+        j = 0
+        while j < v:
+            k = j + 1
+            while k < v and k - j < max_views and host[i][k] == host[i][j]:
+                k += 1
+            tanx, tany, scale, near, far = host[i][j]
+            settings = GaussianRasterizationSettings(
+                image_height=h, image_width=w, tanfovx=tanx, tanfovy=tany, bg=background_color[i], scale_modifier=1.0,
+                viewmatrix=view_matrix[i, j:k], projmatrix=full_projection[i, j:k], sh_degree=degree,
+                campos=cam_ext[i, j:k, :3, 3], prefiltered=False, debug=False, projection=projection,
+                scene_scale=scale, sh_layout=1, cov_layout=1, depth_mode=depth_mode, depth_near=near, depth_far=far)
+            out = rasterize_views(
+                gaussian_means[i], gaussian_opacities[i], gaussian_covariances[i], settings,
+                shs=gaussian_sh_coefficients[i] if use_sh else None,
+                colors_precomp=None if use_sh else gaussian_sh_coefficients[i, :, :, 0])
+            if depth_mode is not None:
+                colors[i, j:k], depths[i, j:k] = out
+            else:
+                colors[i, j:k] = out
+            j = k
+    return (colors, depths) if depth_mode is not None else colors
+
+
+def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                      background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                      gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
+                      use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None,
+                      max_views_per_pass: int = MAX_VIEWS_PER_PASS):
+    """``render_cuda`` for all views at once: extrinsics [b,v,4,4], intrinsics [b,v,3,3], near/far [b,v]; Gaussians
+    [b,g,...] as in ``render_cuda``.  Returns [b,v,3,h,w] (+ [b,v,h,w] depth with ``fused_depth_mode``).
+
+    Values are those of the reference's view loop (decoder_splatting_cuda.py:47-59 -> cuda_splatting.py:47-127); the
+    Gaussians are read once per batch item instead of once per view, and the sort / binning / compositing kernels run
+    once over all views (six cube faces of a panorama: one pass instead of six)."""
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    b, v = extrinsics.shape[:2]
+    scale = torch.ones_like(near)
+    if scale_invariant:
+        scale = 1 / near
+        extrinsics = extrinsics.clone()
+        extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[..., None]
+    near_s, far_s = near * scale, far * scale
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    fov_x, fov_y = get_fov(intrinsics.reshape(b * v, 3, 3)).unbind(dim=-1)
+    projection_matrix = get_projection_matrix(near_s.reshape(-1), far_s.reshape(-1), fov_x, fov_y).transpose(1, 2)
+    view_matrix = extrinsics.reshape(b * v, 4, 4).inverse().transpose(1, 2)
+    full_projection = (view_matrix @ projection_matrix).reshape(b, v, 4, 4)
+    view_matrix = view_matrix.reshape(b, v, 4, 4)
+    host = torch.stack(((0.5 * fov_x).tan().reshape(b, v), (0.5 * fov_y).tan().reshape(b, v), scale, near, far), -1).tolist()
+    host = [[tuple(x) for x in row] for row in host]
+    return _rasterize_views(extrinsics, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
+                            gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
+                            "pinhole", fused_depth_mode, max_views_per_pass)
+
+
+def render_erp_views(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
+                     background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
+                     gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
+                     use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None,
+                     max_views_per_pass: int = 4):
+    """``render_erp`` for all views at once: extrinsics_sphere [b,v,4,4], near/far [b,v] -> [b,v,3,h,w]."""
+    assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
+    b, v = extrinsics_sphere.shape[:2]
+    scale = torch.ones_like(near)
+    if scale_invariant:
+        scale = 1 / near
+        extrinsics_sphere = extrinsics_sphere.clone()
+        extrinsics_sphere[..., :3, 3] = extrinsics_sphere[..., :3, 3] * scale[..., None]
+    n = gaussian_sh_coefficients.shape[-1]
+    degree = isqrt(n) - 1
+    view_matrix = extrinsics_sphere.reshape(b * v, 4, 4).inverse().transpose(1, 2).reshape(b, v, 4, 4)
+    host = torch.stack((torch.ones_like(near), torch.ones_like(near), scale, near, far), -1).tolist()
+    host = [[tuple(x) for x in row] for row in host]
+    return _rasterize_views(extrinsics_sphere, view_matrix, view_matrix, host, image_shape, background_color,
+                            gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree,
+                            use_sh, "erp", fused_depth_mode, max_views_per_pass)
+
+
+# ------------------------------------------------------------------------------------------------
 @dataclass
 class Gaussians:
     """/root/reference/src/model/types.py:7-12."""
@@ -238,28 +332,37 @@ class DecoderSplattingCUDA(nn.Module):
     """Same forward contract as the reference decoder (decoder_splatting_cuda.py:34-97); constructed from a
     background colour instead of the Hydra dataset config."""
 
-    def __init__(self, background_color=(0.0, 0.0, 0.0)) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True) -> None:
         super().__init__()
         self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
+        self.batched_views = batched_views   # False: one rasterizer call per view, like the reference
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v, _, _ = extrinsics.shape
-        colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
         bg = self.background_color[None].expand(b, 3)
         # Without autograd (evaluation / video, model_wrapper_erp.py:319-345) the depth image is a fourth channel of
         # the colour pass; with autograd enabled the reference's separate differentiable depth pass is kept.
         fused = depth_mode is not None and not torch.is_grad_enabled()
-        depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device) if fused else None
-        for view_idx in range(v):
-            out = render_cuda(
-                extrinsics[:, view_idx], intrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
-                bg, gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities,
-                fused_depth_mode=depth_mode if fused else None)
-            if fused:
-                colors[:, view_idx], depth[:, view_idx] = out
-            else:
-                colors[:, view_idx] = out
+        depth = None
+        if self.batched_views:
+            # all views of a batch item in one rasterizer pass (the reference loops them, decoder_splatting_cuda.py:47-59)
+            out = render_cuda_views(extrinsics, intrinsics, near, far, image_shape, bg, gaussians.means,
+                                    gaussians.covariances, gaussians.harmonics, gaussians.opacities,
+                                    fused_depth_mode=depth_mode if fused else None)
+            colors, depth = out if fused else (out, None)
+        else:
+            colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
+            depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device) if fused else None
+            for view_idx in range(v):
+                out = render_cuda(
+                    extrinsics[:, view_idx], intrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
+                    bg, gaussians.means, gaussians.covariances, gaussians.harmonics, gaussians.opacities,
+                    fused_depth_mode=depth_mode if fused else None)
+                if fused:
+                    colors[:, view_idx], depth[:, view_idx] = out
+                else:
+                    colors[:, view_idx] = out
         if depth_mode is not None and not fused:
             depth = self.render_depth(gaussians, extrinsics, intrinsics, near, far, image_shape, depth_mode)
         return DecoderOutput(colors, depth)
@@ -280,26 +383,32 @@ class DecoderSplattingERP(nn.Module):
     (kept in the signature, ignored) so it can be swapped for ``DecoderSplattingCUDA`` at the call sites
     /root/reference/src/model/model_wrapper_erp.py:221-229, 336-345."""
 
-    def __init__(self, background_color=(0.0, 0.0, 0.0)) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True) -> None:
         super().__init__()
         self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
+        self.batched_views = batched_views
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Optional[Tensor], near: Tensor,
                 far: Tensor, image_shape: tuple[int, int],
                 depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v, _, _ = extrinsics.shape
-        colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
         bg = self.background_color[None].expand(b, 3)
         fused = depth_mode is not None and not torch.is_grad_enabled()
-        depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device) if fused else None
-        for view_idx in range(v):
-            out = render_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
-                             bg, gaussians.means, gaussians.covariances, gaussians.harmonics,
-                             gaussians.opacities, fused_depth_mode=depth_mode if fused else None)
-            if fused:
-                colors[:, view_idx], depth[:, view_idx] = out
-            else:
-                colors[:, view_idx] = out
+        if self.batched_views and v > 1:
+            out = render_erp_views(extrinsics, near, far, image_shape, bg, gaussians.means, gaussians.covariances,
+                                   gaussians.harmonics, gaussians.opacities, fused_depth_mode=depth_mode if fused else None)
+            colors, depth = out if fused else (out, None)
+        else:
+            colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)
+            depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device) if fused else None
+            for view_idx in range(v):
+                out = render_erp(extrinsics[:, view_idx], near[:, view_idx], far[:, view_idx], image_shape,
+                                 bg, gaussians.means, gaussians.covariances, gaussians.harmonics,
+                                 gaussians.opacities, fused_depth_mode=depth_mode if fused else None)
+                if fused:
+                    colors[:, view_idx], depth[:, view_idx] = out
+                else:
+                    colors[:, view_idx] = out
         if depth_mode is not None and not fused:
             depth = torch.zeros((b, v, *image_shape), dtype=torch.float32, device=extrinsics.device)
             for view_idx in range(v):

@@ -59,6 +59,7 @@ class GaussianRasterizationSettings(NamedTuple):
     depth_mode: Optional[str] = None   # fused depth channel: "depth" | "disparity" | "relative_disparity" | "log"
     depth_near: float = 0.0            # unscaled near / far used by relative_disparity and log
     depth_far: float = 0.0
+    pair_capacity: Optional[int] = None   # batched path only: slots for (view, Gaussian) pairs; None = V * P (never overflows)
 
 
 _MODES = {"pinhole": _lib.MODE_PINHOLE, "erp": _lib.MODE_ERP}
@@ -80,8 +81,9 @@ def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _make_view(s: GaussianRasterizationSettings, P: int, M: int, device):
-    """Build the host S360View plus the device tensors it points at (returned to keep them alive)."""
+def _make_view(s: GaussianRasterizationSettings, P: int, M: int, device, views: int = 1):
+    """Build the host S360View plus the device tensors it points at (returned to keep them alive).  ``views`` > 1:
+    viewmatrix / projmatrix / campos hold that many consecutive cameras (batched path)."""
     if s.projection not in _MODES:
         raise ValueError(f"unknown projection {s.projection!r} (expected 'pinhole' or 'erp')")
     if s.projection == "erp" and int(s.image_width) % 16 != 0:
@@ -90,8 +92,8 @@ def _make_view(s: GaussianRasterizationSettings, P: int, M: int, device):
     pm = _f32c(torch.as_tensor(s.projmatrix), device)
     cp = _f32c(torch.as_tensor(s.campos), device)
     bg = _f32c(torch.as_tensor(s.bg), device)
-    if vm.numel() != 16 or pm.numel() != 16 or cp.numel() != 3 or bg.numel() != 3:
-        raise ValueError("viewmatrix/projmatrix must have 16 elements, campos/bg 3")
+    if vm.numel() != 16 * views or pm.numel() != 16 * views or cp.numel() != 3 * views or bg.numel() != 3:
+        raise ValueError("viewmatrix/projmatrix must have 16 elements (per view), campos 3 (per view), bg 3")
     v = _lib.S360View()
     v.P, v.M, v.sh_degree = int(P), int(M), int(s.sh_degree)
     v.image_height, v.image_width = int(s.image_height), int(s.image_width)
@@ -256,6 +258,168 @@ def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6:
             torch.cuda.synchronize(device)
     del keep
     return dict(means3D=g_means, means2D=g_means2D, cov3D=g_cov, opacities=g_op, shs=g_sh, colors=g_col)
+
+
+# ------------------------------------------------------------------------------------------------
+# batched multi-view path: V views of the same Gaussians in one pass
+class MultiForwardState(NamedTuple):
+    geom: Tensor
+    point_list: Tensor
+    image_state: Tensor
+    views: int
+    pair_capacity: int
+    num_rendered: int          # -1 when instance_capacity was given (nothing read back)
+    num_pairs: int             # (view, Gaussian) pairs that touch a tile; -1 when not read back
+    radii: Optional[Tensor] = None     # [V,P] int32 when requested
+    depth: Optional[Tensor] = None     # [V,H,W] fused depth channel
+    counters: Optional[Tensor] = None  # device int32[4]: num_rendered, overflow bits, pairs needed, -
+
+
+def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov: Tensor, opacities: Tensor,
+                      shs: Optional[Tensor], colors: Optional[Tensor], want_radii: bool = False):
+    """All views of ``settings`` (viewmatrix [V,4,4], projmatrix [V,4,4], campos [V,3]; everything else shared) in one
+    pass through the batched C-ABI.  Returns (color [V,3,H,W], MultiForwardState)."""
+    lib = _lib.load()
+    device = means3D.device
+    if device.type != "cuda":
+        raise RuntimeError("splatter360_b200 rasterizer needs CUDA tensors (there is no CPU path)")
+    V = int(torch.as_tensor(settings.viewmatrix).numel() // 16)
+    if not 1 <= V <= _lib.MAX_VIEWS:
+        raise ValueError(f"the batched path takes 1..{_lib.MAX_VIEWS} views per pass, got {V}")
+    P = means3D.shape[0]
+    M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
+    H, W = int(settings.image_height), int(settings.image_width)
+    pcap = int(settings.pair_capacity) if settings.pair_capacity is not None else max(V * P, 1)
+    with torch.cuda.device(device):
+        view, keep = _make_view(settings, P, M, device, views=V)
+        u8 = dict(dtype=torch.uint8, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        geom = torch.empty(lib.s360_multi_geom_bytes(P, pcap), **u8)
+        pre_scratch = torch.empty(lib.s360_multi_preprocess_scratch_bytes(P, pcap), **u8)
+        radii = torch.empty((V, P), **i32) if want_radii else None
+        depth_order = torch.empty(pcap, **i32)
+        offsets = torch.empty(pcap, **i32)
+        counters = torch.empty(4, **i32)
+        st = _stream_ptr()
+        head = (ctypes.byref(view), ctypes.c_int32(V), ctypes.c_int64(pcap))
+        _lib.check(lib.s360_multi_forward_project(
+            *head, _ptr(means3D), _ptr(cov), _ptr(opacities), _ptr(shs), _ptr(colors),
+            _ptr(geom), _ptr(radii), _ptr(counters), _ptr(pre_scratch), st))
+        if settings.instance_capacity is not None:
+            _lib.check(lib.s360_multi_forward_order(
+                *head, _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
+            N, npairs = int(settings.instance_capacity), -1
+        else:
+            host_counts, side, ready, lock = _count_reader(device)
+            with lock:
+                ready.record(torch.cuda.current_stream())
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    host_counts.copy_(counters, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                counters.record_stream(side)
+                _lib.check(lib.s360_multi_forward_order(
+                    *head, _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters), _ptr(pre_scratch), st))
+                done.synchronize()
+                N, npairs = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
+            if npairs > pcap:
+                raise RuntimeError(f"pair_capacity {pcap} too small: this batch needs {npairs} (view, Gaussian) pairs")
+        cap = max(N, 1)
+        point_list = torch.empty(cap, **i32)
+        bin_scratch = torch.empty(lib.s360_multi_binning_scratch_bytes(cap, V, H, W), **u8)
+        image_state = torch.empty(lib.s360_multi_image_bytes(V, H, W), **u8)
+        color = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
+        depth = None
+        dmode = 0
+        if settings.depth_mode is not None:
+            if settings.depth_mode not in _lib.DEPTH_MODES:
+                raise ValueError(f"unknown depth_mode {settings.depth_mode!r}")
+            dmode = _lib.DEPTH_MODES[settings.depth_mode]
+            depth = torch.empty((V, H, W), dtype=torch.float32, device=device)
+        _lib.check(lib.s360_multi_forward_render(
+            *head, _ptr(geom), _ptr(depth_order), _ptr(offsets), _ptr(counters),
+            ctypes.c_int64(N), _ptr(point_list), _ptr(image_state), _ptr(color), _ptr(depth),
+            ctypes.c_int32(dmode), ctypes.c_float(settings.depth_near), ctypes.c_float(settings.depth_far),
+            _ptr(bin_scratch), st))
+        if settings.debug:
+            torch.cuda.synchronize(device)
+    del keep
+    return color, MultiForwardState(geom, point_list, image_state, V, pcap,
+                                    N if settings.instance_capacity is None else -1, npairs, radii, depth, counters)
+
+
+def backward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov: Tensor, opacities: Tensor,
+                       shs: Optional[Tensor], colors: Optional[Tensor], state: MultiForwardState, grad_color: Tensor):
+    """Backward of ``forward_views_raw``: grad_color [V,3,H,W] -> gradients summed over the views."""
+    lib = _lib.load()
+    device = means3D.device
+    P = means3D.shape[0]
+    M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
+    V = state.views
+    with torch.cuda.device(device):
+        view, keep = _make_view(settings, P, M, device, views=V)
+        f32 = dict(dtype=torch.float32, device=device)
+        g_means = torch.empty((P, 3), **f32)
+        g_cov = torch.empty_like(cov)
+        g_op = torch.empty((P, 1), **f32)
+        g_sh = torch.empty_like(shs) if shs is not None else None
+        g_col = torch.empty((P, 3), **f32) if colors is not None else None
+        scratch = torch.empty(lib.s360_multi_backward_scratch_bytes(state.pair_capacity), dtype=torch.uint8, device=device)
+        grad_color = _f32c(grad_color, device)
+        _lib.check(lib.s360_multi_backward(
+            ctypes.byref(view), ctypes.c_int32(V), ctypes.c_int64(state.pair_capacity),
+            _ptr(means3D), _ptr(cov), _ptr(opacities), _ptr(shs), _ptr(colors),
+            _ptr(state.geom), _ptr(state.point_list), _ptr(state.image_state), _ptr(grad_color),
+            _ptr(g_means), _ptr(g_cov), _ptr(g_op), _ptr(g_sh), _ptr(g_col), _ptr(scratch), _stream_ptr()))
+        if settings.debug:
+            torch.cuda.synchronize(device)
+    del keep
+    return dict(means3D=g_means, cov3D=g_cov, opacities=g_op, shs=g_sh, colors=g_col)
+
+
+class _RasterizeViews(torch.autograd.Function):
+    """V views in one pass.  Inputs as ``_RasterizeGaussians`` minus means2D/scales/rotations; outputs
+    color [V,3,H,W] (+ depth [V,H,W] when settings.depth_mode is set)."""
+
+    @staticmethod
+    def forward(ctx, means3D, sh, colors_precomp, opacities, cov3Ds_precomp, raster_settings):
+        device = means3D.device
+        means3D_c = _f32c(means3D, device)
+        cov = _f32c(cov3Ds_precomp, device)
+        op = _f32c(opacities, device).reshape(-1)
+        shs_c = _f32c(sh, device) if sh is not None and sh.numel() else None
+        col_c = _f32c(colors_precomp, device) if colors_precomp is not None and colors_precomp.numel() else None
+        P = means3D_c.shape[0]
+        if cov.shape != ((P, 3, 3) if raster_settings.cov_layout else (P, 6)) or op.shape[0] != P:
+            raise ValueError("cov3D_precomp must be [P,6] ([P,3,3] with cov_layout=1) and opacities [P] or [P,1]")
+        if (shs_c is None) == (col_c is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        color, state = forward_views_raw(raster_settings, means3D_c, cov, op, shs_c, col_c)
+        ctx.raster_settings = raster_settings
+        ctx.state = state
+        ctx.has_sh = shs_c is not None
+        ctx.op_shape = opacities.shape
+        ctx.save_for_backward(means3D_c, cov, op, shs_c if shs_c is not None else col_c)
+        if state.depth is not None:
+            ctx.mark_non_differentiable(state.depth)
+            return color, state.depth
+        return color
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_depth=None):
+        means3D, cov, op, feat = ctx.saved_tensors
+        shs = feat if ctx.has_sh else None
+        col = None if ctx.has_sh else feat
+        g = backward_views_raw(ctx.raster_settings, means3D, cov, op, shs, col, ctx.state, grad_out_color)
+        return (g["means3D"], g["shs"], g["colors"], g["opacities"].reshape(ctx.op_shape), g["cov3D"], None)
+
+
+def rasterize_views(means3D, opacities, cov3D_precomp, raster_settings, shs=None, colors_precomp=None):
+    """Render every camera of ``raster_settings`` (viewmatrix [V,4,4], projmatrix [V,4,4], campos [V,3]) in ONE pass:
+    color [V,3,H,W] (and depth [V,H,W] with ``depth_mode``).  Same values as V ``GaussianRasterizer`` calls; the
+    gradients are their sum.  ``means2D`` screen-space gradients are not produced."""
+    return _RasterizeViews.apply(means3D, shs, colors_precomp, opacities, cov3D_precomp, raster_settings)
 
 
 class _RasterizeGaussians(torch.autograd.Function):

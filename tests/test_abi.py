@@ -27,7 +27,7 @@ def test_view_struct_layout_and_sizes():
     from splatter360_b200 import _lib
     lib = _lib.load()
     assert ctypes.sizeof(_lib.S360View) == 8 * 4 + 6 * 4 + 4 * 4 + 4 * 8
-    assert lib.s360_abi_version() == 2
+    assert lib.s360_abi_version() == _lib.ABI_VERSION
     assert lib.s360_geom_bytes(1000) >= 1000 * (48 + 8 + 1)
     assert lib.s360_image_bytes(512, 1024) >= 512 * 1024 * 8 + 2048 * 8
     assert lib.s360_backward_scratch_bytes(10) >= 10 * 9 * 4

@@ -295,7 +295,7 @@ def test_native_erp_agrees_with_six_faces_plus_cube2equirec():
         K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev)[None]
         faces = torch.stack([decoder.render_cuda(faces_c2w[k][None], K, near, far, (Fw, Fw), bg, *args)[0] for k in range(6)])
         strip = torch.cat(list(cubemap.change_order(faces)), dim=-1)[None]   # [1,3,f,6f] in [F R B L U D]
-        pano = cubemap.Cube2Equirec(Fw, H, W).to(dev)(strip)[0]
+        pano = cubemap.Cube2Equirec(Fw, H, W).to(dev)(strip)[0]   # CUDA stitch kernel
     psnr = 10 * np.log10(1.0 / float(((erp - pano) ** 2).mean()))
     assert psnr > 26.0, f"native erp vs cube2equirec PSNR {psnr:.1f} dB"
     band = slice(H // 2 - 32, H // 2 + 32)   # equator: both samplings are close to 1:1 there
