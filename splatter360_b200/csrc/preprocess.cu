@@ -57,14 +57,39 @@ __device__ __forceinline__ void project_view(const S360View& v, const float* V, 
   o.upstream_visible = false;
   o.tiles = 0; o.rect = make_uint2(0u, 0u); o.key = 0xFFFFFFFFu; o.radius = 0; o.cl = 0;
   o.px = o.py = o.cA = o.cB = o.cC = o.op = o.hx = o.hy = 0.f;
+  // near cull first (upstream in_frustum): the same expressions geo_compute evaluates for the view-space centre, so
+  // the sort key is bit-identical; a culled Gaussian skips the covariance projection altogether
+  {
+    const float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+    const float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+    const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
+    if (MODE == S360_MODE_PINHOLE) { o.sortkey = tz; }
+    else { o.sortkey = sqrtf(tx * tx + ty * ty + tz * tz); }
+  }
+  if (!(o.sortkey > v.near_cull)) return;
+  if (MODE == S360_MODE_PINHOLE) {
+    // Cheap conservative frustum reject (most Gaussians miss most cube faces): upstream's radius is
+    // ceil(3 sqrt(lambda1)) with lambda1 <= tr(cov2D) + sqrt(0.1) and tr(cov2D) <= |J|_F^2 |W|_F^2 tr(Sigma) + 2 lowpass,
+    // |J|_F^2 <= (fx^2 (1 + limx^2) + fy^2 (1 + limy^2)) / z^2 because J uses the clamped centre.  A centre farther
+    // than that bound from the image has an empty tile rectangle, which is all the full path would find out.
+    const float fx = (float)W / (2.f * v.tanfovx), fy = (float)H / (2.f * v.tanfovy);
+    const float limx = v.fov_clamp * v.tanfovx, limy = v.fov_clamp * v.tanfovy;
+    const float iz = 1.f / o.sortkey;
+    const float jb = (fx * fx * (1.f + limx * limx) + fy * fy * (1.f + limy * limy)) * iz * iz;
+    const float wf = V[0] * V[0] + V[1] * V[1] + V[2] * V[2] + V[4] * V[4] + V[5] * V[5] + V[6] * V[6] + V[8] * V[8] +
+                     V[9] * V[9] + V[10] * V[10];
+    const float rb = 3.f * sqrtf(jb * wf * fmaxf(cv[0] + cv[3] + cv[5], 0.f) + 2.f * fabsf(v.lowpass) + 0.32f) + 2.f;
+    const float qx = PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12];
+    const float qy = PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13];
+    const float qw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
+    const float pw = 1.f / (qw + 0.0000001f);
+    const float cx = ((qx * pw + 1.f) * W - 1.f) * 0.5f, cy = ((qy * pw + 1.f) * H - 1.f) * 0.5f;
+    if (cx + rb < 0.f || cx - rb > (float)(gx * TILE) || cy + rb < 0.f || cy - rb > (float)(gy * TILE)) return;
+  }
   Geo g;
   geo_compute<MODE>(v, V, mx, my, mz, cv, g);
-  bool alive;
-  if (MODE == S360_MODE_PINHOLE) { o.sortkey = g.t[2]; }
-  else { o.sortkey = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]); }
-  alive = o.sortkey > v.near_cull;
   const float det = g.a * g.c - g.b * g.b;
-  alive = alive && (det != 0.f);
+  const bool alive = det != 0.f;
   if (alive) {
     const float det_inv = 1.f / det;
     o.cA = g.c * det_inv; o.cB = -g.b * det_inv; o.cC = g.a * det_inv;
@@ -507,11 +532,11 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
 // renders a panorama as six pinhole cube faces, i.e. six full rasterizer calls that each re-read all P Gaussians
 // (/root/reference/src/model/decoder/decoder_splatting_cuda.py:44-59, model_wrapper_erp.py:336-345).  Here every
 // Gaussian is read once, projected into all V views, and each (view, Gaussian) PAIR that touches at least one tile
-// gets a slot in compacted pair buffers -- in (Gaussian, view) order, assigned by a CTA scan plus a decoupled
-// look-back across CTAs, so that equal depths keep index order exactly like V separate calls.  Everything
+// gets a slot in compacted pair buffers -- in (Gaussian, view) order (count kernel, scan of the per-CTA counts, write
+// kernel: an in-kernel look-back was measured 45 % slower, its CTAs convoy behind the slowest predecessor), so that
+// equal depths keep index order exactly like V separate calls.  Everything
 // downstream (depth sort, scan, emission, tile sort, compositing, render backward) then runs once over the pairs on
 // a virtual image of V stacked views; per-pair moments are folded back per Gaussian in the batched K8+K9.
-constexpr uint32_t MV_AGG = 1u << 30, MV_PREFIX = 2u << 30, MV_MASK = (1u << 30) - 1u;
 constexpr int CAM_F = 36;   // floats per staged camera: V[16], PM[16], campos[3], pad
 
 __device__ __forceinline__ void stage_cameras(const S360View& v, int NV, bool need_proj, float (*s_cam)[CAM_F]) {
@@ -525,45 +550,33 @@ __device__ __forceinline__ void stage_cameras(const S360View& v, int NV, bool ne
   }
 }
 
+#ifndef S360_MV_FWD_MINB
+#define S360_MV_FWD_MINB 5
+#endif
+#ifndef S360_MV_BWD_MINB
+#define S360_MV_BWD_MINB 4
+#endif
+
+// K1a: which views does each Gaussian reach?  One thread per Gaussian projects it into all NV views (near cull and a
+// conservative frustum test reject most of them before any covariance math), stores the view mask, and the CTA
+// stores its pair count; the instance total is accumulated here (final before the sort, as in the single-view K1).
 template <int MODE>
 __global__ void __launch_bounds__(PRE_THREADS)
-preprocess_multi_kernel(const S360View v, const int NV, const uint32_t cap, const float* __restrict__ means,
-                        const float* __restrict__ cov3D, const float* __restrict__ opac,
-                        const float* __restrict__ shs, const float* __restrict__ colors, GeomState gs, PairState ps,
-                        int32_t* __restrict__ radii, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids,
-                        S360Counters* counters, uint32_t* status, uint32_t* ticket) {
-  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
-  __shared__ uint64_t s_bar;
+multi_count_kernel(const S360View v, const int NV, const float* __restrict__ means, const float* __restrict__ cov3D,
+                   const float* __restrict__ opac, PairState ps, int32_t* __restrict__ radii,
+                   uint32_t* __restrict__ block_count, S360Counters* counters) {
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
-  __shared__ uint32_t s_w[PRE_THREADS / 32];
-  __shared__ uint32_t s_bid, s_base, s_tiles;
-  if (threadIdx.x == 0) { s_bid = atomicAdd(ticket, 1u); s_tiles = 0; }
+  __shared__ uint32_t s_cnt[2];
+  if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
   stage_cameras(v, NV, MODE == S360_MODE_PINHOLE, s_cam);
-  if (shs && threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
-  const uint32_t bid = s_bid;           // CTAs take their block of Gaussians in scheduling order (look-back safe)
-  const int idx = (int)bid * PRE_THREADS + threadIdx.x;
+  const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
   const int P = v.P;
-  const int gy = (v.image_height + TILE - 1) / TILE;
-  const int row = v.M * 3;
-  const int rows = min(PRE_THREADS, P - (int)bid * PRE_THREADS);
-  const float* sh_src = shs ? shs + (size_t)bid * PRE_THREADS * row : nullptr;
-  const uint32_t sh_bytes = (uint32_t)rows * row * 4u;
-  const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u);
-  if (shs) {
-    if (bulk_ok) {
-      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, sh_bytes); bulk_load(s_sh, sh_src, sh_bytes, &s_bar); }
-    } else {
-      for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];   // visible after the scan barrier
-    }
-  }
-  // ---- phase 1: which views does this Gaussian reach?
   uint32_t mask = 0, tiles = 0;
-  float mx = 0.f, my = 0.f, mz = 0.f;
-  float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (idx < P) {
     const float sc = v.scene_scale;
-    mx = means[3 * idx] * sc; my = means[3 * idx + 1] * sc; mz = means[3 * idx + 2] * sc;
+    const float mx = means[3 * idx] * sc, my = means[3 * idx + 1] * sc, mz = means[3 * idx + 2] * sc;
+    float cv[6];
     load_cov6(v, cov3D, idx, cv);
     for (int view = 0; view < NV; view++) {
       Proj pr;
@@ -571,8 +584,92 @@ preprocess_multi_kernel(const S360View v, const int NV, const uint32_t cap, cons
       if (pr.tiles) { mask |= 1u << view; tiles += pr.tiles; }
       if (radii) radii[(size_t)view * P + idx] = pr.radius;
     }
+    ps.mask[idx] = mask;
   }
-  // ---- ordered compaction: CTA scan of the pair counts + decoupled look-back over the preceding CTAs
+  const uint32_t wc = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mask));
+  const uint32_t wt = __reduce_add_sync(0xffffffffu, tiles);
+  if ((threadIdx.x & 31) == 0) {
+    if (wc) atomicAdd(&s_cnt[0], wc);
+    if (wt) atomicAdd(&s_cnt[1], wt);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    block_count[blockIdx.x] = s_cnt[0];
+    if (s_cnt[1]) atomicAdd(&counters->num_rendered, s_cnt[1]);
+  }
+}
+
+// K1b: exclusive scan of the per-CTA pair counts (one CTA; in place) -> first pair slot of every K1c CTA, the pair
+// total, and the overflow flag.  Pairs are therefore numbered in (Gaussian, view) order: equal depths keep index
+// order through the stable sorts exactly like separate per-view calls.
+__global__ void __launch_bounds__(1024)
+multi_scan_kernel(int nblocks, uint32_t* __restrict__ block_count, uint32_t cap, PairState ps, S360Counters* counters) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t x = i < nblocks ? block_count[i] : 0u;
+    uint32_t incl = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_w[w];
+    const uint32_t carry = s_carry;
+    if (i < nblocks) block_count[i] = carry + woff + incl - x;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + woff + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t total = s_carry;
+    counters->num_visible = total;              // pairs this batch needs
+    *ps.count = min(total, cap);                // pairs stored
+    if (total > cap) atomicOr(&counters->overflow, 2u);
+  }
+}
+
+// K1c: write the pair records.  Same CTA partition as K1a; a thread's first slot is its CTA's base plus the
+// in-CTA prefix of the pair counts; only the views in the mask are projected again.
+template <int MODE>
+__global__ void __launch_bounds__(PRE_THREADS, S360_MV_FWD_MINB)
+multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const float* __restrict__ means,
+                   const float* __restrict__ cov3D, const float* __restrict__ opac, const float* __restrict__ shs,
+                   const float* __restrict__ colors, GeomState gs, PairState ps,
+                   const uint32_t* __restrict__ block_base, uint32_t* __restrict__ depth_keys,
+                   uint32_t* __restrict__ ids) {
+  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
+  __shared__ uint64_t s_bar;
+  __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
+  __shared__ uint32_t s_w[PRE_THREADS / 32];
+  const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+  const int P = v.P;
+  const int gy = (v.image_height + TILE - 1) / TILE;
+  const int row = v.M * 3;
+  const int rows = min(PRE_THREADS, P - blockIdx.x * PRE_THREADS);
+  const float* sh_src = shs ? shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
+  const uint32_t sh_bytes = (uint32_t)rows * row * 4u;
+  const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u);
+  const uint32_t mask = idx < P ? ps.mask[idx] : 0u;
+  stage_cameras(v, NV, MODE == S360_MODE_PINHOLE, s_cam);
+  if (shs && threadIdx.x == 0) mbar_init(&s_bar, 1);
+  const bool need = __syncthreads_or(mask != 0u) != 0;   // also publishes the cameras and the barrier
+  if (!need) return;                                      // no pair in this CTA: nothing to write, SH never read
+  if (shs) {
+    if (bulk_ok) {
+      if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, sh_bytes); bulk_load(s_sh, sh_src, sh_bytes, &s_bar); }
+    } else {
+      for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];   // visible after the scan barrier
+    }
+  }
+  // in-CTA exclusive prefix of the pair counts
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t cnt = (uint32_t)__popc(mask);
   uint32_t incl = cnt;
@@ -582,63 +679,29 @@ preprocess_multi_kernel(const S360View v, const int NV, const uint32_t cap, cons
     if (lane >= o) incl += y;
   }
   if (lane == 31) s_w[warp] = incl;
-  {
-    const uint32_t wt = __reduce_add_sync(0xffffffffu, tiles);
-    if (lane == 0 && wt) atomicAdd(&s_tiles, wt);
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (mask) {
+    const float sc = v.scene_scale;
+    mx = means[3 * idx] * sc; my = means[3 * idx + 1] * sc; mz = means[3 * idx + 2] * sc;
+    load_cov6(v, cov3D, idx, cv);
   }
   __syncthreads();
-  uint32_t woff = 0, total = 0;
+  uint32_t woff = 0;
 #pragma unroll
-  for (int w = 0; w < PRE_THREADS / 32; w++) { woff += (w < warp) ? s_w[w] : 0u; total += s_w[w]; }
-  if (warp == 0) {
-    volatile uint32_t* vs = status;
-    uint32_t excl = 0;
-    if (bid == 0) {
-      if (lane == 0) vs[0] = total | MV_PREFIX;
-    } else {
-      if (lane == 0) vs[bid] = total | MV_AGG;
-      int64_t hi = (int64_t)bid - 1;
-      while (true) {
-        const int64_t j = hi - lane;
-        uint32_t sv = MV_PREFIX;
-        if (j >= 0) sv = vs[j];
-        const uint32_t flag = sv & ~MV_MASK;
-        const unsigned notready = __ballot_sync(0xffffffffu, flag == 0u);
-        const unsigned isprefix = __ballot_sync(0xffffffffu, flag == MV_PREFIX);
-        const int first_nr = notready ? __ffs(notready) - 1 : 32;
-        const int first_px = isprefix ? __ffs(isprefix) - 1 : 32;
-        const int upto = first_px < first_nr ? first_px + 1 : first_nr;
-        const uint32_t add = (lane < upto) ? (sv & MV_MASK) : 0u;
-        excl += __reduce_add_sync(0xffffffffu, add);
-        if (first_px < first_nr) break;
-        hi -= upto;
-      }
-      if (lane == 0) vs[bid] = (excl + total) | MV_PREFIX;
-    }
-    if (lane == 0) {
-      s_base = excl;
-      if (s_tiles) atomicAdd(&counters->num_rendered, s_tiles);
-      if (bid == gridDim.x - 1) {
-        counters->num_visible = excl + total;                 // pairs this batch needs
-        *ps.count = min(excl + total, cap);                   // pairs stored
-        if (excl + total > cap) atomicOr(&counters->overflow, 2u);
-      }
-    }
-  }
-  __syncthreads();
-  uint32_t slot = s_base + woff + incl - cnt;
+  for (int w = 0; w < PRE_THREADS / 32; w++) woff += (w < warp) ? s_w[w] : 0u;
+  uint32_t slot = block_base[blockIdx.x] + woff + incl - cnt;
   // every thread waits for the bulk copy: no thread may leave while the TMA still writes this CTA's shared memory
   if (shs && bulk_ok) mbar_wait(&s_bar, 0);
   if (idx >= P) return;
   ps.base[idx] = slot;
-  // ---- phase 2: write the pair records (geometry recomputed: cheaper than keeping V results in registers)
   uint32_t kept = mask;
   float col[3] = {0.f, 0.f, 0.f};
   uint8_t clc = 0;
   int col_view = -1;
   for (uint32_t m = mask; m; m &= m - 1, slot++) {
     const int view = __ffs(m) - 1;
-    if (slot >= cap) { kept &= ~m; break; }   // pair buffers full: drop this and the remaining views (flagged above)
+    if (slot >= cap) { kept &= ~m; break; }   // pair buffers full: drop this and the remaining views (flagged by K1b)
     const float* cam = s_cam[view];
     Proj pr;
     project_view<MODE>(v, cam, cam + 16, mx, my, mz, cv, opac, idx, pr);
@@ -659,7 +722,7 @@ preprocess_multi_kernel(const S360View v, const int NV, const uint32_t cap, cons
     depth_keys[slot] = pr.key;
     ids[slot] = slot;
   }
-  ps.mask[idx] = kept;
+  if (kept != mask) ps.mask[idx] = kept;
 }
 
 int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
@@ -670,17 +733,21 @@ int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, co
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
   if (smem > 190 * 1024) return S360_ERR_UNSUPPORTED;
-  // status: [ticket][status grid]
-  cudaMemsetAsync(status, 0, (size_t)(grid + 1) * sizeof(uint32_t), st);
   const uint32_t cap = (uint32_t)(pair_capacity < 0x3fffffff ? pair_capacity : 0x3fffffff);
+  uint32_t* block_count = status;   // [grid]: pair count per CTA, scanned in place to the CTA's first slot
+  if (v.mode == S360_MODE_PINHOLE)
+    multi_count_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, 0, st>>>(v, NV, means, cov, opac, ps, radii, block_count, counters);
+  else
+    multi_count_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, NV, means, cov, opac, ps, radii, block_count, counters);
+  multi_scan_kernel<<<1, 1024, 0, st>>>(grid, block_count, cap, ps, counters);
   if (v.mode == S360_MODE_PINHOLE) {
-    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_multi_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, radii, depth_keys, ids, counters, status + 1, status);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    multi_write_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
   } else {
-    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_multi_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, radii, depth_keys, ids, counters, status + 1, status);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    multi_write_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
   }
-  count_launch();
+  count_launch(3);
   return (int)cudaGetLastError();
 }
 
@@ -749,7 +816,7 @@ __device__ __forceinline__ void sh_coeff_backward(const S360View& v, float* sh, 
 // Batched K8 + K9: one thread per Gaussian folds the moments of all its pairs into ONE set of gradients
 // (the reference gets the same sum from autograd over V separate rasterizer calls).
 template <int MODE>
-__global__ void __launch_bounds__(PRE_THREADS)
+__global__ void __launch_bounds__(PRE_THREADS, S360_MV_BWD_MINB)
 preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __restrict__ means,
                                  const float* __restrict__ cov3D, const float* __restrict__ opac,
                                  const float* __restrict__ shs, GeomState gs, PairState ps,

@@ -276,7 +276,8 @@ class MultiForwardState(NamedTuple):
 
 
 def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov: Tensor, opacities: Tensor,
-                      shs: Optional[Tensor], colors: Optional[Tensor], want_radii: bool = False):
+                      shs: Optional[Tensor], colors: Optional[Tensor], want_radii: bool = False,
+                      _pair_capacity_override: Optional[int] = None):
     """All views of ``settings`` (viewmatrix [V,4,4], projmatrix [V,4,4], campos [V,3]; everything else shared) in one
     pass through the batched C-ABI.  Returns (color [V,3,H,W], MultiForwardState)."""
     lib = _lib.load()
@@ -289,7 +290,17 @@ def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, 
     P = means3D.shape[0]
     M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
     H, W = int(settings.image_height), int(settings.image_width)
-    pcap = int(settings.pair_capacity) if settings.pair_capacity is not None else max(V * P, 1)
+    if settings.pair_capacity is not None:
+        pcap = int(settings.pair_capacity)
+    elif _pair_capacity_override is not None:
+        pcap = int(_pair_capacity_override)
+    elif settings.projection == "erp" or settings.instance_capacity is not None:
+        pcap = V * P   # erp: every Gaussian is in every view; the sync-free mode cannot retry: worst case
+    else:
+        # pinhole views look in different directions (cube faces: ~1.05 pairs per Gaussian): start with 2 per Gaussian,
+        # the count read back below triggers one exact retry when that was too small
+        pcap = min(V * P, 2 * P + 4096)
+    pcap = max(pcap, 1)
     with torch.cuda.device(device):
         view, keep = _make_view(settings, P, M, device, views=V)
         u8 = dict(dtype=torch.uint8, device=device)
@@ -324,7 +335,10 @@ def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, 
                 done.synchronize()
                 N, npairs = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
             if npairs > pcap:
-                raise RuntimeError(f"pair_capacity {pcap} too small: this batch needs {npairs} (view, Gaussian) pairs")
+                if settings.pair_capacity is not None:
+                    raise RuntimeError(f"pair_capacity {pcap} too small: this batch needs {npairs} (view, Gaussian) pairs")
+                del geom, pre_scratch, depth_order, offsets
+                return forward_views_raw(settings, means3D, cov, opacities, shs, colors, want_radii, npairs)
         cap = max(N, 1)
         point_list = torch.empty(cap, **i32)
         bin_scratch = torch.empty(lib.s360_multi_binning_scratch_bytes(cap, V, H, W), **u8)
