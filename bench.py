@@ -290,6 +290,14 @@ def run_ours(args):
                "api": "splatter360_b200.io.HostSceneFeeder (pinned host -> device, upload of step i+1 overlaps step i) + "
                       "splatter360_b200.decoder.render_erp fwd + bwd + loss D2H; every step's H2D copy is inside the timed region"}
 
+    # ---- the reference's own way of producing this panorama: six 90-degree pinhole faces of edge H/2
+    # (model_wrapper_erp.py:202-205, 336-345) + Cube2Equirec -- once as six separate rasterizer calls (the reference's
+    # call pattern through this library's kernels), once as ONE batched pass + the stitch kernel.  Side measurement on
+    # rank 0 at N=1; it does not enter `value`.
+    cube6 = None
+    if world == 1 and not args.no_cube6:
+        cube6 = cube6_run(dev, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), poses[Wm + K - 1])
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,11 +346,66 @@ def run_ours(args):
                    "sharding": "one independent view per GPU per step; NCCL all-reduce of the scalar loss only",
                    "api": "diff_gaussian_rasterization-compatible GaussianRasterizer autograd call, inputs resident in HBM"},
         "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
-        "cpu_baseline": cpu_baseline, "final_loss": final_loss,
+        "cpu_baseline": cpu_baseline, "final_loss": final_loss, "cube6_reference_style": cube6,
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cube6_run(dev, means, cov6, opac, shs, pose, iters=20):
+    """Six cube faces of edge H/2 for the same scene and pose, forward+backward with an MSE seed on the stitched
+    panorama: (a) six separate rasterizer calls, (b) one batched pass (s360_multi_*), both followed by the stitch
+    kernel.  CUDA events, median of `iters`."""
+    import torch
+    from splatter360_b200 import camera, cubemap, rasterizer as R
+    F = H // 2
+    faces = cubemap.cube_face_extrinsics(pose)
+    Kf = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev)[None].repeat(6, 1, 1)
+    cam = camera.pinhole_camera(faces, Kf, torch.ones(6, device=dev), torch.full((6,), 100.0, device=dev))
+    mk = lambda vm, pm, cp: R.GaussianRasterizationSettings(
+        image_height=F, image_width=F, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3, device=dev), scale_modifier=1.0,
+        viewmatrix=vm.contiguous(), projmatrix=pm.contiguous(), sh_degree=SH_DEGREE, campos=cp.contiguous(),
+        prefiltered=False, debug=False, projection="pinhole")
+    s6 = mk(cam.view_matrix, cam.full_projection, cam.campos)
+    s1 = [mk(cam.view_matrix[k], cam.full_projection[k], cam.campos[k]) for k in range(6)]
+    c2e = cubemap.Cube2Equirec(F, H, W).to(dev)
+    target = torch.rand(3, H, W, device=dev)
+    info = {}
+
+    def stitch_grad(faces_img):
+        f = faces_img[None].detach().requires_grad_()
+        pano = c2e.from_faces(f)
+        (g,) = torch.autograd.grad(pano, f, 2 * (pano - target[None]) / pano.numel())
+        return g[0]
+
+    def batched():
+        color, st = R.forward_views_raw(s6, means, cov6, opac, shs, None)
+        info.update(pairs=st.num_pairs, instances=st.num_rendered)
+        R.backward_views_raw(s6, means, cov6, opac, shs, None, st, stitch_grad(color))
+
+    def separate():
+        outs = [R.forward_raw(s1[k], means, cov6, opac, shs, None) for k in range(6)]
+        g = stitch_grad(torch.stack([o[0] for o in outs]))
+        for k in range(6):
+            R.backward_raw(s1[k], means, cov6, opac, shs, None, outs[k][1], g[k])
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    t_b, t_s = timeit(batched), timeit(separate)
+    P = means.shape[0]
+    return {"what": "same scene/pose as the reference renders it: six 256x256 pinhole faces + Cube2Equirec, fwd+bwd (MSE on the panorama)",
+            "batched_one_pass_ms": t_b, "six_separate_calls_ms": t_s, "speedup": t_s / t_b,
+            "batched_gaussians_per_s": P / (t_b * 1e-3), "batched_views_per_s": 1e3 / t_b, **info}
 
 
 def cpu_oracle_run(sc, pose, P_sample, repeats=1):
@@ -419,6 +482,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cube6", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
