@@ -140,8 +140,9 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
                       const uint32_t* __restrict__ order, uint32_t* __restrict__ work,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, const DepthSpec dspec) {
-  __shared__ float4 s_ev[NWARPS][32];    // A', B', C' (log2-scaled conic), log2(opacity)
-  __shared__ float4 s_col[NWARPS][32];   // r, g, b, -
+  // survivors of the current chunk, compacted in list order: [0] = A', B', C' (log2-scaled conic), log2(opacity);
+  // [1] = -r, -g, -b, -depth value; [2] = centre relative to the warp block (x, y), wide flag, position in the tile list
+  __shared__ float4 s_sv[NWARPS][3][32];
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int tile = (int)order[blockIdx.x];   // heaviest tiles first (longest-processing-time schedule)
   // batched path: the views are stacked on a virtual image, tile row = view * gy + ty (one view: view = 0)
@@ -185,10 +186,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     stage_instance(nx.r0, nx.r1, nx.r2, cull, ev, col);
     const float thr = col.w;
     const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
-    s_ev[warp][lane] = ev;
-    // negated: the loop carries -alpha.  .w = the per-Gaussian depth value of the fused depth channel
-    s_col[warp][lane] = make_float4(-col.x, -col.y, -col.z, -depth_value(dspec, nx.r2.w));
-    __syncwarp();
+    const float dval = -depth_value(dspec, nx.r2.w);   // per-Gaussian value of the fused depth channel (negated like rgb)
     // keep the pipeline full: records of the next chunk, ids of the one after
     nx.gid = gid2;
 #if S360_FWD_PREFETCH
@@ -196,20 +194,27 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
 #endif
     gid2 = (base + 64 + lane < range.y) ? point_list[base + 64 + lane] : 0u;
 
+    // centre relative to this warp's block centre (erp: nearest periodic copy)
     const float ddx = wrap_dx<MODE>(cull.x - wcx, Wf, halfW), ddy = cull.y - wcy;
     const bool hit = valid && (huge || rect_can_contribute(cull, ev, thr, ddx, ddy));
-    const float cx = ddx, cy = ddy;   // centre relative to this warp's block centre (erp: nearest periodic copy)
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    const unsigned hmask = MODE == S360_MODE_ERP ? __ballot_sync(0xffffffffu, hit && huge) : 0u;
-    while (mask) {
-      const int k = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float xs = __shfl_sync(0xffffffffu, cx, k), ys = __shfl_sync(0xffffffffu, cy, k);
-      const float4 e = s_ev[warp][k];
-      const float4 c = s_col[warp][k];
-      float dx = xs - offx;
-      if (MODE == S360_MODE_ERP && ((hmask >> k) & 1u)) dx = wrap_dx<MODE>(dx, Wf, halfW);
-      const float2 dy = __fadd2_rn(make_float2(ys, ys), npy);
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      // survivors are written compacted, in list order: the evaluation loop just walks the slice
+      const int slot = __popc(mask & ((1u << lane) - 1u));
+      s_sv[warp][0][slot] = ev;
+      s_sv[warp][1][slot] = make_float4(-col.x, -col.y, -col.z, dval);   // negated: the loop carries -alpha
+      s_sv[warp][2][slot] = make_float4(ddx, ddy, huge ? 1.f : 0.f, __uint_as_float(base - range.x + (uint32_t)lane + 1u));
+    }
+    __syncwarp();
+    const int nsv = __popc(mask);
+    const float4* sv = &s_sv[warp][0][0];
+    for (int k = 0; k < nsv; k++) {
+      const float4 e = sv[k];
+      const float4 c = sv[32 + k];
+      const float4 g = sv[64 + k];
+      float dx = g.x - offx;
+      if (MODE == S360_MODE_ERP && g.z != 0.f) dx = wrap_dx<MODE>(dx, Wf, halfW);
+      const float2 dy = __fadd2_rn(make_float2(g.y, g.y), npy);
       const float u = e.y * dx, pb = e.x * dx * dx;
       const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
       const float2 a = __fadd2_rn(p, make_float2(e.w, e.w));          // power * log2(e) + log2(opacity)
@@ -225,7 +230,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
       Cb = __ffma2_rn(make_float2(c.z, c.z), nw, Cb);
       Cd = __ffma2_rn(make_float2(c.w, c.w), nw, Cd);
       T = __ffma2_rn(T, nae, T);
-      const uint32_t pos = base - range.x + (uint32_t)k + 1u;
+      const uint32_t pos = __float_as_uint(g.w);
       if (nae.x < 0.f) last0 = pos;
       if (nae.y < 0.f) last1 = pos;
     }
@@ -331,8 +336,9 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
                        const uint32_t* __restrict__ order,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dcolor, float* __restrict__ acc) {
-  __shared__ float4 s_ev[NWARPS][32];    // A', B', C', log2(opacity)
-  __shared__ float4 s_col[NWARPS][32];   // r, g, b, bits of the Gaussian id
+  // survivors of the current chunk, compacted back-to-front: [0] = A', B', C', log2(opacity); [1] = r, g, b, bits of the
+  // Gaussian id; [2] = centre relative to the warp block (x, y), wide flag, position in the tile list
+  __shared__ float4 s_sv[NWARPS][3][32];
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const int tile = (int)order[blockIdx.x];   // heaviest tiles first (longest-processing-time schedule)
   // batched path: the views are stacked on a virtual image, tile row = view * gy + ty (one view: view = 0)
@@ -382,9 +388,6 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     const float thr = col.w;
     const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
     col.w = __uint_as_float(nx.gid);
-    s_ev[warp][lane] = ev;
-    s_col[warp][lane] = col;
-    __syncwarp();
     nx.gid = gid2;                       // chunks below the last one are always full
 #if S360_BWD_PREFETCH
     load_records(nx, rec, ci > 0);
@@ -393,18 +396,24 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
 
     const float ddx = wrap_dx<MODE>(cull.x - wcx, Wf, halfW), ddy = cull.y - wcy;
     const bool hit = valid && (huge || rect_can_contribute(cull, ev, thr, ddx, ddy));
-    const float cx = ddx, cy = ddy;
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    const unsigned hmask = MODE == S360_MODE_ERP ? __ballot_sync(0xffffffffu, hit && huge) : 0u;
-    while (mask) {
-      const int k = 31 - __clz(mask);
-      mask &= ~(1u << k);
-      const uint32_t pos = pos0 + (uint32_t)k;
-      const float xs = __shfl_sync(0xffffffffu, cx, k), ys = __shfl_sync(0xffffffffu, cy, k);
-      const float4 e = s_ev[warp][k];
-      float dx = xs - offx;
-      if (MODE == S360_MODE_ERP && ((hmask >> k) & 1u)) dx = wrap_dx<MODE>(dx, Wf, halfW);
-      const float2 dy = __fadd2_rn(make_float2(ys, ys), npy);
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      // compacted back-to-front: slot = number of surviving lanes above this one
+      const int slot = __popc(mask & ~((2u << lane) - 1u));
+      s_sv[warp][0][slot] = ev;
+      s_sv[warp][1][slot] = col;
+      s_sv[warp][2][slot] = make_float4(ddx, ddy, huge ? 1.f : 0.f, __uint_as_float(pos0 + (uint32_t)lane));
+    }
+    __syncwarp();
+    const int nsv = __popc(mask);
+    const float4* sv = &s_sv[warp][0][0];
+    for (int k = 0; k < nsv; k++) {
+      const float4 e = sv[k];
+      const float4 g = sv[64 + k];
+      const uint32_t pos = __float_as_uint(g.w);
+      float dx = g.x - offx;
+      if (MODE == S360_MODE_ERP && g.z != 0.f) dx = wrap_dx<MODE>(dx, Wf, halfW);
+      const float2 dy = __fadd2_rn(make_float2(g.y, g.y), npy);
       const float u = e.y * dx, pb = e.x * dx * dx;
       const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
       // same expressions as the forward pass, so that T / (1 - alpha) undoes exactly what it applied
@@ -413,7 +422,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const bool ok0 = (pos < S.lastc0) && (p.x <= 0.f) && (-nal0 >= ALPHA_MIN);
       const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
-      const float4 c = s_col[warp][k];
+      const float4 c = sv[32 + k];
       // A pixel that does not take this instance runs the same recurrences with alpha = 0, which only folds the
       // pending (last_alpha, last_color) term into accum_rec early -- bit-identical to skipping it.
       const float2 nae = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);                  // -alpha or 0

@@ -44,3 +44,22 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu():
     v.P, v.image_height, v.image_width, v.mode = 10, 16, 16, 7   # invalid mode, null matrices
     assert lib.s360_mark_visible(ctypes.byref(v), None, None, None) == -1
     assert lib.s360_forward_preprocess(ctypes.byref(v), *([None] * 12)) == -1
+
+
+def test_batched_entry_points_size_queries_and_argument_checks():
+    from splatter360_b200 import _lib
+    lib = _lib.load()
+    P, cap, V = 1000, 2500, 6
+    assert lib.s360_multi_geom_bytes(P, cap) >= cap * (48 + 8 + 1) + 2 * 4 * P + 4
+    assert lib.s360_multi_preprocess_scratch_bytes(P, cap) >= 4 * 4 * cap + 4 * (P // 128 + 1)
+    assert lib.s360_multi_image_bytes(V, 256, 256) >= V * (256 * 256 * 8 + 256 * 8)
+    assert lib.s360_multi_image_bytes(1, 512, 1024) == lib.s360_image_bytes(512, 1024)
+    assert lib.s360_multi_binning_scratch_bytes(1 << 20, 1, 512, 1024) == lib.s360_binning_scratch_bytes(1 << 20, 512, 1024)
+    assert lib.s360_multi_backward_scratch_bytes(cap) >= cap * 9 * 4
+    v = _lib.S360View()
+    v.P, v.image_height, v.image_width, v.mode, v.scene_scale = 10, 16, 16, 0, 1.0
+    # null camera pointers, zero / too many views: rejected before anything is launched
+    assert lib.s360_multi_forward_project(ctypes.byref(v), 0, 10, *([None] * 10)) == -1
+    assert lib.s360_multi_forward_project(ctypes.byref(v), _lib.MAX_VIEWS + 1, 10, *([None] * 10)) == -1
+    assert lib.s360_multi_backward(ctypes.byref(v), 2, 10, *([None] * 16)) == -1
+    assert lib.s360_cube2equirec_forward(None, None, 0, 1, 3, 8, 16, 32, None, None) == -1

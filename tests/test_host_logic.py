@@ -122,3 +122,61 @@ def test_world_size_2_gloo_sharding_and_loss_allreduce():
         assert r[2] == [0.0, 1.0, 2.0, 3.0, 4.0]          # every rank reassembles all views
         assert abs(r[3] - (0 + 1 + 4 + 9 + 16)) < 1e-5     # loss all-reduce = single-process sum
         assert r[4] == 3.0                                  # gradient all-reduce: 1 + 2
+
+
+def test_batched_decoder_groups_views_and_builds_the_reference_cameras(monkeypatch):
+    """render_cuda_views (no GPU needed: the rasterizer call is intercepted): views of a batch item that share
+    fov / near / far go through ONE rasterize_views pass in chunks of max_views_per_pass, a change of near starts a new
+    pass, and the camera blocks handed over are exactly what the reference's per-view render_cuda builds
+    (cuda_splatting.py:63-87, pinned against the reference in tests/test_golden.py)."""
+    from splatter360_b200 import camera, cubemap, decoder, synthetic
+    calls = []
+
+    def fake(means3D, opacities, cov3D_precomp, settings, shs=None, colors_precomp=None):
+        calls.append(settings)
+        v = settings.viewmatrix.shape[0]
+        out = torch.zeros(v, 3, settings.image_height, settings.image_width)
+        return (out, torch.zeros(v, settings.image_height, settings.image_width)) if settings.depth_mode else out
+
+    monkeypatch.setattr(decoder, "rasterize_views", fake)
+    b, g = 2, 5
+    faces = torch.stack([cubemap.cube_face_extrinsics(synthetic.target_pose(k)) for k in range(b)])       # [b,6,4,4]
+    ext = torch.cat([faces, faces[:, :2]], dim=1)                                                         # 8 views
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None, None].repeat(b, 8, 1, 1)
+    near = torch.full((b, 8), 0.5); far = torch.full((b, 8), 20.0)
+    near[1, 5:] = 0.25                                                                                    # item 1: views 5.. differ
+    out = decoder.render_cuda_views(ext, K, near, far, (32, 32), torch.zeros(b, 3), torch.zeros(b, g, 3),
+                                    torch.eye(3).expand(b, g, 3, 3), torch.zeros(b, g, 3, 25), torch.ones(b, g),
+                                    max_views_per_pass=6)
+    assert out.shape == (b, 8, 3, 32, 32)
+    assert [s.viewmatrix.shape[0] for s in calls] == [6, 2, 5, 3]
+    assert [s.scene_scale for s in calls] == [2.0, 2.0, 2.0, 4.0]
+    assert all(s.sh_layout == 1 and s.cov_layout == 1 and s.projection == "pinhole" and s.sh_degree == 4 for s in calls)
+    # camera blocks == the per-view construction of render_cuda
+    for s, (i, j0) in zip(calls, [(0, 0), (0, 6), (1, 0), (1, 5)]):
+        for k in range(s.viewmatrix.shape[0]):
+            e = ext[i, j0 + k].clone()
+            sc = 1 / near[i, j0 + k]
+            e[:3, 3] *= sc
+            cam = camera.pinhole_camera(e[None], K[i, j0 + k][None], (near[i, j0 + k] * sc)[None], (far[i, j0 + k] * sc)[None])
+            assert torch.allclose(s.viewmatrix[k], cam.view_matrix[0], atol=1e-6)
+            assert torch.allclose(s.projmatrix[k], cam.full_projection[0], atol=1e-6)
+            assert torch.allclose(s.campos[k], cam.campos[0], atol=1e-6)
+            assert abs(s.tanfovx - float(cam.tan_fov_x[0])) < 1e-6
+    # fused depth request is forwarded with the unscaled near / far
+    calls.clear()
+    col, dep = decoder.render_cuda_views(ext[:1, :6], K[:1, :6], near[:1, :6], far[:1, :6], (32, 32), torch.zeros(1, 3),
+                                         torch.zeros(1, g, 3), torch.eye(3).expand(1, g, 3, 3), torch.zeros(1, g, 3, 25),
+                                         torch.ones(1, g), fused_depth_mode="depth")
+    assert dep.shape == (1, 6, 32, 32) and calls[0].depth_mode == "depth" and calls[0].depth_near == 0.5 and calls[0].depth_far == 20.0
+
+
+def test_batched_path_refuses_cpu_tensors_and_too_many_views():
+    from splatter360_b200 import rasterizer
+    s = _settings(viewmatrix=torch.eye(4)[None].repeat(2, 1, 1), projmatrix=torch.eye(4)[None].repeat(2, 1, 1),
+                  campos=torch.zeros(2, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rasterizer.rasterize_views(torch.zeros(4, 3), torch.ones(4, 1), torch.zeros(4, 6), s, colors_precomp=torch.zeros(4, 3))
+    from splatter360_b200.cubemap import Cube2Equirec
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Cube2Equirec(8, 16, 32)(torch.zeros(1, 3, 8, 48))
