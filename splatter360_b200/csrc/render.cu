@@ -17,6 +17,8 @@
 // lanes issue one fire-and-forget RED.ADD.F32 each into the per-Gaussian accumulator.  Moments are converted to
 // dL/d{mean2D, conic, opacity} once per Gaussian in preprocess_backward_kernel.  Replaces upstream renderCUDA
 // (forward.cu / backward.cu) behind /root/reference/src/model/decoder/cuda_splatting.py:113-124.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace s360 {
@@ -33,6 +35,15 @@ __device__ __forceinline__ float wrap_dx(float dx, float W, float halfW) {
     else if (dx < -halfW) dx += W;
   }
   return dx;
+}
+
+// nal if (p <= 0 && -nal >= amin) else 0 -- one predicate chain and one select (the compiler's own lowering of the
+// conditional spends two selects per pixel)
+__device__ __forceinline__ float take_alpha(float p, float nal, float amin) {
+  float r;
+  asm("{\n\t.reg .pred q, t;\n\tsetp.le.f32 q, %1, 0f00000000;\n\tsetp.ge.and.f32 t, %2, %3, q;\n\t"
+      "selp.f32 %0, %4, 0f00000000, t;\n\t}" : "=f"(r) : "f"(p), "f"(-nal), "f"(amin), "f"(nal));
+  return r;
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -133,7 +144,7 @@ __device__ __forceinline__ void load_records(ChunkRegs& c, const float4* __restr
   }
 }
 
-template <int MODE>
+template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(RT, S360_FWD_MINB)
 render_forward_kernel(const int W, const int H, const float* __restrict__ bg, const float4* __restrict__ rec,
                       const uint32_t* __restrict__ point_list, const uint2* __restrict__ ranges,
@@ -186,7 +197,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     stage_instance(nx.r0, nx.r1, nx.r2, cull, ev, col);
     const float thr = col.w;
     const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
-    const float dval = -depth_value(dspec, nx.r2.w);   // per-Gaussian value of the fused depth channel (negated like rgb)
+    const float dval = DEPTH ? -depth_value(dspec, nx.r2.w) : 0.f;   // per-Gaussian value of the fused depth channel (negated like rgb)
     // keep the pipeline full: records of the next chunk, ids of the one after
     nx.gid = gid2;
 #if S360_FWD_PREFETCH
@@ -203,37 +214,44 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
       const int slot = __popc(mask & ((1u << lane) - 1u));
       s_sv[warp][0][slot] = ev;
       s_sv[warp][1][slot] = make_float4(-col.x, -col.y, -col.z, dval);   // negated: the loop carries -alpha
-      s_sv[warp][2][slot] = make_float4(ddx, ddy, huge ? 1.f : 0.f, __uint_as_float(base - range.x + (uint32_t)lane + 1u));
+      s_sv[warp][2][slot] = make_float4(ddx, ddy, 0.f, __uint_as_float(base - range.x + (uint32_t)lane + 1u));
     }
+    // erp: does any survivor of this chunk need the per-pixel wrap (wider than half the panorama)?  Almost never.
+    const bool any_wide = MODE == S360_MODE_ERP && __any_sync(0xffffffffu, hit && huge);
     __syncwarp();
     const int nsv = __popc(mask);
     const float4* sv = &s_sv[warp][0][0];
-    for (int k = 0; k < nsv; k++) {
-      const float4 e = sv[k];
-      const float4 c = sv[32 + k];
-      const float4 g = sv[64 + k];
-      float dx = g.x - offx;
-      if (MODE == S360_MODE_ERP && g.z != 0.f) dx = wrap_dx<MODE>(dx, Wf, halfW);
-      const float2 dy = __fadd2_rn(make_float2(g.y, g.y), npy);
-      const float u = e.y * dx, pb = e.x * dx * dx;
-      const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
-      const float2 a = __fadd2_rn(p, make_float2(e.w, e.w));          // power * log2(e) + log2(opacity)
-      const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));   // -alpha
-      // -alpha if this pixel takes the Gaussian (power <= 0, alpha >= 1/255, pixel not finished), else 0
-      float2 nae = make_float2((p.x <= 0.f && -nal0 >= amin0) ? nal0 : 0.f, (p.y <= 0.f && -nal1 >= amin1) ? nal1 : 0.f);
-      const float2 tt = __ffma2_rn(T, nae, T);                          // T (1 - alpha); == T when not taken
-      if (tt.x < T_EPS) { nae.x = 0.f; amin0 = INF; }                   // would saturate: not blended, pixel done
-      if (tt.y < T_EPS) { nae.y = 0.f; amin1 = INF; }
-      const float2 nw = __fmul2_rn(nae, T);                             // -alpha T
-      Cr = __ffma2_rn(make_float2(c.x, c.x), nw, Cr);                   // c holds -rgb
-      Cg = __ffma2_rn(make_float2(c.y, c.y), nw, Cg);
-      Cb = __ffma2_rn(make_float2(c.z, c.z), nw, Cb);
-      Cd = __ffma2_rn(make_float2(c.w, c.w), nw, Cd);
-      T = __ffma2_rn(T, nae, T);
-      const uint32_t pos = __float_as_uint(g.w);
-      if (nae.x < 0.f) last0 = pos;
-      if (nae.y < 0.f) last1 = pos;
-    }
+    auto composite = [&](auto wide_tag) {
+      constexpr bool WIDE = decltype(wide_tag)::value;
+#pragma unroll 2
+      for (int k = 0; k < nsv; k++) {
+        const float4 e = sv[k];
+        const float4 c = sv[32 + k];
+        const float4 g = sv[64 + k];
+        float dx = g.x - offx;
+        if (WIDE) dx = wrap_dx<MODE>(dx, Wf, halfW);
+        const float2 dy = __fadd2_rn(make_float2(g.y, g.y), npy);
+        const float u = e.y * dx, pb = e.x * dx * dx;
+        const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
+        const float2 a = __fadd2_rn(p, make_float2(e.w, e.w));          // power * log2(e) + log2(opacity)
+        const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));   // -alpha
+        // -alpha if this pixel takes the Gaussian (power <= 0, alpha >= 1/255, pixel not finished), else 0
+        float2 nae = make_float2(take_alpha(p.x, nal0, amin0), take_alpha(p.y, nal1, amin1));
+        const float2 tt = __ffma2_rn(T, nae, T);                          // T (1 - alpha); == T when not taken
+        if (tt.x < T_EPS) { nae.x = 0.f; amin0 = INF; }                   // would saturate: not blended, pixel done
+        if (tt.y < T_EPS) { nae.y = 0.f; amin1 = INF; }
+        const float2 nw = __fmul2_rn(nae, T);                             // -alpha T
+        Cr = __ffma2_rn(make_float2(c.x, c.x), nw, Cr);                   // c holds -rgb
+        Cg = __ffma2_rn(make_float2(c.y, c.y), nw, Cg);
+        Cb = __ffma2_rn(make_float2(c.z, c.z), nw, Cb);
+        if (DEPTH) Cd = __ffma2_rn(make_float2(c.w, c.w), nw, Cd);
+        T = __ffma2_rn(T, nae, T);
+        const uint32_t pos = __float_as_uint(g.w);
+        if (nae.x < 0.f) last0 = pos;
+        if (nae.y < 0.f) last1 = pos;
+      }
+    };
+    if (any_wide) composite(std::true_type{}); else composite(std::false_type{});
     __syncwarp();
   }
   // how far this warp had to walk: the backward pass replays at most that much of the tile's list
@@ -245,18 +263,18 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
   final_T += (size_t)view * plane; n_contrib += (size_t)view * plane;   // pixel state and outputs of this view
   out_color += (size_t)view * 3 * plane;
-  if (out_depth) out_depth += (size_t)view * plane;
+  if (DEPTH) out_depth += (size_t)view * plane;
   if (in0) {
     const size_t pid = (size_t)py0 * W + px;
     final_T[pid] = T.x; n_contrib[pid] = last0;
     out_color[pid] = Cr.x + T.x * b0; out_color[plane + pid] = Cg.x + T.x * b1; out_color[2 * plane + pid] = Cb.x + T.x * b2;
-    if (out_depth) out_depth[pid] = Cd.x;
+    if (DEPTH) out_depth[pid] = Cd.x;
   }
   if (in1) {
     const size_t pid = (size_t)py1 * W + px;
     final_T[pid] = T.y; n_contrib[pid] = last1;
     out_color[pid] = Cr.y + T.y * b0; out_color[plane + pid] = Cg.y + T.y * b1; out_color[2 * plane + pid] = Cb.y + T.y * b2;
-    if (out_depth) out_depth[pid] = Cd.y;
+    if (DEPTH) out_depth[pid] = Cd.y;
   }
 }
 
@@ -268,10 +286,11 @@ int launch_render_forward(const S360View& v, int NV, GeomState g, const uint32_t
   if (tiles == 0) return 0;
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
-  if (v.mode == S360_MODE_PINHOLE)
-    render_forward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order, img.work, img.final_T, img.n_contrib, out_color, out_depth, ds);
-  else
-    render_forward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order, img.work, img.final_T, img.n_contrib, out_color, out_depth, ds);
+#define S360_LAUNCH_FWD(MODE_, DEPTH_) render_forward_kernel<MODE_, DEPTH_><<<tiles, RT, 0, st>>>( \
+      W, H, v.bg, g.rec, point_list, img.ranges, img.order, img.work, img.final_T, img.n_contrib, out_color, out_depth, ds)
+  if (v.mode == S360_MODE_PINHOLE) { if (out_depth) S360_LAUNCH_FWD(S360_MODE_PINHOLE, true); else S360_LAUNCH_FWD(S360_MODE_PINHOLE, false); }
+  else { if (out_depth) S360_LAUNCH_FWD(S360_MODE_ERP, true); else S360_LAUNCH_FWD(S360_MODE_ERP, false); }
+#undef S360_LAUNCH_FWD
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -402,17 +421,20 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const int slot = __popc(mask & ~((2u << lane) - 1u));
       s_sv[warp][0][slot] = ev;
       s_sv[warp][1][slot] = col;
-      s_sv[warp][2][slot] = make_float4(ddx, ddy, huge ? 1.f : 0.f, __uint_as_float(pos0 + (uint32_t)lane));
+      s_sv[warp][2][slot] = make_float4(ddx, ddy, 0.f, __uint_as_float(pos0 + (uint32_t)lane));
     }
+    const bool any_wide = MODE == S360_MODE_ERP && __any_sync(0xffffffffu, hit && huge);
     __syncwarp();
     const int nsv = __popc(mask);
     const float4* sv = &s_sv[warp][0][0];
+    auto replay = [&](auto wide_tag) {
+    constexpr bool WIDE = decltype(wide_tag)::value;
     for (int k = 0; k < nsv; k++) {
       const float4 e = sv[k];
       const float4 g = sv[64 + k];
       const uint32_t pos = __float_as_uint(g.w);
       float dx = g.x - offx;
-      if (MODE == S360_MODE_ERP && g.z != 0.f) dx = wrap_dx<MODE>(dx, Wf, halfW);
+      if (WIDE) dx = wrap_dx<MODE>(dx, Wf, halfW);
       const float2 dy = __fadd2_rn(make_float2(g.y, g.y), npy);
       const float u = e.y * dx, pb = e.x * dx * dx;
       const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
@@ -442,14 +464,15 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       dLda = __ffma2_rn(dLda, S.T, __fmul2_rn(S.bgT, inv));
       float2 q = __fmul2_rn(make_float2(ex2_approx(p.x), ex2_approx(p.y)), dLda);          // G dL/dalpha
       q.x = ok0 ? q.x : 0.f; q.y = ok1 ? q.y : 0.f;
-      const float2 dx2 = make_float2(dx, dx);
-      const float2 qx = __fmul2_rn(q, dx2), qy = __fmul2_rn(q, dy);
+      // the lane's two pixels share dx: sum them first, then apply the common factor
+      const float2 qy = __fmul2_rn(q, dy);
       const float2 t0 = __fmul2_rn(nw, S.dp0), t1 = __fmul2_rn(nw, S.dp1), t2 = __fmul2_rn(nw, S.dp2);
-      const float2 t5 = __fmul2_rn(qx, dx2), t6 = __fmul2_rn(qx, dy), t7 = __fmul2_rn(qy, dy);
+      const float2 t7 = __fmul2_rn(qy, dy);
       float v[NACC];
       v[0] = -(t0.x + t0.y); v[1] = -(t1.x + t1.y); v[2] = -(t2.x + t2.y);
-      v[3] = qx.x + qx.y; v[4] = qy.x + qy.y; v[5] = t5.x + t5.y; v[6] = t6.x + t6.y; v[7] = t7.x + t7.y;
       v[8] = q.x + q.y;
+      v[4] = qy.x + qy.y;
+      v[3] = v[8] * dx; v[5] = v[3] * dx; v[6] = v[4] * dx; v[7] = t7.x + t7.y;
       const float s8 = warp_reduce8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], lane);
       float v8 = v[8];
       v8 += __shfl_xor_sync(0xffffffffu, v8, 16);
@@ -464,6 +487,8 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       if ((lane & 3) == 0) atomicAdd(dst + ((lane >> 2) & 7), s8);
       if (lane == 1) atomicAdd(dst + 8, v8);
     }
+    };
+    if (any_wide) replay(std::true_type{}); else replay(std::false_type{});
     __syncwarp();
   }
 }
