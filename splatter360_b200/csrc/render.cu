@@ -119,10 +119,10 @@ __device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth
 #define S360_BWD_PREFETCH 0
 #endif
 #ifndef S360_FWD_MINB
-#define S360_FWD_MINB 1
+#define S360_FWD_MINB 6
 #endif
 #ifndef S360_BWD_MINB
-#define S360_BWD_MINB 1
+#define S360_BWD_MINB 7
 #endif
 
 constexpr int NWARPS = RT / 32;
@@ -429,6 +429,9 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     const float4* sv = &s_sv[warp][0][0];
     auto replay = [&](auto wide_tag) {
     constexpr bool WIDE = decltype(wide_tag)::value;
+#ifdef S360_BWD_UNROLL
+#pragma unroll 2
+#endif
     for (int k = 0; k < nsv; k++) {
       const float4 e = sv[k];
       const float4 g = sv[64 + k];
@@ -443,7 +446,9 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));
       const bool ok0 = (pos < S.lastc0) && (p.x <= 0.f) && (-nal0 >= ALPHA_MIN);
       const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
+#ifndef S360_BWD_NOSKIP
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+#endif
       const float4 c = sv[32 + k];
       // A pixel that does not take this instance runs the same recurrences with alpha = 0, which only folds the
       // pending (last_alpha, last_color) term into accum_rec early -- bit-identical to skipping it.
