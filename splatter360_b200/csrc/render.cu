@@ -5,12 +5,15 @@
 // (x, y + 4), whose state is packed in float2 and advanced with Blackwell's two-wide FP32 instructions
 // (FFMA2 / FMUL2 / FADD2).  The kernels are warp-autonomous (no CTA barrier): every warp streams the tile's
 // depth-sorted instance list itself in chunks of 32 -- lane j gathers instance j (its id was prefetched one chunk
-// earlier, the 48-B record comes from L2/L1, which the four warps of the tile share) -- tests its own instance
-// against the warp's pixel rectangle with an exact "can the alpha >= 1/255 ellipse reach it" test, and only the
-// ballot survivors are evaluated: centre by SHFL from the testing lane, conic and colour broadcast from a per-warp
-// shared-memory slice.  The conic is staged pre-multiplied by -0.5*log2(e) and the opacity as log2(opacity), so that
+// earlier, the 48-B record comes from L2/L1, which the four warps of a tile share) -- tests its own instance
+// against the warp's pixel rectangle with an exact "can the alpha >= 1/255 ellipse reach it" test, and the ballot
+// survivors write their staged parameters COMPACTED, in list order, into a per-warp shared-memory slice (conic
+// pre-multiplied by -0.5*log2(e), log2(opacity), colour, centre relative to the warp block, list position).  The
+// evaluation loop then just walks that slice (3 LDS.128 per survivor, no ffs / shuffle bookkeeping):
 // alpha = ex2(A'dx^2 + C'dy^2 + B'dxdy + log2 o).  Blending is branch-free: a pixel that does not take an instance
-// runs the recurrences with alpha = 0.  The CTAs pick their tile from a longest-first schedule.
+// runs the recurrences with alpha = 0.  erp: the per-pixel seam wrap is needed only by Gaussians wider than half the
+// panorama; whether a chunk holds one is decided once per chunk and selects a second instantiation of the loop.
+// The CTAs pick their tile from a longest-first schedule; V stacked views (batched path) are just more tiles.
 //
 // Backward: per (pixel, instance) only the moments q, q*dx, q*dy, q*dx^2, q*dxdy, q*dy^2 (q = G * dL/dalpha) and the
 // three colour terms are formed; they are summed over the warp with a transposed butterfly (14 shuffles) and nine
@@ -429,9 +432,6 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     const float4* sv = &s_sv[warp][0][0];
     auto replay = [&](auto wide_tag) {
     constexpr bool WIDE = decltype(wide_tag)::value;
-#ifdef S360_BWD_UNROLL
-#pragma unroll 2
-#endif
     for (int k = 0; k < nsv; k++) {
       const float4 e = sv[k];
       const float4 g = sv[64 + k];
@@ -446,9 +446,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));
       const bool ok0 = (pos < S.lastc0) && (p.x <= 0.f) && (-nal0 >= ALPHA_MIN);
       const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
-#ifndef S360_BWD_NOSKIP
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
-#endif
       const float4 c = sv[32 + k];
       // A pixel that does not take this instance runs the same recurrences with alpha = 0, which only folds the
       // pending (last_alpha, last_color) term into accum_rec early -- bit-identical to skipping it.
