@@ -51,7 +51,7 @@ struct Proj {
 template <int MODE>
 __device__ __forceinline__ void project_view(const S360View& v, const float* V, const float* PM, float mx, float my,
                                              float mz, const float* cv, const float* __restrict__ opac, int idx,
-                                             Proj& o) {
+                                             float wf, Proj& o) {
   const int W = v.image_width, H = v.image_height;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   o.upstream_visible = false;
@@ -60,11 +60,13 @@ __device__ __forceinline__ void project_view(const S360View& v, const float* V, 
   // near cull first (upstream in_frustum): the same expressions geo_compute evaluates for the view-space centre, so
   // the sort key is bit-identical; a culled Gaussian skips the covariance projection altogether
   {
-    const float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
-    const float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
     const float tz = V[2] * mx + V[6] * my + V[10] * mz + V[14];
     if (MODE == S360_MODE_PINHOLE) { o.sortkey = tz; }
-    else { o.sortkey = sqrtf(tx * tx + ty * ty + tz * tz); }
+    else {
+      const float tx = V[0] * mx + V[4] * my + V[8] * mz + V[12];
+      const float ty = V[1] * mx + V[5] * my + V[9] * mz + V[13];
+      o.sortkey = sqrtf(tx * tx + ty * ty + tz * tz);
+    }
   }
   if (!(o.sortkey > v.near_cull)) return;
   if (MODE == S360_MODE_PINHOLE) {
@@ -76,8 +78,6 @@ __device__ __forceinline__ void project_view(const S360View& v, const float* V, 
     const float limx = v.fov_clamp * v.tanfovx, limy = v.fov_clamp * v.tanfovy;
     const float iz = 1.f / o.sortkey;
     const float jb = (fx * fx * (1.f + limx * limx) + fy * fy * (1.f + limy * limy)) * iz * iz;
-    const float wf = V[0] * V[0] + V[1] * V[1] + V[2] * V[2] + V[4] * V[4] + V[5] * V[5] + V[6] * V[6] + V[8] * V[8] +
-                     V[9] * V[9] + V[10] * V[10];
     const float rb = 3.f * sqrtf(jb * wf * fmaxf(cv[0] + cv[3] + cv[5], 0.f) + 2.f * fabsf(v.lowpass) + 0.32f) + 2.f;
     const float qx = PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12];
     const float qy = PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13];
@@ -157,6 +157,13 @@ __device__ __forceinline__ void project_view(const S360View& v, const float* V, 
   }
 }
 
+// squared Frobenius norm of the rotation block of a view matrix (3 for a rigid camera); scales the reject bound of
+// project_view so that it stays conservative for any matrix a caller hands in
+__device__ __forceinline__ float view_frobenius2(const float* V) {
+  return V[0] * V[0] + V[1] * V[1] + V[2] * V[2] + V[4] * V[4] + V[5] * V[5] + V[6] * V[6] + V[8] * V[8] + V[9] * V[9] +
+         V[10] * V[10];
+}
+
 // SH -> RGB for one Gaussian (row `sh` of the staged block) seen from `campos`; sets the clamp bits 0..2 of cl
 __device__ __forceinline__ void sh_to_rgb(const S360View& v, const float* sh, float mx, float my, float mz,
                                           const float* campos, float* col, uint8_t& cl) {
@@ -222,7 +229,7 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     float cv[6];
     load_cov6(v, cov3D, idx, cv);
     Proj pr;
-    project_view<MODE>(v, cam.V, cam.PM, mx, my, mz, cv, opac, idx, pr);
+    project_view<MODE>(v, cam.V, cam.PM, mx, my, mz, cv, opac, idx, view_frobenius2(cam.V), pr);
     upstream_visible = pr.upstream_visible;
     my_tiles = pr.tiles;
     px = pr.px; py = pr.py; cA = pr.cA; cB = pr.cB; cC = pr.cC; op = pr.op; hx = pr.hx; hy = pr.hy; sortkey = pr.sortkey;
@@ -546,7 +553,15 @@ __device__ __forceinline__ void stage_cameras(const S360View& v, int NV, bool ne
     if (j < 16) x = __ldg(v.viewmatrix + 16 * view + j);
     else if (j < 32) x = need_proj ? __ldg(v.projmatrix + 16 * view + (j - 16)) : 0.f;
     else if (j < 35) x = __ldg(v.campos + 3 * view + (j - 32));
-    s_cam[view][j] = x;
+    if (j < 35) s_cam[view][j] = x;
+  }
+  // slot 35: squared Frobenius norm of the rotation block (bound of project_view's frustum reject)
+  for (int view = threadIdx.x; view < NV; view += blockDim.x) {
+    const float* V = v.viewmatrix + 16 * view;
+    float f = 0.f;
+    for (int c = 0; c < 3; c++)
+      for (int r = 0; r < 3; r++) { const float x = __ldg(V + 4 * c + r); f += x * x; }
+    s_cam[view][35] = f;
   }
 }
 
@@ -580,7 +595,7 @@ multi_count_kernel(const S360View v, const int NV, const float* __restrict__ mea
     load_cov6(v, cov3D, idx, cv);
     for (int view = 0; view < NV; view++) {
       Proj pr;
-      project_view<MODE>(v, s_cam[view], s_cam[view] + 16, mx, my, mz, cv, opac, idx, pr);
+      project_view<MODE>(v, s_cam[view], s_cam[view] + 16, mx, my, mz, cv, opac, idx, s_cam[view][35], pr);
       if (pr.tiles) { mask |= 1u << view; tiles += pr.tiles; }
       if (radii) radii[(size_t)view * P + idx] = pr.radius;
     }
@@ -704,7 +719,7 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
     if (slot >= cap) { kept &= ~m; break; }   // pair buffers full: drop this and the remaining views (flagged by K1b)
     const float* cam = s_cam[view];
     Proj pr;
-    project_view<MODE>(v, cam, cam + 16, mx, my, mz, cv, opac, idx, pr);
+    project_view<MODE>(v, cam, cam + 16, mx, my, mz, cv, opac, idx, cam[35], pr);
     if (shs != nullptr) {
       // same camera centre as the last evaluated view (cube faces): same direction, same colour
       const bool same = col_view >= 0 && s_cam[col_view][32] == cam[32] && s_cam[col_view][33] == cam[33] &&

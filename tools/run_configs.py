@@ -56,10 +56,10 @@ def run(name, scene, H, W, n_views, backward):
     F = H // 2
     K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev)[None].repeat(6, 1, 1)
     tgt6 = torch.rand(3, F, F, device=dev)
+    camps = [camera.pinhole_camera(face_poses(poses[i]), K, torch.ones(6, device=dev), torch.full((6,), 100.0, device=dev)) for i in range(n_views)]
     def cube_step(bwd):
         for i in range(n_views):
-            fp = face_poses(poses[i])
-            camp = camera.pinhole_camera(fp, K, torch.ones(6, device=dev), torch.full((6,), 100.0, device=dev))
+            camp = camps[i]
             for f in range(6):
                 color, st = rasterizer.forward_raw(settings(F, F, camp, f, "pinhole"), means, cov6, op, shs, None)
                 if bwd:
@@ -74,8 +74,7 @@ def run(name, scene, H, W, n_views, backward):
     stats = {}
     def cube_batched_step(bwd, stitch):
         for i in range(n_views):
-            fp = face_poses(poses[i])
-            camp = camera.pinhole_camera(fp, K, torch.ones(6, device=dev), torch.full((6,), 100.0, device=dev))
+            camp = camps[i]
             s6 = rasterizer.GaussianRasterizationSettings(image_height=F, image_width=F, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3, device=dev),
                 scale_modifier=1.0, viewmatrix=camp.view_matrix, projmatrix=camp.full_projection, sh_degree=4, campos=camp.campos,
                 prefiltered=False, debug=False, projection="pinhole")
