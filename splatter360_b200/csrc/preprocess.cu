@@ -76,13 +76,17 @@ __device__ __forceinline__ void project_view(const S360View& v, const float* V, 
     // than that bound from the image has an empty tile rectangle, which is all the full path would find out.
     const float fx = (float)W / (2.f * v.tanfovx), fy = (float)H / (2.f * v.tanfovy);
     const float limx = v.fov_clamp * v.tanfovx, limy = v.fov_clamp * v.tanfovy;
-    const float iz = 1.f / o.sortkey;
+    // approximate reciprocal / square root are fine here: the bound carries 1 % + 2 px of slack
+    float iz, pw;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iz) : "f"(o.sortkey));
     const float jb = (fx * fx * (1.f + limx * limx) + fy * fy * (1.f + limy * limy)) * iz * iz;
-    const float rb = 3.f * sqrtf(jb * wf * fmaxf(cv[0] + cv[3] + cv[5], 0.f) + 2.f * fabsf(v.lowpass) + 0.32f) + 2.f;
+    float rb;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(jb * wf * fmaxf(cv[0] + cv[3] + cv[5], 0.f) + 2.f * fabsf(v.lowpass) + 0.32f));
+    rb = 3.03f * rb + 2.f;
     const float qx = PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12];
     const float qy = PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13];
     const float qw = PM[3] * mx + PM[7] * my + PM[11] * mz + PM[15];
-    const float pw = 1.f / (qw + 0.0000001f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(qw + 0.0000001f));
     const float cx = ((qx * pw + 1.f) * W - 1.f) * 0.5f, cy = ((qy * pw + 1.f) * H - 1.f) * 0.5f;
     if (cx + rb < 0.f || cx - rb > (float)(gx * TILE) || cy + rb < 0.f || cy - rb > (float)(gy * TILE)) return;
   }
