@@ -300,3 +300,33 @@ def test_cube2equirec_kernel_matches_golden_and_reference_formulation():
     (fused * w).sum().backward()
     assert rel_l2(fused.detach().cpu().numpy(), chain.detach().cpu().numpy()) < 1e-6
     assert rel_l2(faces.grad.cpu().numpy(), g_chain.cpu().numpy()) < 1e-5
+
+
+def test_erp_decoder_batched_switch_and_views_entry():
+    """DecoderSplattingERP: batched_views on/off give the same panoramas (bitwise) and gradients; render_erp_views equals
+    per-view render_erp."""
+    from splatter360_b200 import decoder, synthetic
+    dev = "cuda"
+    sc = synthetic.random_cloud_scene(4000, sh_degree=4, seed=15, ref_width=256, depth_range=(0.5, 4.0))
+    poses = torch.stack([synthetic.target_pose(20 + k) for k in range(3)])[None].to(dev)     # [1,3,4,4]
+    near, far = torch.full((1, 3), 0.5, device=dev), torch.full((1, 3), 20.0, device=dev)
+    g = decoder.Gaussians(*[t[None].to(dev).requires_grad_() for t in (sc.means, sc.covariances, sc.harmonics, sc.opacities)])
+    outs, grads = [], []
+    for batched in (True, False):
+        dec = decoder.DecoderSplattingERP((0.1, 0.0, 0.2), batched_views=batched).to(dev)
+        out = dec(g, poses, None, near, far, (64, 128))
+        for t in (g.means, g.covariances, g.harmonics, g.opacities):
+            t.grad = None
+        (out.color * torch.linspace(0, 1, out.color.numel(), device=dev).reshape(out.color.shape)).sum().backward()
+        outs.append(out.color.detach().clone())
+        grads.append([t.grad.clone() for t in (g.means, g.covariances, g.harmonics, g.opacities)])
+    assert torch.equal(outs[0], outs[1])
+    for a, b in zip(*grads):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+    with torch.no_grad():
+        col, dep = decoder.render_erp_views(poses, near, far, (64, 128), torch.zeros(1, 3, device=dev), g.means, g.covariances,
+                                            g.harmonics, g.opacities, fused_depth_mode="disparity")
+        for k in range(3):
+            c1, d1 = decoder.render_erp(poses[:, k], near[:, k], far[:, k], (64, 128), torch.zeros(1, 3, device=dev), g.means,
+                                        g.covariances, g.harmonics, g.opacities, fused_depth_mode="disparity")
+            assert torch.equal(col[:, k], c1) and torch.equal(dep[:, k], d1)

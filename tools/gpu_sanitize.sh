@@ -12,6 +12,19 @@ for mode, H, W, n in (("pinhole", 64, 80, 1500), ("erp", 48, 96, 1500), ("erp", 
     case["colors"] = torch.rand(n, 3)
     out = run_cuda(case, dL=dL, use_sh=False)
     print(mode, "ok", float(out["color"].mean()))
+# batched multi-view pass (six cube faces, three erp views) + the stitch kernel
+import test_gpu_views as tv
+from splatter360_b200 import cubemap
+sc = tv._scene(1200, seed=3)
+for mode, cam, H, W in (("pinhole", tv._cube_cameras(4), 48, 48), ("erp", tv._erp_cameras(3, seed=1), 32, 64)):
+    V = cam.view_matrix.shape[0]
+    dL = torch.randn(V, 3, H, W, generator=torch.Generator().manual_seed(2))
+    out = tv._run_views(sc, tv._settings(cam, H, W, mode, "cuda"), dL=dL)
+    print("batched", mode, "ok", float(out["color"].mean()))
+c2e = cubemap.Cube2Equirec(16, 32, 64).to("cuda")
+f = torch.rand(1, 6, 3, 16, 16, device="cuda", requires_grad=True)
+c2e.from_faces(f).sum().backward()
+print("stitch ok", float(f.grad.sum()))
 PY
 for tool in memcheck racecheck initcheck synccheck; do
   echo "== $tool"
