@@ -330,3 +330,28 @@ def test_erp_decoder_batched_switch_and_views_entry():
             c1, d1 = decoder.render_erp(poses[:, k], near[:, k], far[:, k], (64, 128), torch.zeros(1, 3, device=dev), g.means,
                                         g.covariances, g.harmonics, g.opacities, fused_depth_mode="disparity")
             assert torch.equal(col[:, k], c1) and torch.equal(dep[:, k], d1)
+
+
+def test_many_overlapping_views_trigger_the_exact_pair_capacity_retry():
+    """Eight pinhole views that all look at the same cloud: pairs ~ 8 P exceeds the default 2 P + 4096 pair slots, so the
+    forward pass re-runs K1 with the exact count it read back -- results must still equal the per-view oracle."""
+    from splatter360_b200 import camera, rasterizer, synthetic
+    n, H, W, V = 3000, 48, 64, 8
+    sc = _scene(n, seed=17)
+    # put the whole cloud in front of the cameras
+    sc["means"] = sc["means"].clone()
+    sc["means"][:, 2] = sc["means"][:, 2].abs() + 1.0
+    poses = torch.eye(4)[None].repeat(V, 1, 1)
+    poses[:, 0, 3] = torch.linspace(-0.2, 0.2, V)
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None].repeat(V, 1, 1)
+    cam = camera.pinhole_camera(poses, K, torch.ones(V), torch.full((V,), 100.0))
+    s = _settings(cam, H, W, "pinhole", "cuda")
+    dev = "cuda"
+    _, st = rasterizer.forward_views_raw(s, sc["means"].to(dev), sc["cov6"].to(dev), sc["opac"].to(dev), sc["shs"].to(dev), None)
+    assert st.num_pairs > 2 * n + 4096 and st.pair_capacity == st.num_pairs     # the retry sized the buffers exactly
+    dL = torch.randn(V, 3, H, W, generator=torch.Generator().manual_seed(8))
+    outs = _oracle_views(sc, cam, H, W, "pinhole", dL=dL)
+    c = _run_views(sc, s, dL=dL)
+    for k in range(V):
+        assert rel_l2(c["color"][k], outs[k]["color"]) < TOL, k
+    _check_sum(c, outs, "d_shs")

@@ -46,6 +46,11 @@ def timeit(fn, iters=40, warm=5):
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return statistics.median(ts)
 
+if "--profile" in sys.argv:   # under ncu: a few forward+backward passes, nothing else
+    for _ in range(4):
+        batched(True)
+    torch.cuda.synchronize()
+    sys.exit(0)
 res = {"lib": os.environ.get("S360_LIB", "default"), "face": F, "P": means.shape[0]}
 res["batched_fwd_ms"] = timeit(lambda: batched(False))
 res["batched_fwd_bwd_ms"] = timeit(lambda: batched(True))
