@@ -44,6 +44,44 @@ def all_reduce_loss(loss: Tensor, average: bool = False) -> Tensor:
     return out / ws if average else out
 
 
+class AsyncLossReducer:
+    """The loss all-reduce off the critical path: the reduction of step i is issued asynchronously (NCCL runs it on
+    its own stream, ordered after the loss of step i) and is only waited for when its ring slot is reused ``depth``
+    steps later or when the value is read, so rendering of step i+1 never waits for the slowest rank's step i."""
+
+    def __init__(self, device, depth: int = 2) -> None:
+        self.bufs = [torch.zeros(1, dtype=torch.float32, device=device) for _ in range(depth)]
+        self.works = [None] * depth
+        self.n = 0
+
+    def submit(self, loss: Tensor) -> None:
+        j = self.n % len(self.bufs)
+        if self.works[j] is not None:
+            self.works[j].wait()
+            self.works[j] = None
+        self.bufs[j].copy_(loss.detach().reshape(1))
+        _, ws = world()
+        if ws > 1:
+            self.works[j] = dist.all_reduce(self.bufs[j], op=dist.ReduceOp.SUM, async_op=True)
+        self.n += 1
+
+    def latest(self) -> Tensor:
+        """Summed loss of the most recently submitted step (waits for its all-reduce)."""
+        if self.n == 0:
+            raise RuntimeError("no loss submitted yet")
+        j = (self.n - 1) % len(self.bufs)
+        if self.works[j] is not None:
+            self.works[j].wait()
+            self.works[j] = None
+        return self.bufs[j]
+
+    def flush(self) -> None:
+        for j, w in enumerate(self.works):
+            if w is not None:
+                w.wait()
+                self.works[j] = None
+
+
 def all_reduce_gradients(grads: Iterable[Optional[Tensor]]) -> None:
     """In-place sum over ranks of per-Gaussian gradient tensors (only needed when the views of ONE scene are
     split across ranks and the Gaussians are replicated)."""

@@ -102,7 +102,16 @@ def _worker(rank, ws, port, q):
     total = parallel.all_reduce_loss(torch.as_tensor(loss, dtype=torch.float32))
     g = [torch.full((4, 3), float(rank + 1)), None]
     parallel.all_reduce_gradients(g)
-    q.put((rank, idx, full[:, 0, 0, 0].tolist(), float(total), g[0][0, 0].item()))
+    # asynchronous loss reducer: five steps through a ring of two slots, every step's sum is rank-independent
+    red = parallel.AsyncLossReducer("cpu", depth=2)
+    sums = []
+    for step in range(5):
+        red.submit(torch.tensor(float((rank + 1) * (step + 1))))
+        if step % 2 == 1:
+            sums.append(float(red.latest()))
+    red.flush()
+    sums.append(float(red.latest()))
+    q.put((rank, idx, full[:, 0, 0, 0].tolist(), float(total), g[0][0, 0].item(), sums))
     dist.destroy_process_group()
 
 
@@ -122,6 +131,7 @@ def test_world_size_2_gloo_sharding_and_loss_allreduce():
         assert r[2] == [0.0, 1.0, 2.0, 3.0, 4.0]          # every rank reassembles all views
         assert abs(r[3] - (0 + 1 + 4 + 9 + 16)) < 1e-5     # loss all-reduce = single-process sum
         assert r[4] == 3.0                                  # gradient all-reduce: 1 + 2
+        assert r[5] == [6.0, 12.0, 15.0]                    # async reducer: (1 + 2) * step for steps 2, 4, 5
 
 
 def test_batched_decoder_groups_views_and_builds_the_reference_cameras(monkeypatch):
