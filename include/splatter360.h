@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S360_ABI_VERSION 3
+#define S360_ABI_VERSION 4
 
 #define S360_MODE_PINHOLE 0 /* upstream semantics                     */
 #define S360_MODE_ERP 1     /* native equirectangular splatting      */
@@ -231,10 +231,17 @@ int s360_mse_loss_grad(const float* color, const float* target, int64_t n, float
  *   layout 1: faces [B,6,C,f,f]  rasterizer output in the dataset face order [U B L F R D]; the reorder and the
  *                                180-degree turn of U and D are applied by index arithmetic */
 int s360_cube2equirec_forward(const float* faces, const float* grid, int32_t layout, int32_t B, int32_t C,
-                              int32_t face_w, int32_t H, int32_t W, float* out /*[B,C,H,W]*/, void* stream);
+                              int32_t face_w, int32_t H, int32_t W,
+                              const float* depth_to_distance /* host [4] = fx, fy, cx, cy in pixels, or NULL */,
+                              float* out /*[B,C,H,W]*/, void* stream);
 int s360_cube2equirec_backward(const float* dL_dout /*[B,C,H,W]*/, const float* grid, int32_t layout, int32_t B,
-                               int32_t C, int32_t face_w, int32_t H, int32_t W,
+                               int32_t C, int32_t face_w, int32_t H, int32_t W, const float* depth_to_distance,
                                float* dL_dfaces /* out, same layout as faces; zeroed by the call */, void* stream);
+/* depth_to_distance != NULL: the faces hold z-depth and the panorama is wanted in radial distance -- every tap is
+ * scaled by sqrt(((r - cx)/fx)^2 + ((c - cy)/fy)^2 + 1) of its texel (row r, column c; the reference's meshgrid is
+ * 'ij'-indexed) on the reordered face, i.e. the reference's
+ * depth_to_distance_map_batch (/root/reference/src/geometry/z_depth_to_distance.py:4-34) applied between change_order
+ * and the stitch exactly as its depth video does (model_wrapper_erp.py:447-463). */
 
 /* ---- debugging / introspection ---------------------------------------------------------------- */
 /* Unpack the geometry state for per-stage parity tests.  Any output may be NULL. */

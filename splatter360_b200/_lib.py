@@ -28,7 +28,7 @@ EXPORTS = [
     "s360_multi_forward_project", "s360_multi_forward_order", "s360_multi_forward_render", "s360_multi_backward",
     "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward",
 ]
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_VIEWS = 32
 
 STAGES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
@@ -124,7 +124,7 @@ def load() -> ctypes.CDLL:
     lib.s360_multi_backward.argtypes = head + [vp] * 16
     for n in ("s360_cube2equirec_forward", "s360_cube2equirec_backward"):
         getattr(lib, n).restype = c_int
-        getattr(lib, n).argtypes = [vp, vp] + [c_int32] * 6 + [vp, vp]
+        getattr(lib, n).argtypes = [vp, vp] + [c_int32] * 6 + [vp, vp, vp]
     lib.s360_debug_unpack_pairs.restype = c_int
     lib.s360_debug_unpack_pairs.argtypes = [c_int32, c_int64] + [vp] * 5
     if lib.s360_abi_version() != ABI_VERSION:

@@ -48,6 +48,16 @@ def change_order(cubes: Tensor) -> Tensor:
     return torch.stack([cubes[3], cubes[4], cubes[1], cubes[2], up, down])
 
 
+def depth_to_distance_factor(face_w: int, fx: float, fy: float, cx: float, cy: float) -> Tensor:
+    """[f, f] factor distance / z-depth of every texel, literal to the reference's ``depth_to_distance_map_batch``
+    (/root/reference/src/geometry/z_depth_to_distance.py:4-34): integer pixel coordinates, and its default-indexed
+    ``torch.meshgrid(arange(width), arange(height))`` makes "u" (cx, fx) run along the rows.  Torch formulation: the checker
+    of the fused kernel option (``Cube2Equirec.from_faces(depth_to_distance=...)``)."""
+    r = torch.arange(face_w, dtype=torch.float32)[:, None]
+    c = torch.arange(face_w, dtype=torch.float32)[None, :]
+    return torch.sqrt(((r - cx) / fx) ** 2 + ((c - cy) / fy) ** 2 + 1.0)
+
+
 class Cube2Equirec(nn.Module):
     """faces [b, c, f, 6 f] laid out side by side in the order [F R B L U D] -> panorama [b, c, H, W]."""
 
@@ -101,18 +111,23 @@ class Cube2Equirec(nn.Module):
         """Strip [b, c, f, 6f] in the order [F R B L U D] -> panorama [b, c, H, W] (libsplatter360 gather kernel)."""
         bs, ch, h, w = cube_feat.shape
         assert h == self.face_w and w == 6 * self.face_w
-        return _Cube2EquirecFn.apply(cube_feat, self.sample_grid, 0, self.face_w, self.equ_h, self.equ_w)
+        return _Cube2EquirecFn.apply(cube_feat, self.sample_grid, 0, self.face_w, self.equ_h, self.equ_w, None)
 
-    def from_faces(self, faces: Tensor) -> Tensor:
+    def from_faces(self, faces: Tensor, depth_to_distance=None) -> Tensor:
         """Rasterizer output [b, 6, c, f, f] in the dataset face order [U B L F R D] -> panorama [b, c, H, W]:
-        ``change_order`` + strip concatenation + stitch in one kernel."""
+        ``change_order`` + strip concatenation + stitch in one kernel.
+
+        ``depth_to_distance=(fx, fy, cx, cy)`` (pixels): the faces hold z-depth and the panorama comes out in radial
+        distance -- the reference's ``depth_to_distance_map_batch`` between ``change_order`` and the stitch
+        (model_wrapper_erp.py:447-463, z_depth_to_distance.py:4-34), fused into the gather."""
         assert faces.dim() == 5 and faces.shape[1] == 6 and faces.shape[-1] == faces.shape[-2] == self.face_w
-        return _Cube2EquirecFn.apply(faces, self.sample_grid, 1, self.face_w, self.equ_h, self.equ_w)
+        k = None if depth_to_distance is None else tuple(float(x) for x in depth_to_distance)
+        return _Cube2EquirecFn.apply(faces, self.sample_grid, 1, self.face_w, self.equ_h, self.equ_w, k)
 
 
 class _Cube2EquirecFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, faces, grid, layout, face_w, H, W):
+    def forward(ctx, faces, grid, layout, face_w, H, W, d2d):
         import ctypes
         from . import _lib
         if faces.device.type != "cuda":
@@ -126,9 +141,10 @@ class _Cube2EquirecFn(torch.autograd.Function):
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(faces.device):
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(lib.s360_cube2equirec_forward(p(faces_c), p(grid_c), layout, B, C, face_w, H, W, p(out), st))
+            k = None if d2d is None else (ctypes.c_float * 4)(*d2d)
+            _lib.check(lib.s360_cube2equirec_forward(p(faces_c), p(grid_c), layout, B, C, face_w, H, W, k, p(out), st))
         ctx.save_for_backward(grid_c)
-        ctx.meta = (layout, face_w, H, W, B, C, faces_c.shape)
+        ctx.meta = (layout, face_w, H, W, B, C, faces_c.shape, d2d)
         return out
 
     @staticmethod
@@ -137,11 +153,12 @@ class _Cube2EquirecFn(torch.autograd.Function):
         from . import _lib
         lib = _lib.load()
         (grid_c,) = ctx.saved_tensors
-        layout, face_w, H, W, B, C, shape = ctx.meta
+        layout, face_w, H, W, B, C, shape, d2d = ctx.meta
         g = grad_out.float().contiguous()
         d_faces = torch.empty(shape, dtype=torch.float32, device=g.device)
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         with torch.cuda.device(g.device):
             st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _lib.check(lib.s360_cube2equirec_backward(p(g), p(grid_c), layout, B, C, face_w, H, W, p(d_faces), st))
-        return d_faces, None, None, None, None, None
+            k = None if d2d is None else (ctypes.c_float * 4)(*d2d)
+            _lib.check(lib.s360_cube2equirec_backward(p(g), p(grid_c), layout, B, C, face_w, H, W, k, p(d_faces), st))
+        return d_faces, None, None, None, None, None, None

@@ -355,3 +355,28 @@ def test_many_overlapping_views_trigger_the_exact_pair_capacity_retry():
     for k in range(V):
         assert rel_l2(c["color"][k], outs[k]["color"]) < TOL, k
     _check_sum(c, outs, "d_shs")
+
+
+def test_stitch_kernel_depth_to_distance_matches_reference_golden():
+    """from_faces(depth_to_distance=...) = the reference's depth-panorama chain (golden vector generated by the reference's
+    own change_order_batch / depth_to_distance_map_batch / Cube2Equirec, tests/golden/make_golden_depth.py); gradient
+    against the torch chain."""
+    import os
+    from splatter360_b200 import cubemap
+    dev = "cuda"
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "depth_panorama.npz"))
+    f, H, W = int(g["face_w"]), int(g["H"]), int(g["W"])
+    k = [float(x) for x in g["fxfycxcy"]]
+    c2e = cubemap.Cube2Equirec(f, H, W).to(dev)
+    faces = torch.from_numpy(g["faces"]).to(dev)[:, :, None].contiguous().requires_grad_()      # [v,6,1,f,f]
+    pano = c2e.from_faces(faces, depth_to_distance=k)
+    np.testing.assert_allclose(pano[:, 0].detach().cpu().numpy(), g["pano"], rtol=2e-5, atol=2e-5)
+    w = torch.randn(pano.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    (pano * w).sum().backward()
+    g_kernel = faces.grad.clone(); faces.grad = None
+    fac = cubemap.depth_to_distance_factor(f, *k).to(dev)
+    chain = torch.stack([c2e.forward_reference(torch.cat(list(cubemap.change_order(faces[v]) * fac), dim=-1)[None])[0]
+                         for v in range(faces.shape[0])])
+    (chain * w).sum().backward()
+    assert rel_l2(pano.detach().cpu().numpy(), chain.detach().cpu().numpy()) < 1e-6
+    assert rel_l2(g_kernel.cpu().numpy(), faces.grad.cpu().numpy()) < 1e-5
