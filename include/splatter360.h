@@ -146,7 +146,7 @@ int s360_forward_render(
     uint32_t* point_list,        /* [instance_capacity] out: Gaussian ids sorted by (tile, depth, id) */
     void* image_state,           /* s360_image_bytes(H,W) out                                  */
     float* out_color,            /* [3,H,W] out                                                */
-    float* out_depth,            /* [H,W] out or NULL: fused depth channel (no gradient)       */
+    float* out_depth,            /* [H,W] out or NULL: fused depth channel (gradient: s360_backward's dL_ddepth) */
     int32_t depth_mode,          /* S360_DEPTH_*                                               */
     float depth_near, float depth_far, /* unscaled near / far for relative_disparity and log   */
     void* scratch,               /* s360_binning_scratch_bytes(instance_capacity,H,W)          */
@@ -160,6 +160,8 @@ int s360_backward(
     const void* geom, const int32_t* radii,
     const uint32_t* point_list, const void* image_state,
     const float* dL_dcolor,      /* [3,H,W]                                                    */
+    const float* dL_ddepth,      /* [H,W] gradient w.r.t. the fused depth channel, or NULL     */
+    int32_t depth_mode, float depth_near, float depth_far, /* as given to s360_forward_render  */
     float* dL_dmeans3D,          /* [P,3] out                                                  */
     float* dL_dmeans2D,          /* [P,3] out (NDC units, z = 0)  */
     float* dL_dcov3D,            /* [P,6] out                                                  */
@@ -210,8 +212,9 @@ int s360_multi_forward_render(const S360View* view, int32_t V, int64_t pair_capa
 int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, const float* means3D,
                         const float* cov3D, const float* opacities, const float* shs, const float* colors_precomp,
                         const void* geom, const uint32_t* point_list, const void* image_state, const float* dL_dcolor,
-                        float* dL_dmeans3D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs, float* dL_dcolors,
-                        void* scratch, void* stream);
+                        const float* dL_ddepth /* [V,H,W] or NULL */, int32_t depth_mode, float depth_near,
+                        float depth_far, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs,
+                        float* dL_dcolors, void* scratch, void* stream);
 
 /* ---- visibility mask (replaces upstream _C.mark_visible) ------------------------------------ */
 int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream);

@@ -89,7 +89,7 @@ def load() -> ctypes.CDLL:
     lib.s360_forward_render.restype = c_int
     lib.s360_forward_render.argtypes = [ctypes.POINTER(S360View), vp, vp, vp, vp, c_int64, vp, vp, vp, vp, c_int32, c_float, c_float, vp, vp]
     lib.s360_backward.restype = c_int
-    lib.s360_backward.argtypes = [ctypes.POINTER(S360View)] + [vp] * 18
+    lib.s360_backward.argtypes = [ctypes.POINTER(S360View)] + [vp] * 10 + [vp, c_int32, c_float, c_float] + [vp] * 8
     lib.s360_mark_visible.restype = c_int
     lib.s360_mark_visible.argtypes = [ctypes.POINTER(S360View), vp, vp, vp]
     lib.s360_debug_unpack_geom.restype = c_int
@@ -121,7 +121,7 @@ def load() -> ctypes.CDLL:
     lib.s360_multi_forward_render.restype = c_int
     lib.s360_multi_forward_render.argtypes = head + [vp, vp, vp, vp, c_int64, vp, vp, vp, vp, c_int32, c_float, c_float, vp, vp]
     lib.s360_multi_backward.restype = c_int
-    lib.s360_multi_backward.argtypes = head + [vp] * 16
+    lib.s360_multi_backward.argtypes = head + [vp] * 9 + [vp, c_int32, c_float, c_float] + [vp] * 7
     for n in ("s360_cube2equirec_forward", "s360_cube2equirec_backward"):
         getattr(lib, n).restype = c_int
         getattr(lib, n).argtypes = [vp, vp] + [c_int32] * 6 + [vp, vp, vp]

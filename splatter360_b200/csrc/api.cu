@@ -246,6 +246,7 @@ int s360_forward_render(const S360View* view, const void* geom, const uint32_t* 
 int s360_backward(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
                   const float* shs, const float* colors_precomp, const void* geom, const int32_t* radii,
                   const uint32_t* point_list, const void* image_state, const float* dL_dcolor,
+                  const float* dL_ddepth, int32_t depth_mode, float depth_near, float depth_far,
                   float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs,
                   float* dL_dcolors, void* scratch, void* stream) {
   (void)colors_precomp;
@@ -254,6 +255,7 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
   if (view->P > 0 && shs && !dL_dshs) return S360_ERR_BAD_ARGUMENT;
   if (view->P > 0 && !shs && !dL_dcolors) return S360_ERR_BAD_ARGUMENT;
   if ((size_t)view->image_height * view->image_width > 0 && !dL_dcolor) return S360_ERR_BAD_ARGUMENT;
+  if (dL_ddepth && (depth_mode < S360_DEPTH_DEPTH || depth_mode > S360_DEPTH_LOG)) return S360_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = view->P, H = view->image_height, W = view->image_width;
   GeomState g = carve_geom(const_cast<void*>(geom), P > 0 ? P : 1);
@@ -265,12 +267,12 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
     StageTimer t(S360_STAGE_RENDER_BWD, st);
     rc = launch_tile_order(*view, 1, img.work, img.order_bwd, st);
     if (rc) return rc;
-    rc = launch_render_backward(*view, 1, g, point_list, img, dL_dcolor, acc, st);
+    rc = launch_render_backward(*view, 1, g, point_list, img, dL_dcolor, dL_ddepth, depth_mode, depth_near, depth_far, acc, st);
     if (rc) return rc;
   }
   StageTimer t(S360_STAGE_PREPROCESS_BWD, st);
   return launch_preprocess_backward(*view, means3D, cov3D, opacities, shs, g, radii, acc, dL_dmeans3D, dL_dmeans2D, dL_dcov3D,
-                                    dL_dopacity, dL_dshs, dL_dcolors, st);
+                                    dL_dopacity, dL_dshs, dL_dcolors, dL_ddepth != nullptr, depth_mode, depth_near, depth_far, st);
 }
 
 // ---- batched multi-view path ---------------------------------------------------------------------------------
@@ -336,6 +338,7 @@ int s360_multi_forward_render(const S360View* view, int32_t V, int64_t pair_capa
 int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, const float* means3D,
                         const float* cov3D, const float* opacities, const float* shs, const float* colors_precomp,
                         const void* geom, const uint32_t* point_list, const void* image_state, const float* dL_dcolor,
+                        const float* dL_ddepth, int32_t depth_mode, float depth_near, float depth_far,
                         float* dL_dmeans3D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs, float* dL_dcolors,
                         void* scratch, void* stream) {
   (void)colors_precomp;
@@ -344,6 +347,7 @@ int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, 
   if (view->P > 0 && shs && !dL_dshs) return S360_ERR_BAD_ARGUMENT;
   if (view->P > 0 && !shs && !dL_dcolors) return S360_ERR_BAD_ARGUMENT;
   if ((size_t)view->image_height * view->image_width > 0 && !dL_dcolor) return S360_ERR_BAD_ARGUMENT;
+  if (dL_ddepth && (depth_mode < S360_DEPTH_DEPTH || depth_mode > S360_DEPTH_LOG)) return S360_ERR_BAD_ARGUMENT;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = view->P, H = view->image_height, W = view->image_width;
   const int64_t cap = pair_capacity > 0 ? pair_capacity : 1;
@@ -358,12 +362,12 @@ int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, 
     if (rc) return rc;
     rc = launch_tile_order(*view, V, img.work, img.order_bwd, st);
     if (rc) return rc;
-    rc = launch_render_backward(*view, V, g, point_list, img, dL_dcolor, acc, st);
+    rc = launch_render_backward(*view, V, g, point_list, img, dL_dcolor, dL_ddepth, depth_mode, depth_near, depth_far, acc, st);
     if (rc) return rc;
   }
   StageTimer t(S360_STAGE_PREPROCESS_BWD, st);
   return launch_preprocess_multi_backward(*view, V, means3D, cov3D, opacities, shs, g, ps, acc, dL_dmeans3D, dL_dcov3D,
-                                          dL_dopacity, dL_dshs, dL_dcolors, st);
+                                          dL_dopacity, dL_dshs, dL_dcolors, dL_ddepth != nullptr, depth_mode, depth_near, depth_far, st);
 }
 
 int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream) {

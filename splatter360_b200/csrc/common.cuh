@@ -123,6 +123,44 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 void count_launch(int n = 1);
 
 // ---------------------------------------------------------------------------------------------
+// Fused depth channel: what the reference renders in a second full pass by feeding
+// per-Gaussian depth as colour (cuda_splatting.py:226-269).  The geometry record stores the sort depth of the
+// rescaled scene (camera z for pinhole, radial distance for erp); dividing by scene_scale recovers the value the
+// reference computes from the unscaled means.
+struct DepthSpec {
+  int mode;          // S360_DEPTH_*
+  float inv_scale;   // 1 / scene_scale
+  float near, far;   // unscaled, for relative_disparity / log
+};
+__device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth) {
+  const float z = rec_depth * d.inv_scale;
+  if (d.mode == S360_DEPTH_DISPARITY) return 1.f / z;
+  if (d.mode == S360_DEPTH_RELATIVE_DISPARITY) {
+    const float eps = 1e-10f;
+    const float dn = 1.f / (d.near + eps), df = 1.f / (d.far + eps), dz = 1.f / (z + eps);
+    return 1.f - (dz - df) / (dn - df + eps);
+  }
+  if (d.mode == S360_DEPTH_LOG) return logf(fmaxf(fminf(z, d.near), d.far));   // literal: .minimum(near).maximum(far).log()
+  return z;
+}
+// d depth_value / d rec_depth (what autograd gives through the reference's torch expressions)
+__device__ __forceinline__ float depth_value_grad(const DepthSpec& d, float rec_depth) {
+  const float z = rec_depth * d.inv_scale;
+  if (d.mode == S360_DEPTH_DISPARITY) return -d.inv_scale / (z * z);
+  if (d.mode == S360_DEPTH_RELATIVE_DISPARITY) {
+    const float eps = 1e-10f;
+    const float dn = 1.f / (d.near + eps), df = 1.f / (d.far + eps), zi = 1.f / (z + eps);
+    return d.inv_scale * zi * zi / (dn - df + eps);
+  }
+  if (d.mode == S360_DEPTH_LOG) {
+    // gradient reaches z only where the clamps select it: z <= near and min(z, near) >= far
+    const float m = fminf(z, d.near);
+    return (z <= d.near && m >= d.far) ? d.inv_scale / z : 0.f;
+  }
+  return d.inv_scale;
+}
+
+// ---------------------------------------------------------------------------------------------
 // camera block loaded once per thread from the tiny device-resident matrices
 struct Cam {
   float V[16];
@@ -294,7 +332,7 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
 int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* opac, const float* shs,
                                GeomState g, const int32_t* radii, const float* acc, float* d_means,
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
-                               cudaStream_t st);
+                               int has_depth, int depth_mode, float depth_near, float depth_far, cudaStream_t st);
 int launch_mark_visible(const S360View& v, const float* means, uint8_t* present, cudaStream_t st);
 // batched multi-view K1 / K8+K9 (v.viewmatrix / projmatrix / campos point at NV consecutive cameras)
 int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
@@ -304,7 +342,8 @@ int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, co
 int launch_zero_acc(float* acc, const uint32_t* n_dev, int64_t cap, cudaStream_t st);
 int launch_preprocess_multi_backward(const S360View& v, int NV, const float* means, const float* cov, const float* opac,
                                      const float* shs, GeomState g, PairState ps, const float* acc, float* d_means,
-                                     float* d_cov, float* d_opac, float* d_shs, float* d_colors, cudaStream_t st);
+                                     float* d_cov, float* d_opac, float* d_shs, float* d_colors, int has_depth,
+                                     int depth_mode, float depth_near, float depth_far, cudaStream_t st);
 
 // onesweep radix sort of (u32 key, u32 value) pairs on bits [0, nbits).  keys_a/vals_a hold the input;
 // *_b are same-sized alternates; *result_in_b says where the result landed.  n_dev (device u32, may be NULL)
@@ -333,7 +372,8 @@ int launch_render_forward(const S360View& v, int NV, GeomState g, const uint32_t
                           float* out_color, float* out_depth, int depth_mode, float depth_near, float depth_far,
                           cudaStream_t st);
 int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
-                           const float* dL_dcolor, float* acc, cudaStream_t st);
+                           const float* dL_dcolor, const float* dL_ddepth /* [NV,H,W] or NULL */, int depth_mode,
+                           float depth_near, float depth_far, float* acc, cudaStream_t st);
 
 constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator (9 used)
 

@@ -321,7 +321,8 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
 template <int MODE>
 __device__ __forceinline__ void view_backward(const S360View& v, const float* V, const float* PM, float mx, float my,
                                               float mz, const float* cv, float op, const float4& a0, const float4& a1,
-                                              float* dm, float* dm2, float* dcov) {
+                                              float* dm, float* dm2, float* dcov, const DepthSpec* ds = nullptr,
+                                              float dl_dd = 0.f) {
   const int W = v.image_width, H = v.image_height;
   Geo g;
   geo_compute<MODE>(v, V, mx, my, mz, cv, g);
@@ -400,6 +401,17 @@ __device__ __forceinline__ void view_backward(const S360View& v, const float* V,
     dt[1] += g.J[0][1] * gu + g.J[1][1] * gv;
     dt[2] += g.J[0][2] * gu + g.J[1][2] * gv;
   }
+  if (ds != nullptr) {
+    // fused depth channel: dl_dd = dL/d(depth value of this Gaussian); the value is a function of the sort depth
+    // (camera z, or radial distance in erp mode), whose view-space gradient is e_z resp. t / |t|
+    if (MODE == S360_MODE_PINHOLE) {
+      dt[2] += dl_dd * depth_value_grad(*ds, g.t[2]);
+    } else {
+      const float r = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]);
+      const float coef = dl_dd * depth_value_grad(*ds, r) / r;
+      dt[0] += coef * g.t[0]; dt[1] += coef * g.t[1]; dt[2] += coef * g.t[2];
+    }
+  }
   // mean3D <- view-space gradient: dm_k += sum_i R[i][k] dt_i,  R[i][k] = V[4k + i]
 #pragma unroll
   for (int k = 0; k < 3; k++) dm[k] += V[4 * k] * dt[0] + V[4 * k + 1] * dt[1] + V[4 * k + 2] * dt[2];
@@ -414,7 +426,8 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
                            const float* __restrict__ opac, const float* __restrict__ shs, GeomState gs, const int32_t* __restrict__ radii,
                            const float* __restrict__ acc, float* __restrict__ d_means,
                            float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
-                           float* __restrict__ d_shs, float* __restrict__ d_colors) {
+                           float* __restrict__ d_shs, float* __restrict__ d_colors, const DepthSpec dspec,
+                           const int has_depth) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
   __shared__ uint64_t s_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -459,7 +472,8 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     float cv[6];
     load_cov6(v, cov3D, idx, cv);
     const float op = opac[idx];
-    view_backward<MODE>(v, V, cam.PM, mx, my, mz, cv, op, a0, a1, dm, dm2, dcov);
+    view_backward<MODE>(v, V, cam.PM, mx, my, mz, cv, op, a0, a1, dm, dm2, dcov, has_depth ? &dspec : nullptr,
+                        has_depth ? acc[(size_t)idx * ACC_STRIDE + 9] : 0.f);
     if (shs != nullptr) {
       const float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
       const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
@@ -522,17 +536,19 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
 int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* opac, const float* shs,
                                GeomState g, const int32_t* radii, const float* acc, float* d_means,
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
-                               cudaStream_t st) {
+                               int has_depth, int depth_mode, float depth_near, float depth_far, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
   if (smem > 200 * 1024) return S360_ERR_UNSUPPORTED;
+  DepthSpec ds;
+  ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
   if (v.mode == S360_MODE_PINHOLE) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors);
+    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
   }
   count_launch();
   return (int)cudaGetLastError();
@@ -841,7 +857,7 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
                                  const float* __restrict__ shs, GeomState gs, PairState ps,
                                  const float* __restrict__ acc, float* __restrict__ d_means,
                                  float* __restrict__ d_cov, float* __restrict__ d_opac, float* __restrict__ d_shs,
-                                 float* __restrict__ d_colors) {
+                                 float* __restrict__ d_colors, const DepthSpec dspec, const int has_depth) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
   __shared__ uint64_t s_bar;
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
@@ -900,7 +916,8 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
       const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)slot * ACC_STRIDE + 4);
       dop += acc[(size_t)slot * ACC_STRIDE + 8];
       float dmv[3], dm2v[2], dcv[6];
-      view_backward<MODE>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dmv, dm2v, dcv);
+      view_backward<MODE>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dmv, dm2v, dcv, has_depth ? &dspec : nullptr,
+                          has_depth ? acc[(size_t)slot * ACC_STRIDE + 9] : 0.f);
 #pragma unroll
       for (int k = 0; k < 3; k++) dm[k] += dmv[k];
 #pragma unroll
@@ -963,17 +980,20 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
 
 int launch_preprocess_multi_backward(const S360View& v, int NV, const float* means, const float* cov, const float* opac,
                                      const float* shs, GeomState g, PairState ps, const float* acc, float* d_means,
-                                     float* d_cov, float* d_opac, float* d_shs, float* d_colors, cudaStream_t st) {
+                                     float* d_cov, float* d_opac, float* d_shs, float* d_colors, int has_depth,
+                                     int depth_mode, float depth_near, float depth_far, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
   if (smem > 190 * 1024) return S360_ERR_UNSUPPORTED;
+  DepthSpec ds;
+  ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
   if (v.mode == S360_MODE_PINHOLE) {
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_multi_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors);
+    preprocess_multi_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
   } else {
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_multi_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors);
+    preprocess_multi_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
   }
   count_launch();
   return (int)cudaGetLastError();

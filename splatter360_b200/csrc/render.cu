@@ -94,27 +94,6 @@ __device__ __forceinline__ bool rect_can_contribute(const float4& q, const float
   return !(best < thr);
 }
 
-// Fused depth channel: what the reference renders in a second full pass by feeding
-// per-Gaussian depth as colour (cuda_splatting.py:226-269).  The geometry record stores the sort depth of the
-// rescaled scene (camera z for pinhole, radial distance for erp); dividing by scene_scale recovers the value the
-// reference computes from the unscaled means.
-struct DepthSpec {
-  int mode;          // S360_DEPTH_*
-  float inv_scale;   // 1 / scene_scale
-  float near, far;   // unscaled, for relative_disparity / log
-};
-__device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth) {
-  const float z = rec_depth * d.inv_scale;
-  if (d.mode == S360_DEPTH_DISPARITY) return 1.f / z;
-  if (d.mode == S360_DEPTH_RELATIVE_DISPARITY) {
-    const float eps = 1e-10f;
-    const float dn = 1.f / (d.near + eps), df = 1.f / (d.far + eps), dz = 1.f / (z + eps);
-    return 1.f - (dz - df) / (dn - df + eps);
-  }
-  if (d.mode == S360_DEPTH_LOG) return logf(fmaxf(fminf(z, d.near), d.far));   // literal: .minimum(near).maximum(far).log()
-  return z;
-}
-
 #ifndef S360_FWD_PREFETCH
 #define S360_FWD_PREFETCH 0   // 1: next chunk's records travel in registers during compositing; 0: only its ids do (measured faster: fewer registers)
 #endif
@@ -351,13 +330,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-template <int MODE>
+template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(RT, S360_BWD_MINB)
 render_backward_kernel(const int W, const int H, const float* __restrict__ bg, const float4* __restrict__ rec,
                        const uint32_t* __restrict__ point_list, const uint2* __restrict__ ranges,
                        const uint32_t* __restrict__ order,
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-                       const float* __restrict__ dL_dcolor, float* __restrict__ acc) {
+                       const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const DepthSpec dspec,
+                       float* __restrict__ acc) {
   // survivors of the current chunk, compacted back-to-front: [0] = A', B', C', log2(opacity); [1] = r, g, b, bits of the
   // Gaussian id; [2] = centre relative to the warp block (x, y), wide flag, position in the tile list
   __shared__ float4 s_sv[NWARPS][3][32];
@@ -379,6 +359,13 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   pair_init(S, in0, in1, (size_t)py0 * W + px, (size_t)py1 * W + px, plane, final_T + (size_t)view * plane,
             n_contrib + (size_t)view * plane, dL_dcolor + (size_t)view * 3 * plane, bg);
   float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // colour of the previously processed instance
+  // fused depth channel with gradient (DEPTH): a fourth blended channel without background
+  float2 dpd = make_float2(0.f, 0.f), nar3 = make_float2(0.f, 0.f);
+  float lc3 = 0.f;
+  if (DEPTH) {
+    const float* gd = dL_ddepth + (size_t)view * plane;
+    dpd = make_float2(in0 ? gd[(size_t)py0 * W + px] : 0.f, in1 ? gd[(size_t)py1 * W + px] : 0.f);
+  }
   // pixel offsets from the warp-block centre: instance centres are broadcast relative to that centre, which keeps
   // dx, dy accurate to an ulp of the (small) distance even at coordinates in the thousands
   const float offx = pxf - wcx;
@@ -410,6 +397,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     const float thr = col.w;
     const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
     col.w = __uint_as_float(nx.gid);
+    const float nx_depth = nx.r2.w;      // sort depth of this lane's instance (fused depth channel)
     nx.gid = gid2;                       // chunks below the last one are always full
 #if S360_BWD_PREFETCH
     load_records(nx, rec, ci > 0);
@@ -424,7 +412,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const int slot = __popc(mask & ~((2u << lane) - 1u));
       s_sv[warp][0][slot] = ev;
       s_sv[warp][1][slot] = col;
-      s_sv[warp][2][slot] = make_float4(ddx, ddy, 0.f, __uint_as_float(pos0 + (uint32_t)lane));
+      s_sv[warp][2][slot] = make_float4(ddx, ddy, DEPTH ? depth_value(dspec, nx_depth) : 0.f, __uint_as_float(pos0 + (uint32_t)lane));
     }
     const bool any_wide = MODE == S360_MODE_ERP && __any_sync(0xffffffffu, hit && huge);
     __syncwarp();
@@ -459,11 +447,14 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       S.nar0 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc0, lc0), S.nar0), S.nar0);
       S.nar1 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc1, lc1), S.nar1), S.nar1);
       S.nar2 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc2, lc2), S.nar2), S.nar2);
+      if (DEPTH) nar3 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc3, lc3), nar3), nar3);
       lc0 = c.x; lc1 = c.y; lc2 = c.z;
+      if (DEPTH) lc3 = g.z;
       S.nla = nae;
       float2 dLda = __fmul2_rn(__fadd2_rn(make_float2(c.x, c.x), S.nar0), S.dp0);
       dLda = __ffma2_rn(__fadd2_rn(make_float2(c.y, c.y), S.nar1), S.dp1, dLda);
       dLda = __ffma2_rn(__fadd2_rn(make_float2(c.z, c.z), S.nar2), S.dp2, dLda);
+      if (DEPTH) dLda = __ffma2_rn(__fadd2_rn(make_float2(g.z, g.z), nar3), dpd, dLda);
       dLda = __ffma2_rn(dLda, S.T, __fmul2_rn(S.bgT, inv));
       float2 q = __fmul2_rn(make_float2(ex2_approx(p.x), ex2_approx(p.y)), dLda);          // G dL/dalpha
       q.x = ok0 ? q.x : 0.f; q.y = ok1 ? q.y : 0.f;
@@ -478,6 +469,13 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       v[3] = v[8] * dx; v[5] = v[3] * dx; v[6] = v[4] * dx; v[7] = t7.x + t7.y;
       const float s8 = warp_reduce8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], lane);
       float v8 = v[8];
+      if (DEPTH) {
+        // tenth sum: dL/d(depth value) = sum alpha T dL/dD; shares the butterfly of the ninth (upper half-warp)
+        const float2 t3 = __fmul2_rn(nw, dpd);
+        const float v9 = -(t3.x + t3.y);
+        const bool up = lane & 16;
+        v8 = (up ? v9 : v8) + __shfl_xor_sync(0xffffffffu, up ? v8 : v9, 16);
+      } else
       v8 += __shfl_xor_sync(0xffffffffu, v8, 16);
       v8 += __shfl_xor_sync(0xffffffffu, v8, 8);
       v8 += __shfl_xor_sync(0xffffffffu, v8, 4);
@@ -489,6 +487,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       float* dst = acc + (size_t)__float_as_uint(c.w) * ACC_STRIDE;
       if ((lane & 3) == 0) atomicAdd(dst + ((lane >> 2) & 7), s8);
       if (lane == 1) atomicAdd(dst + 8, v8);
+      if (DEPTH && lane == 17) atomicAdd(dst + 9, v8);
     }
     };
     if (any_wide) replay(std::true_type{}); else replay(std::false_type{});
@@ -497,14 +496,18 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
 }
 
 int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
-                           const float* dL_dcolor, float* acc, cudaStream_t st) {
+                           const float* dL_dcolor, const float* dL_ddepth, int depth_mode, float depth_near,
+                           float depth_far, float* acc, cudaStream_t st) {
   const int W = v.image_width, H = v.image_height;
   const int tiles = NV * ((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
   if (tiles == 0) return 0;
-  if (v.mode == S360_MODE_PINHOLE)
-    render_backward_kernel<S360_MODE_PINHOLE><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, acc);
-  else
-    render_backward_kernel<S360_MODE_ERP><<<tiles, RT, 0, st>>>(W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, acc);
+  DepthSpec ds;
+  ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
+#define S360_LAUNCH_BWD(MODE_, DEPTH_) render_backward_kernel<MODE_, DEPTH_><<<tiles, RT, 0, st>>>( \
+      W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, dL_ddepth, ds, acc)
+  if (v.mode == S360_MODE_PINHOLE) { if (dL_ddepth) S360_LAUNCH_BWD(S360_MODE_PINHOLE, true); else S360_LAUNCH_BWD(S360_MODE_PINHOLE, false); }
+  else { if (dL_ddepth) S360_LAUNCH_BWD(S360_MODE_ERP, true); else S360_LAUNCH_BWD(S360_MODE_ERP, false); }
+#undef S360_LAUNCH_BWD
   count_launch();
   return (int)cudaGetLastError();
 }

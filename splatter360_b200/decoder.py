@@ -87,7 +87,7 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
     """Pinhole render of a batch: [b,3,h,w].  Argument meaning identical to the reference.
 
     ``fused_depth_mode`` (extension): also return the depth image [b,h,w] that ``render_depth_cuda`` would produce,
-    accumulated as a fourth channel of the same pass (no gradient flows through it)."""
+    accumulated as a fourth, differentiable channel of the same pass."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b = extrinsics.shape[0]
     depth = None if fused_depth_mode is None else (fused_depth_mode, near.tolist(), far.tolist())
@@ -332,18 +332,19 @@ class DecoderSplattingCUDA(nn.Module):
     """Same forward contract as the reference decoder (decoder_splatting_cuda.py:34-97); constructed from a
     background colour instead of the Hydra dataset config."""
 
-    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True, fused_depth: bool = True) -> None:
         super().__init__()
         self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
         self.batched_views = batched_views   # False: one rasterizer call per view, like the reference
+        self.fused_depth = fused_depth       # False: separate depth-as-colour pass, like the reference
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v, _, _ = extrinsics.shape
         bg = self.background_color[None].expand(b, 3)
-        # Without autograd (evaluation / video, model_wrapper_erp.py:319-345) the depth image is a fourth channel of
-        # the colour pass; with autograd enabled the reference's separate differentiable depth pass is kept.
-        fused = depth_mode is not None and not torch.is_grad_enabled()
+        # the depth image is a fourth, differentiable channel of the colour pass (the reference renders it in a second
+        # full rasterisation with depth as colour, cuda_splatting.py:226-269); fused_depth=False keeps that second pass
+        fused = depth_mode is not None and self.fused_depth
         depth = None
         if self.batched_views:
             # all views of a batch item in one rasterizer pass (the reference loops them, decoder_splatting_cuda.py:47-59)
@@ -383,17 +384,18 @@ class DecoderSplattingERP(nn.Module):
     (kept in the signature, ignored) so it can be swapped for ``DecoderSplattingCUDA`` at the call sites
     /root/reference/src/model/model_wrapper_erp.py:221-229, 336-345."""
 
-    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True) -> None:
+    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True, fused_depth: bool = True) -> None:
         super().__init__()
         self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
         self.batched_views = batched_views
+        self.fused_depth = fused_depth
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Optional[Tensor], near: Tensor,
                 far: Tensor, image_shape: tuple[int, int],
                 depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
         b, v, _, _ = extrinsics.shape
         bg = self.background_color[None].expand(b, 3)
-        fused = depth_mode is not None and not torch.is_grad_enabled()
+        fused = depth_mode is not None and self.fused_depth
         if self.batched_views and v > 1:
             out = render_erp_views(extrinsics, near, far, image_shape, bg, gaussians.means, gaussians.covariances,
                                    gaussians.harmonics, gaussians.opacities, fused_depth_mode=depth_mode if fused else None)

@@ -56,7 +56,7 @@ class GaussianRasterizationSettings(NamedTuple):
     instance_capacity: Optional[int] = None   # None: read the instance count back (exact buffers, one small host read);
     #                                           int: trust this capacity -> no host read at all (CUDA-graph capturable); the
     #                                           device-side overflow flag is in ForwardState.counters, see overflowed()
-    depth_mode: Optional[str] = None   # fused depth channel: "depth" | "disparity" | "relative_disparity" | "log"
+    depth_mode: Optional[str] = None   # fused, differentiable depth channel: "depth" | "disparity" | "relative_disparity" | "log"
     depth_near: float = 0.0            # unscaled near / far used by relative_disparity and log
     depth_far: float = 0.0
     pair_capacity: Optional[int] = None   # batched path only: slots for (view, Gaussian) pairs; None = V * P (never overflows)
@@ -231,9 +231,20 @@ def instances_needed(state: ForwardState) -> int:
     return int(state.counters[0].item()) & 0xFFFFFFFF
 
 
+def _depth_args(settings: GaussianRasterizationSettings, grad_depth: Optional[Tensor], device):
+    """(pointer, mode, near, far) of the fused depth channel's gradient for the backward entry points."""
+    if grad_depth is None or settings.depth_mode is None:
+        return None, ctypes.c_int32(0), ctypes.c_float(0.0), ctypes.c_float(0.0), None
+    g = _f32c(grad_depth, device)
+    return (_ptr(g), ctypes.c_int32(_lib.DEPTH_MODES[settings.depth_mode]), ctypes.c_float(settings.depth_near),
+            ctypes.c_float(settings.depth_far), g)
+
+
 def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: Tensor, opacities: Tensor,
-                 shs: Optional[Tensor], colors: Optional[Tensor], state: ForwardState, grad_color: Tensor):
-    """Run the backward pass through the C-ABI.  Returns a dict of gradient tensors."""
+                 shs: Optional[Tensor], colors: Optional[Tensor], state: ForwardState, grad_color: Tensor,
+                 grad_depth: Optional[Tensor] = None):
+    """Run the backward pass through the C-ABI.  Returns a dict of gradient tensors.  ``grad_depth`` [H,W]: gradient
+    w.r.t. the fused depth channel (settings.depth_mode)."""
     lib = _lib.load()
     device = means3D.device
     P = means3D.shape[0]
@@ -249,11 +260,14 @@ def backward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6:
         g_col = torch.empty((P, 3), **f32) if colors is not None else None
         scratch = torch.empty(lib.s360_backward_scratch_bytes(P), dtype=torch.uint8, device=device)
         grad_color = _f32c(grad_color, device)
+        gd_ptr, gd_mode, gd_near, gd_far, gd_keep = _depth_args(settings, grad_depth, device)
         _lib.check(lib.s360_backward(
             ctypes.byref(view), _ptr(means3D), _ptr(cov6), _ptr(opacities), _ptr(shs), _ptr(colors),
             _ptr(state.geom), _ptr(state.radii), _ptr(state.point_list), _ptr(state.image_state),
-            _ptr(grad_color), _ptr(g_means), _ptr(g_means2D), _ptr(g_cov), _ptr(g_op), _ptr(g_sh), _ptr(g_col),
+            _ptr(grad_color), gd_ptr, gd_mode, gd_near, gd_far,
+            _ptr(g_means), _ptr(g_means2D), _ptr(g_cov), _ptr(g_op), _ptr(g_sh), _ptr(g_col),
             _ptr(scratch), _stream_ptr()))
+        del gd_keep
         if settings.debug:
             torch.cuda.synchronize(device)
     del keep
@@ -364,8 +378,10 @@ def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, 
 
 
 def backward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov: Tensor, opacities: Tensor,
-                       shs: Optional[Tensor], colors: Optional[Tensor], state: MultiForwardState, grad_color: Tensor):
-    """Backward of ``forward_views_raw``: grad_color [V,3,H,W] -> gradients summed over the views."""
+                       shs: Optional[Tensor], colors: Optional[Tensor], state: MultiForwardState, grad_color: Tensor,
+                       grad_depth: Optional[Tensor] = None):
+    """Backward of ``forward_views_raw``: grad_color [V,3,H,W] (and grad_depth [V,H,W] of the fused depth channel)
+    -> gradients summed over the views."""
     lib = _lib.load()
     device = means3D.device
     P = means3D.shape[0]
@@ -381,11 +397,14 @@ def backward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor,
         g_col = torch.empty((P, 3), **f32) if colors is not None else None
         scratch = torch.empty(lib.s360_multi_backward_scratch_bytes(state.pair_capacity), dtype=torch.uint8, device=device)
         grad_color = _f32c(grad_color, device)
+        gd_ptr, gd_mode, gd_near, gd_far, gd_keep = _depth_args(settings, grad_depth, device)
         _lib.check(lib.s360_multi_backward(
             ctypes.byref(view), ctypes.c_int32(V), ctypes.c_int64(state.pair_capacity),
             _ptr(means3D), _ptr(cov), _ptr(opacities), _ptr(shs), _ptr(colors),
             _ptr(state.geom), _ptr(state.point_list), _ptr(state.image_state), _ptr(grad_color),
+            gd_ptr, gd_mode, gd_near, gd_far,
             _ptr(g_means), _ptr(g_cov), _ptr(g_op), _ptr(g_sh), _ptr(g_col), _ptr(scratch), _stream_ptr()))
+        del gd_keep
         if settings.debug:
             torch.cuda.synchronize(device)
     del keep
@@ -415,17 +434,19 @@ class _RasterizeViews(torch.autograd.Function):
         ctx.has_sh = shs_c is not None
         ctx.op_shape = opacities.shape
         ctx.save_for_backward(means3D_c, cov, op, shs_c if shs_c is not None else col_c)
+        ctx.out_shape = color.shape
         if state.depth is not None:
-            ctx.mark_non_differentiable(state.depth)
             return color, state.depth
         return color
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_depth=None):
+    def backward(ctx, grad_out_color, grad_depth=None):
         means3D, cov, op, feat = ctx.saved_tensors
         shs = feat if ctx.has_sh else None
         col = None if ctx.has_sh else feat
-        g = backward_views_raw(ctx.raster_settings, means3D, cov, op, shs, col, ctx.state, grad_out_color)
+        if grad_out_color is None:   # only the depth channel entered the loss
+            grad_out_color = torch.zeros(ctx.out_shape, dtype=torch.float32, device=means3D.device)
+        g = backward_views_raw(ctx.raster_settings, means3D, cov, op, shs, col, ctx.state, grad_out_color, grad_depth)
         return (g["means3D"], g["shs"], g["colors"], g["opacities"].reshape(ctx.op_shape), g["cov3D"], None)
 
 
@@ -461,17 +482,19 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.has_sh = shs_c is not None
         ctx.save_for_backward(means3D_c, cov6, op, shs_c if shs_c is not None else col_c)
         ctx.mark_non_differentiable(state.radii)
+        ctx.out_shape = color.shape
         if state.depth is not None:
-            ctx.mark_non_differentiable(state.depth)
             return color, state.radii, state.depth
         return color, state.radii
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_radii, _grad_depth=None):
+    def backward(ctx, grad_out_color, _grad_radii, grad_depth=None):
         means3D, cov6, op, feat = ctx.saved_tensors
         shs = feat if ctx.has_sh else None
         col = None if ctx.has_sh else feat
-        g = backward_raw(ctx.raster_settings, means3D, cov6, op, shs, col, ctx.state, grad_out_color)
+        if grad_out_color is None:   # only the depth channel entered the loss
+            grad_out_color = torch.zeros(ctx.out_shape, dtype=torch.float32, device=means3D.device)
+        g = backward_raw(ctx.raster_settings, means3D, cov6, op, shs, col, ctx.state, grad_out_color, grad_depth)
         return (g["means3D"], g["means2D"], g["shs"], g["colors"], g["opacities"], None, None, g["cov3D"], None)
 
 

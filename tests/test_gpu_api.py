@@ -354,3 +354,63 @@ def test_capacity_mode_and_cuda_graph_replay():
     assert torch.equal(color, img_e) and not gv.overflowed()
     for k in ("means3D", "cov3D", "opacities", "shs"):
         assert float((grads[k] - g_e[k]).norm() / g_e[k].norm()) < 1e-5, k
+
+
+@pytest.mark.parametrize("mode", ["depth", "disparity", "relative_disparity", "log"])
+def test_fused_depth_channel_is_differentiable_like_the_separate_pass(mode):
+    """Gradients through the fused depth channel (render backward carries a fourth channel, the per-Gaussian backward
+    differentiates the depth value w.r.t. the mean) equal autograd through the reference's formulation: a second
+    rasterisation with depth-as-colour whose colours are torch functions of the means (cuda_splatting.py:226-269).
+    Pinhole, erp, and the batched multi-view pass."""
+    from splatter360_b200 import decoder, synthetic
+    sc = synthetic.random_cloud_scene(2500, sh_degree=4, seed=31, ref_width=64, depth_range=(0.5, 4.0))
+    dev = "cuda"
+    poses = torch.stack([synthetic.target_pose(31 + k) for k in range(3)]).to(dev)
+    near, far = torch.tensor([0.5], device=dev), torch.tensor([20.0], device=dev)
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev)[None]
+    bg = torch.zeros(1, 3, device=dev)
+    leaves = [t[None].to(dev).requires_grad_() for t in (sc.means, sc.covariances, sc.harmonics, sc.opacities)]
+    gen = torch.Generator().manual_seed(2)
+
+    def grads(loss):
+        for t in leaves:
+            t.grad = None
+        loss.backward()
+        return [None if t.grad is None else t.grad.clone() for t in leaves]
+
+    def check(ga, gb, what):
+        for a, b, name in zip(ga, gb, ("means", "covariances", "harmonics", "opacities")):
+            assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < TOL, (what, mode, name, rel_l2(a.cpu().numpy(), b.cpu().numpy()))
+
+    # pinhole
+    w1 = torch.randn(1, 3, 64, 80, generator=gen).to(dev); w2 = torch.randn(1, 64, 80, generator=gen).to(dev)
+    img, dep = decoder.render_cuda(poses[:1], K, near, far, (64, 80), bg, *leaves, fused_depth_mode=mode)
+    g_fused = grads((img * w1).sum() + (dep * w2).sum())
+    img_r = decoder.render_cuda(poses[:1], K, near, far, (64, 80), bg, *leaves)
+    dep_r = decoder.render_depth_cuda(poses[:1], K, near, far, (64, 80), leaves[0], leaves[1], leaves[3], mode=mode)
+    check(g_fused, grads((img_r * w1).sum() + (dep_r * w2).sum()), "pinhole")
+    # depth alone in the loss (no colour gradient at all)
+    img, dep = decoder.render_cuda(poses[:1], K, near, far, (64, 80), bg, *leaves, fused_depth_mode=mode)
+    g_d = grads((dep * w2).sum())
+    dep_r = decoder.render_depth_cuda(poses[:1], K, near, far, (64, 80), leaves[0], leaves[1], leaves[3], mode=mode)
+    g_dr = grads((dep_r * w2).sum())
+    for a, b in ((g_d[0], g_dr[0]), (g_d[1], g_dr[1]), (g_d[3], g_dr[3])):
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < TOL
+    # erp
+    w1 = torch.randn(1, 3, 64, 128, generator=gen).to(dev); w2 = torch.randn(1, 64, 128, generator=gen).to(dev)
+    img, dep = decoder.render_erp(poses[:1], near, far, (64, 128), bg, *leaves, fused_depth_mode=mode)
+    g_fused = grads((img * w1).sum() + (dep * w2).sum())
+    img_r = decoder.render_erp(poses[:1], near, far, (64, 128), bg, *leaves)
+    dep_r = decoder.render_depth_erp(poses[:1], near, far, (64, 128), leaves[0], leaves[1], leaves[3], mode=mode)
+    check(g_fused, grads((img_r * w1).sum() + (dep_r * w2).sum()), "erp")
+    # batched: three pinhole views in one pass, depth channel with gradient
+    w1 = torch.randn(1, 3, 3, 48, 64, generator=gen).to(dev); w2 = torch.randn(1, 3, 48, 64, generator=gen).to(dev)
+    nb, fb = near[None].expand(1, 3), far[None].expand(1, 3)
+    img, dep = decoder.render_cuda_views(poses[None], K[None].expand(1, 3, 3, 3), nb, fb, (48, 64), bg, *leaves, fused_depth_mode=mode)
+    g_fused = grads((img * w1).sum() + (dep * w2).sum())
+    loss = 0
+    for k in range(3):
+        img_r = decoder.render_cuda(poses[k:k + 1], K, near, far, (48, 64), bg, *leaves)
+        dep_r = decoder.render_depth_cuda(poses[k:k + 1], K, near, far, (48, 64), leaves[0], leaves[1], leaves[3], mode=mode)
+        loss = loss + (img_r * w1[:, k]).sum() + (dep_r * w2[:, k]).sum()
+    check(g_fused, grads(loss), "batched")
