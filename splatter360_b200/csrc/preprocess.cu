@@ -696,7 +696,10 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
   stage_cameras(v, NV, MODE == S360_MODE_PINHOLE, s_cam);
   if (shs && threadIdx.x == 0) mbar_init(&s_bar, 1);
   const bool need = __syncthreads_or(mask != 0u) != 0;   // also publishes the cameras and the barrier
-  if (!need) return;                                      // no pair in this CTA: nothing to write, SH never read
+  if (!need) {                                            // no pair in this CTA: nothing to write, SH never read
+    if (idx < P) ps.base[idx] = 0u;                       // (the backward pass loads base next to mask, unconditionally)
+    return;
+  }
   if (shs) {
     if (bulk_ok) {
       if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, sh_bytes); bulk_load(s_sh, sh_src, sh_bytes, &s_bar); }
@@ -872,6 +875,7 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
   const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u) &&
                        ((reinterpret_cast<uintptr_t>(dsh_dst) & 15u) == 0u);
   const uint32_t mask = idx < P ? ps.mask[idx] : 0u;
+  const uint32_t slot0 = idx < P ? ps.base[idx] : 0u;   // loaded with the mask: one dependent global load less before acc
   const bool vis = mask != 0u;
   stage_cameras(v, NV, MODE == S360_MODE_PINHOLE, s_cam);
   if (threadIdx.x == 0) {
@@ -903,7 +907,6 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
     float cv[6];
     load_cov6(v, cov3D, idx, cv);
     const float op = opac[idx];
-    const uint32_t slot0 = ps.base[idx];
     float* sh = s_sh + threadIdx.x * row;
     if (shs != nullptr && bulk_ok) mbar_wait(&s_bar, 0);
     uint32_t slot = slot0;
