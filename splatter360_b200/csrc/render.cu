@@ -299,12 +299,13 @@ __device__ __forceinline__ float warp_reduce8(float v0, float v1, float v2, floa
 constexpr int NACC = 9;         // colour x3, q*dx, q*dy, q*dx^2, q*dxdy, q*dy^2, q
 
 // running state of the lane's pixel pair in the back-to-front pass, packed for FFMA2/FMUL2/FADD2
-// (.x = row py0, .y = row py0 + 4).  nar = -accum_rec, nla = -last_alpha; the colour of the previously processed
-// instance is the same for both pixels and lives in scalar registers of the kernel.
+// (.x = row py0, .y = row py0 + 4).  Upstream carries accum_rec[3] (the colour behind the current instance) and forms
+// dL/dalpha = sum_c (c_c - accum_rec_c) T dL/dC_c.  Here the colour behind instance i enters only through the scalar
+//   B_i = sum_{j behind i} w_j alpha_j T_j + T_final sum_c bg_c dL/dC_c,   w_j = sum_c c_{j,c} dL/dC_c,
+// and dL/dalpha_i = T_i w_i - B_i / (1 - alpha_i): one running value per pixel instead of three, no "previous
+// instance" bookkeeping.  nB = -B.
 struct PairB {
-  float2 T, bgT;
-  float2 nar0, nar1, nar2;
-  float2 nla;
+  float2 T, nB;
   float2 dp0, dp1, dp2;
   uint32_t lastc0, lastc1;
 };
@@ -319,9 +320,8 @@ __device__ __forceinline__ void pair_init(PairB& p, bool in0, bool in1, size_t p
   p.dp1 = make_float2(in0 ? dL[plane + pid0] : 0.f, in1 ? dL[plane + pid1] : 0.f);
   p.dp2 = make_float2(in0 ? dL[2 * plane + pid0] : 0.f, in1 ? dL[2 * plane + pid1] : 0.f);
   const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
-  p.bgT = make_float2(-T0 * (b0 * p.dp0.x + b1 * p.dp1.x + b2 * p.dp2.x), -T1 * (b0 * p.dp0.y + b1 * p.dp1.y + b2 * p.dp2.y));
+  p.nB = make_float2(-T0 * (b0 * p.dp0.x + b1 * p.dp1.x + b2 * p.dp2.x), -T1 * (b0 * p.dp0.y + b1 * p.dp1.y + b2 * p.dp2.y));
   p.T = make_float2(T0, T1);
-  p.nar0 = p.nar1 = p.nar2 = p.nla = make_float2(0.f, 0.f);
 }
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -358,10 +358,8 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   PairB S;
   pair_init(S, in0, in1, (size_t)py0 * W + px, (size_t)py1 * W + px, plane, final_T + (size_t)view * plane,
             n_contrib + (size_t)view * plane, dL_dcolor + (size_t)view * 3 * plane, bg);
-  float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;   // colour of the previously processed instance
   // fused depth channel with gradient (DEPTH): a fourth blended channel without background
-  float2 dpd = make_float2(0.f, 0.f), nar3 = make_float2(0.f, 0.f);
-  float lc3 = 0.f;
+  float2 dpd = make_float2(0.f, 0.f);
   if (DEPTH) {
     const float* gd = dL_ddepth + (size_t)view * plane;
     dpd = make_float2(in0 ? gd[(size_t)py0 * W + px] : 0.f, in1 ? gd[(size_t)py1 * W + px] : 0.f);
@@ -436,26 +434,19 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
       const float4 c = sv[32 + k];
-      // A pixel that does not take this instance runs the same recurrences with alpha = 0, which only folds the
-      // pending (last_alpha, last_color) term into accum_rec early -- bit-identical to skipping it.
+      // A pixel that does not take this instance runs the same recurrences with alpha = 0: T and B stay as they are.
       const float2 nae = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);                  // -alpha or 0
       const float2 om = __fadd2_rn(make_float2(1.f, 1.f), nae);                            // 1 - alpha
       const float2 inv = make_float2(rcp_approx(om.x), rcp_approx(om.y));
       S.T = __fmul2_rn(S.T, inv);
       const float2 nw = __fmul2_rn(nae, S.T);                                              // -alpha T
-      // accum_rec <- last_alpha * last_color + (1 - last_alpha) * accum_rec, kept negated
-      S.nar0 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc0, lc0), S.nar0), S.nar0);
-      S.nar1 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc1, lc1), S.nar1), S.nar1);
-      S.nar2 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc2, lc2), S.nar2), S.nar2);
-      if (DEPTH) nar3 = __ffma2_rn(S.nla, __fadd2_rn(make_float2(lc3, lc3), nar3), nar3);
-      lc0 = c.x; lc1 = c.y; lc2 = c.z;
-      if (DEPTH) lc3 = g.z;
-      S.nla = nae;
-      float2 dLda = __fmul2_rn(__fadd2_rn(make_float2(c.x, c.x), S.nar0), S.dp0);
-      dLda = __ffma2_rn(__fadd2_rn(make_float2(c.y, c.y), S.nar1), S.dp1, dLda);
-      dLda = __ffma2_rn(__fadd2_rn(make_float2(c.z, c.z), S.nar2), S.dp2, dLda);
-      if (DEPTH) dLda = __ffma2_rn(__fadd2_rn(make_float2(g.z, g.z), nar3), dpd, dLda);
-      dLda = __ffma2_rn(dLda, S.T, __fmul2_rn(S.bgT, inv));
+      // w = sum_c c_c dL/dC_c ;  dL/dalpha = T w - B / (1 - alpha) ;  then B += w alpha T  (nB = -B, nw = -alpha T)
+      float2 w = __fmul2_rn(make_float2(c.x, c.x), S.dp0);
+      w = __ffma2_rn(make_float2(c.y, c.y), S.dp1, w);
+      w = __ffma2_rn(make_float2(c.z, c.z), S.dp2, w);
+      if (DEPTH) w = __ffma2_rn(make_float2(g.z, g.z), dpd, w);
+      const float2 dLda = __ffma2_rn(S.T, w, __fmul2_rn(S.nB, inv));
+      S.nB = __ffma2_rn(w, nw, S.nB);
       float2 q = __fmul2_rn(make_float2(ex2_approx(p.x), ex2_approx(p.y)), dLda);          // G dL/dalpha
       q.x = ok0 ? q.x : 0.f; q.y = ok1 ? q.y : 0.f;
       // the lane's two pixels share dx: sum them first, then apply the common factor
