@@ -318,11 +318,10 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
 // dL/d(mean3D) through the projection and the Jacobian, dL/d(cov3D), screen-space gradient dm2 (NDC units).
 // a0 = {dL/dr, dL/dg, dL/db, sum q dx}, a1 = {sum q dy, sum q dx^2, sum q dxdy, sum q dy^2}, q = G dL/dalpha.
 // Shared by the single-view and the batched kernel; the SH part (direction gradient) is added by the caller.
-template <int MODE>
+template <int MODE, bool DEPTH = false>
 __device__ __forceinline__ void view_backward(const S360View& v, const float* V, const float* PM, float mx, float my,
                                               float mz, const float* cv, float op, const float4& a0, const float4& a1,
-                                              float* dm, float* dm2, float* dcov, const DepthSpec* ds = nullptr,
-                                              float dl_dd = 0.f) {
+                                              float* dm, float* dm2, float* dcov, const DepthSpec& ds, float dl_dd) {
   const int W = v.image_width, H = v.image_height;
   Geo g;
   geo_compute<MODE>(v, V, mx, my, mz, cv, g);
@@ -401,14 +400,14 @@ __device__ __forceinline__ void view_backward(const S360View& v, const float* V,
     dt[1] += g.J[0][1] * gu + g.J[1][1] * gv;
     dt[2] += g.J[0][2] * gu + g.J[1][2] * gv;
   }
-  if (ds != nullptr) {
+  if (DEPTH) {
     // fused depth channel: dl_dd = dL/d(depth value of this Gaussian); the value is a function of the sort depth
     // (camera z, or radial distance in erp mode), whose view-space gradient is e_z resp. t / |t|
     if (MODE == S360_MODE_PINHOLE) {
-      dt[2] += dl_dd * depth_value_grad(*ds, g.t[2]);
+      dt[2] += dl_dd * depth_value_grad(ds, g.t[2]);
     } else {
       const float r = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]);
-      const float coef = dl_dd * depth_value_grad(*ds, r) / r;
+      const float coef = dl_dd * depth_value_grad(ds, r) / r;
       dt[0] += coef * g.t[0]; dt[1] += coef * g.t[1]; dt[2] += coef * g.t[2];
     }
   }
@@ -420,14 +419,13 @@ __device__ __forceinline__ void view_backward(const S360View& v, const float* V,
 // ------------------------------------------------------------------------------------------------
 // K8 + K9 fused.  acc[idx*12 + 0..8] = {dL/dr, dL/dg, dL/db, and the moments sum(q dx), sum(q dy), sum(q dx^2),
 // sum(q dx dy), sum(q dy^2), sum(q)} with q = G dL/dalpha, accumulated by render_backward_kernel
-template <int MODE>
+template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_backward_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
                            const float* __restrict__ opac, const float* __restrict__ shs, GeomState gs, const int32_t* __restrict__ radii,
                            const float* __restrict__ acc, float* __restrict__ d_means,
                            float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
-                           float* __restrict__ d_shs, float* __restrict__ d_colors, const DepthSpec dspec,
-                           const int has_depth) {
+                           float* __restrict__ d_shs, float* __restrict__ d_colors, const DepthSpec dspec) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
   __shared__ uint64_t s_bar;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -472,8 +470,8 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     float cv[6];
     load_cov6(v, cov3D, idx, cv);
     const float op = opac[idx];
-    view_backward<MODE>(v, V, cam.PM, mx, my, mz, cv, op, a0, a1, dm, dm2, dcov, has_depth ? &dspec : nullptr,
-                        has_depth ? acc[(size_t)idx * ACC_STRIDE + 9] : 0.f);
+    view_backward<MODE, DEPTH>(v, V, cam.PM, mx, my, mz, cv, op, a0, a1, dm, dm2, dcov, dspec,
+                               DEPTH ? acc[(size_t)idx * ACC_STRIDE + 9] : 0.f);
     if (shs != nullptr) {
       const float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
       const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
@@ -543,13 +541,12 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
   if (smem > 200 * 1024) return S360_ERR_UNSUPPORTED;
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
-  if (v.mode == S360_MODE_PINHOLE) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
-  }
+#define S360_LAUNCH_K8(MODE_, DEPTH_) do { \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    preprocess_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
+  if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_K8(S360_MODE_PINHOLE, true); else S360_LAUNCH_K8(S360_MODE_PINHOLE, false); }
+  else { if (has_depth) S360_LAUNCH_K8(S360_MODE_ERP, true); else S360_LAUNCH_K8(S360_MODE_ERP, false); }
+#undef S360_LAUNCH_K8
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -853,14 +850,14 @@ __device__ __forceinline__ void sh_coeff_backward(const S360View& v, float* sh, 
 
 // Batched K8 + K9: one thread per Gaussian folds the moments of all its pairs into ONE set of gradients
 // (the reference gets the same sum from autograd over V separate rasterizer calls).
-template <int MODE>
+template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(PRE_THREADS, S360_MV_BWD_MINB)
 preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __restrict__ means,
                                  const float* __restrict__ cov3D, const float* __restrict__ opac,
                                  const float* __restrict__ shs, GeomState gs, PairState ps,
                                  const float* __restrict__ acc, float* __restrict__ d_means,
                                  float* __restrict__ d_cov, float* __restrict__ d_opac, float* __restrict__ d_shs,
-                                 float* __restrict__ d_colors, const DepthSpec dspec, const int has_depth) {
+                                 float* __restrict__ d_colors, const DepthSpec dspec) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
   __shared__ uint64_t s_bar;
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
@@ -919,8 +916,8 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
       const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)slot * ACC_STRIDE + 4);
       dop += acc[(size_t)slot * ACC_STRIDE + 8];
       float dmv[3], dm2v[2], dcv[6];
-      view_backward<MODE>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dmv, dm2v, dcv, has_depth ? &dspec : nullptr,
-                          has_depth ? acc[(size_t)slot * ACC_STRIDE + 9] : 0.f);
+      view_backward<MODE, DEPTH>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dmv, dm2v, dcv, dspec,
+                                 DEPTH ? acc[(size_t)slot * ACC_STRIDE + 9] : 0.f);
 #pragma unroll
       for (int k = 0; k < 3; k++) dm[k] += dmv[k];
 #pragma unroll
@@ -991,13 +988,12 @@ int launch_preprocess_multi_backward(const S360View& v, int NV, const float* mea
   if (smem > 190 * 1024) return S360_ERR_UNSUPPORTED;
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
-  if (v.mode == S360_MODE_PINHOLE) {
-    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_multi_backward_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
-  } else {
-    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_multi_backward_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds, has_depth);
-  }
+#define S360_LAUNCH_MK8(MODE_, DEPTH_) do { \
+    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    preprocess_multi_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
+  if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_MK8(S360_MODE_PINHOLE, true); else S360_LAUNCH_MK8(S360_MODE_PINHOLE, false); }
+  else { if (has_depth) S360_LAUNCH_MK8(S360_MODE_ERP, true); else S360_LAUNCH_MK8(S360_MODE_ERP, false); }
+#undef S360_LAUNCH_MK8
   count_launch();
   return (int)cudaGetLastError();
 }
