@@ -87,12 +87,35 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     key[r] = 0; val[r] = 0;
     if (j < n) { key[r] = keys_in[j]; val[r] = vals_in[j]; }
   }
+#ifndef S360_RS_MATCH
+  // lanes with the same digit, from eight ballots (one per digit bit) instead of MATCH.ANY: the match instruction's
+  // latency grows with the number of distinct values in the warp (~30 of 256 digits here) and every round waits for it;
+  // the ballots of all rounds are independent and are issued back to back before the serial counter updates
+  unsigned peer_mask[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    const int64_t j = base + warp * (RS_ITEMS * 32) + r * 32 + lane;
+    const uint32_t d = (key[r] >> shift) & 0xffu;
+    unsigned m = __ballot_sync(0xffffffffu, j < n);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      m &= bit ? bal : ~bal;
+    }
+    peer_mask[r] = m;
+  }
+#endif
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; r++) {
     const int64_t j = base + warp * (RS_ITEMS * 32) + r * 32 + lane;
     const bool valid = j < n;
     const uint32_t d = valid ? ((key[r] >> shift) & 0xffu) : (0x100u | lane);
+#ifdef S360_RS_MATCH
     const unsigned peers = __match_any_sync(0xffffffffu, d);
+#else
+    const unsigned peers = valid ? peer_mask[r] : (1u << lane);
+#endif
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
     if (valid && lane == leader) {
