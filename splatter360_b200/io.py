@@ -3,7 +3,7 @@
 A scene is 352 B/Gaussian (means 12, covariances 36, harmonics 300, opacity 4): at 1M Gaussians the upload (~370 MB
 over PCIe) takes several times longer than rendering it, so a serving / training loop that receives its Gaussians from
 the host should upload scene i+1 on a copy stream while scene i is being rasterized.  ``HostSceneFeeder`` does exactly
-that with pinned source buffers and stream-ordered hand-over; it owns no device memory beyond the in-flight uploads.
+that with pinned source buffers, a small ring of reusable device buffers and stream-ordered hand-over.
 """
 from __future__ import annotations
 
@@ -20,25 +20,49 @@ class Ticket(NamedTuple):
 
 
 class HostSceneFeeder:
-    def __init__(self, device) -> None:
+    """``depth`` sets of device buffers are allocated once (per tensor name / shape / dtype) and reused in a ring, so a
+    steady-state step allocates nothing.  Intended call pattern (one producer/consumer thread):
+
+        t = feeder.submit(host_i)            # upload i starts on the copy stream
+        loop:  d = feeder.get(t);  t = feeder.submit(host_{i+1});  compute(d)
+
+    A ring slot is overwritten ``depth`` submits later; the copy stream first waits for everything enqueued on the
+    consumer's stream so far, which includes the last computation that read that slot."""
+
+    def __init__(self, device, depth: int = 3) -> None:
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = max(2, int(depth))
+        self.rings: Dict[tuple, list] = {}
+        self.n = 0
+
+    def _slot(self, key: str, t: Tensor) -> Tensor:
+        k = (key, tuple(t.shape), t.dtype)
+        ring = self.rings.get(k)
+        if ring is None:
+            ring = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for _ in range(self.depth)]
+            self.rings[k] = ring
+        return ring[self.n % self.depth]
 
     def submit(self, host: Dict[str, Tensor]) -> Ticket:
         """Start the asynchronous upload of a dict of (ideally pinned) host tensors; returns immediately."""
         out, nbytes = {}, 0
+        cur = torch.cuda.current_stream(self.device)
+        free = torch.cuda.Event()
+        free.record(cur)                       # the slot's previous reader was enqueued before this point
+        self.stream.wait_event(free)
         with torch.cuda.stream(self.stream):
             for k, t in host.items():
-                out[k] = t.to(self.device, non_blocking=True)
+                dst = self._slot(k, t)
+                dst.copy_(t, non_blocking=True)
+                out[k] = dst.detach()          # fresh tensor object on the same storage: no autograd state carried over
                 nbytes += t.numel() * t.element_size()
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self.n += 1
         return Ticket(out, ev, nbytes)
 
     def get(self, ticket: Ticket) -> Dict[str, Tensor]:
         """Make the current stream wait for the upload and hand the device tensors over to it."""
-        cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(ticket.ready)
-        for t in ticket.tensors.values():
-            t.record_stream(cur)
+        torch.cuda.current_stream(self.device).wait_event(ticket.ready)
         return ticket.tensors

@@ -414,3 +414,24 @@ def test_fused_depth_channel_is_differentiable_like_the_separate_pass(mode):
         dep_r = decoder.render_depth_cuda(poses[k:k + 1], K, near, far, (48, 64), leaves[0], leaves[1], leaves[3], mode=mode)
         loss = loss + (img_r * w1[:, k]).sum() + (dep_r * w2[:, k]).sum()
     check(g_fused, grads(loss), "batched")
+
+
+def test_host_scene_feeder_ring_hands_over_the_right_data():
+    """Double-buffered upload through a ring of reusable device buffers: every step sees exactly its own host data, also
+    when the consumer attaches autograd state to the handed-over tensors and the slots are recycled."""
+    from splatter360_b200.io import HostSceneFeeder
+    dev = torch.device("cuda")
+    feeder = HostSceneFeeder(dev, depth=2)
+    steps = [dict(a=torch.full((1 << 20,), float(i)).pin_memory(), b=torch.arange(8, dtype=torch.float32).add_(i).pin_memory())
+             for i in range(7)]
+    t = feeder.submit(steps[0])
+    sums = []
+    for i in range(7):
+        d = feeder.get(t)
+        if i + 1 < 7:
+            t = feeder.submit(steps[i + 1])
+        a = d["a"].requires_grad_()
+        (a * d["b"].sum()).sum().backward()          # some work on the consumer stream + autograd state on the slot
+        assert a.grad is not None and float(a.grad[0]) == float(steps[i]["b"].sum())
+        sums.append(float(a.detach().sum()))
+    assert sums == [float(i) * (1 << 20) for i in range(7)]
