@@ -61,5 +61,5 @@ def test_batched_entry_points_size_queries_and_argument_checks():
     # null camera pointers, zero / too many views: rejected before anything is launched
     assert lib.s360_multi_forward_project(ctypes.byref(v), 0, 10, *([None] * 10)) == -1
     assert lib.s360_multi_forward_project(ctypes.byref(v), _lib.MAX_VIEWS + 1, 10, *([None] * 10)) == -1
-    assert lib.s360_multi_backward(ctypes.byref(v), 2, 10, *([None] * 16)) == -1
+    assert lib.s360_multi_backward(ctypes.byref(v), 2, 10, *([None] * 9), None, 0, 0.0, 0.0, *([None] * 7)) == -1
     assert lib.s360_cube2equirec_forward(None, None, 0, 1, 3, 8, 16, 32, None, None, None) == -1
