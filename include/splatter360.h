@@ -31,6 +31,10 @@
  *   s360_forward_render       emit (tile,id) instances in depth order -> stable radix sort by tile
  *                             -> tile ranges -> front-to-back compositing
  *   s360_backward             per-tile back-to-front gradient pass + fused per-Gaussian backward
+ *                             (optionally also the gradient of the fused depth channel)
+ *
+ * Batched form (s360_multi_*): V views of the same Gaussians through the same stages ONCE -- the reference's loop
+ * over views / cube faces as a single pass; and s360_cube2equirec_* stitches six faces into the panorama.
  */
 #ifndef SPLATTER360_H
 #define SPLATTER360_H
