@@ -190,3 +190,19 @@ def test_batched_path_refuses_cpu_tensors_and_too_many_views():
     from splatter360_b200.cubemap import Cube2Equirec
     with pytest.raises(RuntimeError, match="CUDA"):
         Cube2Equirec(8, 16, 32)(torch.zeros(1, 3, 8, 48))
+
+
+def test_only_test_infrastructure_touches_the_oracle():
+    """oracle/ may be used by tests/, __graft_entry__.smoke() and bench.py only (its header says so): nothing in the
+    package, the drop-in module or tools/ imports or loads it."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for sub in ("splatter360_b200", "diff_gaussian_rasterization", "tools"):
+        for dp, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith((".py", ".sh", ".cu", ".cuh")):
+                    src = open(os.path.join(dp, f)).read()
+                    if re.search(r"^\s*(import|from)\s+oracle\b|liboracle|run_oracle", src, flags=re.M):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

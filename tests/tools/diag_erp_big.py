@@ -1,5 +1,5 @@
 import sys, os, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import make_case, run_cuda, run_oracle, rel_l2
 case = make_case(40000, "erp", 1024, 2048, seed=7)

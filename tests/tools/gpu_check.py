@@ -1,7 +1,7 @@
 """First-light GPU check: per-stage parity vs the oracle + a coarse timing at bench scale."""
 import sys, os, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import make_case, rel_l2, run_cuda, run_oracle, make_settings
 from splatter360_b200 import rasterizer, synthetic, camera, _lib

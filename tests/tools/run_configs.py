@@ -2,7 +2,7 @@
 config 1.  Writes gpurun_out/configs.json; the table goes into BASELINE.md / profiles/."""
 import json, math, os, sys, time, statistics
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from splatter360_b200 import camera, rasterizer, synthetic, _lib
 
