@@ -107,6 +107,12 @@ __device__ __forceinline__ bool rect_can_contribute(const float4& q, const float
 #define S360_BWD_MINB 7
 #endif
 
+#ifndef S360_FWD_UNROLL
+#define S360_FWD_UNROLL 2   // survivors evaluated per loop trip of the forward kernel (measured: 1 -> 2 = -8 %)
+#endif
+#define S360_PRAGMA_(x) _Pragma(#x)
+#define S360_PRAGMA(x) S360_PRAGMA_(x)
+
 constexpr int NWARPS = RT / 32;
 
 // Warp-autonomous streaming of a tile's instance list: lane j of every warp gathers instance
@@ -205,7 +211,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     const float4* sv = &s_sv[warp][0][0];
     auto composite = [&](auto wide_tag) {
       constexpr bool WIDE = decltype(wide_tag)::value;
-#pragma unroll 2
+      S360_PRAGMA(unroll S360_FWD_UNROLL)
       for (int k = 0; k < nsv; k++) {
         const float4 e = sv[k];
         const float4 c = sv[32 + k];
