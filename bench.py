@@ -318,6 +318,21 @@ def run_ours(args):
         except Exception:
             traffic = None
     whole = sum(alg.values())
+    # what actually bounds the dominant kernel, from the committed ncu capture of this same command (profiles/)
+    ncu_note = None
+    try:
+        import re
+        kname = {"render_bwd": "render_backward_kernel", "render_fwd": "render_forward_kernel",
+                 "preprocess": "preprocess_kernel", "preprocess_bwd": "preprocess_backward_kernel"}.get(dom)
+        txt = open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.txt")).read()
+        blk = next(b for b in txt.split("== ")[1:] if kname and kname in b.split("\n")[0])
+        pick = lambda key: float(re.search(key + r"\s+([\d.]+)", blk).group(1))
+        ncu_note = {"source": "profiles/r01_ncu_full_summary.txt (ncu --set full of this command)",
+                    "issue_slot_utilisation_pct": pick("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "fma_pipe_utilisation_pct": pick("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "dram_utilisation_pct": pick("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}
+    except Exception:
+        ncu_note = None
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -328,6 +343,7 @@ def run_ours(args):
         "stages_ms": stage_ms,
         "stages_GBps": {k: (alg[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None) for k in alg},
         "instances": {"P": P, "P_visible": P_vis, "N": N},
+        "ncu": ncu_note,
     }
 
     cpu_baseline = None
