@@ -429,6 +429,8 @@ def cpu_oracle_run(sc, pose, P_sample, repeats=1):
     import torch
     import oracle
     from splatter360_b200 import camera, synthetic
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would handicap the CPU arm)
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     means = sc.means.detach().cpu()
     n = means.shape[0]
     idx = torch.arange(n) if P_sample >= n else torch.randperm(n, generator=torch.Generator().manual_seed(0))[:P_sample]
