@@ -65,6 +65,7 @@ def lib():
         build()
         _lib = ctypes.CDLL(_SO)
         _lib.oracle_render.restype = ctypes.c_int
+        _lib.oracle_render_ex.restype = ctypes.c_int
         _lib.oracle_num_threads.restype = ctypes.c_int
         _lib.oracle_cfg_size.restype = ctypes.c_int
         assert _lib.oracle_cfg_size() == ctypes.sizeof(OrcCfg), "OrcCfg layout mismatch"
@@ -112,6 +113,11 @@ def render(
     mode: str = "pinhole",
     dL_dpix=None,
     stages: bool = True,
+    depth_mode: Optional[str] = None,
+    depth_near: float = 0.0,
+    depth_far: float = 0.0,
+    depth_scale: float = 1.0,
+    dL_ddepth=None,
     **consts,
 ) -> dict:
     """Run the C oracle on one view.  All arrays numpy float32.
@@ -120,6 +126,10 @@ def render(
     view/proj: 4x4 as handed to GaussianRasterizationSettings (row-vector convention,
     cuda_splatting.py:85-87).  Returns dict with 'color' [3,H,W], 'radii', and (if
     stages) the per-stage intermediates; gradients if dL_dpix [3,H,W] is given.
+
+    ``depth_mode`` ("depth" | "disparity" | "relative_disparity" | "log"): also blend the per-Gaussian depth value
+    (of sort depth / depth_scale) as a fourth channel -> 'depth_image' [H,W]; ``dL_ddepth`` [H,W] adds its gradient to the
+    returned gradients (the reference's second rasterisation with depth as colour, cuda_splatting.py:226-269).
     """
     L = lib()
     k = dict(DEFAULTS)
@@ -169,6 +179,13 @@ def render(
         }
     n_out = ctypes.c_int64(0)
     grads = {}
+    dmode = -1 if depth_mode is None else {"depth": 0, "disparity": 1, "relative_disparity": 2, "log": 3}[depth_mode]
+    if dmode >= 0:
+        out["depth_image"] = np.zeros((H, W), np.float32)
+    if dL_ddepth is not None:
+        dL_ddepth = _f32(dL_ddepth).reshape(H, W)
+        if dL_dpix is None:
+            dL_dpix = np.zeros((3, H, W), np.float32)
     if dL_dpix is not None:
         dL_dpix = _f32(dL_dpix).reshape(3, H, W)
         grads = {
@@ -181,7 +198,7 @@ def render(
         }
 
     def call(cap, it, ig):
-        return L.oracle_render(
+        return L.oracle_render_ex(
             ctypes.byref(cfg), _ptr(means), _ptr(cov6), _ptr(opac), _ptr(shs), _ptr(colors),
             _ptr(out["color"]), _ptr(out["radii"]), _ptr(st.get("final_T")), _ptr(st.get("n_contrib")),
             _ptr(st.get("xy")), _ptr(st.get("depth")), _ptr(st.get("conic_opacity")), _ptr(st.get("rgb")),
@@ -191,6 +208,8 @@ def render(
             _ptr(dL_dpix), _ptr(grads.get("d_means")), _ptr(grads.get("d_means2D")),
             _ptr(grads.get("d_cov6")), _ptr(grads.get("d_opac")), _ptr(grads.get("d_shs")),
             _ptr(grads.get("d_colors")),
+            ctypes.c_int(dmode), ctypes.c_float(1.0 / depth_scale), ctypes.c_float(depth_near), ctypes.c_float(depth_far),
+            _ptr(out.get("depth_image")), _ptr(dL_ddepth),
         )
 
     rc = call(0, None, None)

@@ -269,7 +269,29 @@ static void sort_pairs_u64(uint64_t* keys, uint32_t* vals, size_t n, int nbits) 
  *   d_means[P,3], d_means2D[P,3], d_cov6[P,6], d_opac[P], d_shs[P,M,3], d_colors[P,3].
  * Returns 0, or -1 on allocation failure, -2 if inst capacity too small.
  * ===================================================================== */
-int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const float* opac,
+/* Depth channel (what the reference renders in a second rasterisation with depth as colour,
+ * /root/reference/src/model/decoder/cuda_splatting.py:226-269): per-Gaussian value of the sort depth z (camera z in
+ * pinhole mode, radial distance in erp mode) divided by `scale`:
+ *   0 depth: z   1 disparity: 1/z   2 relative_disparity: 1 - (1/(z+eps) - 1/(far+eps)) / (1/(near+eps) - 1/(far+eps) + eps)
+ *   3 log: log(max(min(z, near), far))   (literal .minimum(near).maximum(far).log()),
+ * blended with the colour weights, no background.  Returns the value and its derivative w.r.t. the sort depth
+ * (what autograd gives through the reference's torch expressions). */
+static float depth_value(int mode, float sortdepth, float inv_scale, float near, float far, float* dval_dsort) {
+  const float z = sortdepth * inv_scale, eps = 1e-10f;
+  float v, d;
+  if (mode == 1) { v = 1.f / z; d = -1.f / (z * z); }
+  else if (mode == 2) {
+    float dn = 1.f / (near + eps), df = 1.f / (far + eps), zi = 1.f / (z + eps);
+    v = 1.f - (zi - df) / (dn - df + eps); d = zi * zi / (dn - df + eps);
+  } else if (mode == 3) {
+    float m = fminf(z, near);
+    v = logf(fmaxf(m, far)); d = (z <= near && m >= far) ? 1.f / z : 0.f;
+  } else { v = z; d = 1.f; }
+  if (dval_dsort) *dval_dsort = d * inv_scale;
+  return v;
+}
+
+int oracle_render_ex(const OrcCfg* c, const float* means, const float* cov6, const float* opac,
                   const float* shs, const float* colors,
                   float* out_color, int32_t* out_radii, float* out_final_T, uint32_t* out_n_contrib,
                   float* g_xy, float* g_depth, float* g_conic_op, float* g_rgb, uint32_t* g_tiles,
@@ -277,7 +299,10 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
                   int64_t inst_cap, uint32_t* inst_tile, uint32_t* inst_gid, uint32_t* tile_ranges,
                   int64_t* num_rendered,
                   const float* dL_dpix, float* d_means, float* d_means2D, float* d_cov6, float* d_opac,
-                  float* d_shs, float* d_colors) {
+                  float* d_shs, float* d_colors,
+                  int depth_mode /* -1: no depth channel */, float depth_inv_scale, float depth_near, float depth_far,
+                  float* out_depth /* [H,W] or NULL */, const float* dL_ddepth /* [H,W] or NULL */) {
+  const int with_depth = depth_mode >= 0 && depth_mode <= 3;
   const int P = c->P, H = c->H, W = c->W;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE, ntiles = gx * gy;
   const int deg = c->D < c->max_sh_degree ? c->D : c->max_sh_degree;
@@ -421,7 +446,7 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
       for (int lx = 0; lx < TILE; lx++) {
         int pxi = tx * TILE + lx, pyi = ty * TILE + ly;
         if (pxi >= W || pyi >= H) continue;
-        float T = 1.f, C[3] = {0, 0, 0};
+        float T = 1.f, C[3] = {0, 0, 0}, Dz = 0.f;
         uint32_t contributor = 0, last = 0;
         for (uint32_t k = s; k < e; k++) {
           contributor++;
@@ -436,12 +461,14 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
           float test_T = T * (1.f - alpha);
           if (test_T < 0.0001f) break; /* this Gaussian is not blended */
           for (int ch = 0; ch < 3; ch++) C[ch] += rgb[3 * (size_t)g + ch] * alpha * T;
+          if (with_depth) Dz += depth_value(depth_mode, depth[g], depth_inv_scale, depth_near, depth_far, NULL) * alpha * T;
           T = test_T;
           last = contributor;
         }
         size_t pid = (size_t)pyi * W + pxi;
         final_T[pid] = T; n_contrib[pid] = last;
         for (int ch = 0; ch < 3; ch++) out_color[(size_t)ch * H * W + pid] = C[ch] + T * c->bg[ch];
+        if (with_depth && out_depth) out_depth[pid] = Dz;
       }
   }
 
@@ -462,7 +489,8 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
   if (dL_dpix) {
     /* per-Gaussian screen-space accumulators: [0..2] dL/drgb, [3,4] dL/dmean2D (pixel units),
        [5..7] dL/dconic (A, B_true, C), [8] dL/dopacity */
-    double* acc = (double*)calloc((size_t)P * 9 + 1, sizeof(double));
+    const int with_dgrad = with_depth && dL_ddepth != NULL;
+    double* acc = (double*)calloc((size_t)P * 10 + 1, sizeof(double));
     if (!acc) return -1;
     /* ---------------------------------------------------------- K7 render bwd */
 #pragma omp parallel for schedule(dynamic, 1)
@@ -478,6 +506,7 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
           float T = T_final;
           uint32_t last_contributor = n_contrib[pid];
           float dpix[3], accum_rec[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, last_alpha = 0.f;
+          float dpd = with_dgrad ? dL_ddepth[pid] : 0.f, accum_rec_d = 0.f, last_d = 0.f;
           float bg_dot = 0.f;
           for (int ch = 0; ch < 3; ch++) { dpix[ch] = dL_dpix[(size_t)ch * H * W + pid]; bg_dot += c->bg[ch] * dpix[ch]; }
           for (uint32_t k = s + last_contributor; k-- > s;) {
@@ -493,7 +522,16 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
             T = T / (1.f - alpha);
             float dchannel_dcolor = alpha * T;
             float dL_dalpha = 0.f;
-            double* a9 = acc + 9 * (size_t)g;
+            double* a9 = acc + 10 * (size_t)g;
+            if (with_dgrad) {   /* fourth blended channel, no background term */
+              float dv = depth_value(depth_mode, depth[g], depth_inv_scale, depth_near, depth_far, NULL);
+              accum_rec_d = last_alpha * last_d + (1.f - last_alpha) * accum_rec_d;
+              last_d = dv;
+              dL_dalpha += (dv - accum_rec_d) * dpd;
+              double v = (double)(dchannel_dcolor * dpd);
+#pragma omp atomic
+              a9[9] += v;
+            }
             for (int ch = 0; ch < 3; ch++) {
               float cc = rgb[3 * (size_t)g + ch];
               accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
@@ -537,7 +575,7 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
       float dm[3] = {0, 0, 0}, dcov[6] = {0, 0, 0, 0, 0, 0}, dop = 0.f, dm2[3] = {0, 0, 0};
       float dcol[3] = {0, 0, 0};
       if (tiles[i] != 0) {
-        const double* a9 = acc + 9 * (size_t)i;
+        const double* a9 = acc + 10 * (size_t)i;
         const float* m = means + 3 * (size_t)i;
         const float* cv = cov6 + 6 * (size_t)i;
         float gu = (float)a9[3], gv = (float)a9[4];           /* pixel units */
@@ -617,6 +655,14 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
           dt[1] += g.J[0][1] * gu + g.J[1][1] * gv;
           dt[2] += g.J[0][2] * gu + g.J[1][2] * gv;
         }
+        if (with_dgrad) {   /* depth value depends on the mean through the sort depth (view z, or |t| in erp mode) */
+          float tv[3], dd;
+          view_point(c->view, m, tv);
+          depth_value(depth_mode, depth[i], depth_inv_scale, depth_near, depth_far, &dd);
+          float coef = (float)a9[9] * dd;
+          if (c->mode == 0) dt[2] += coef;
+          else { float r = sqrtf(tv[0] * tv[0] + tv[1] * tv[1] + tv[2] * tv[2]); for (int k = 0; k < 3; k++) dt[k] += coef * tv[k] / r; }
+        }
         for (int k = 0; k < 3; k++) dm[k] += R[0][k] * dt[0] + R[1][k] * dt[1] + R[2][k] * dt[2];
         /* SH backward */
         if (c->use_sh) {
@@ -660,6 +706,20 @@ int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const 
   free(xy); free(depth); free(conop); free(rgb); free(ext); free(tiles); free(clamped);
   free(offs); free(keys); free(gids); free(ranges); free(final_T); free(n_contrib);
   return 0;
+}
+
+int oracle_render(const OrcCfg* c, const float* means, const float* cov6, const float* opac,
+                  const float* shs, const float* colors,
+                  float* out_color, int32_t* out_radii, float* out_final_T, uint32_t* out_n_contrib,
+                  float* g_xy, float* g_depth, float* g_conic_op, float* g_rgb, uint32_t* g_tiles,
+                  uint8_t* g_clamped,
+                  int64_t inst_cap, uint32_t* inst_tile, uint32_t* inst_gid, uint32_t* tile_ranges,
+                  int64_t* num_rendered,
+                  const float* dL_dpix, float* d_means, float* d_means2D, float* d_cov6, float* d_opac,
+                  float* d_shs, float* d_colors) {
+  return oracle_render_ex(c, means, cov6, opac, shs, colors, out_color, out_radii, out_final_T, out_n_contrib, g_xy, g_depth,
+                          g_conic_op, g_rgb, g_tiles, g_clamped, inst_cap, inst_tile, inst_gid, tile_ranges, num_rendered,
+                          dL_dpix, d_means, d_means2D, d_cov6, d_opac, d_shs, d_colors, -1, 1.f, 0.f, 0.f, NULL, NULL);
 }
 
 int oracle_num_threads(void) {

@@ -50,11 +50,14 @@ def sh_basis(deg: int, d: torch.Tensor) -> torch.Tensor:
 
 def render(means, cov6, opac, *, shs=None, colors=None, H, W, view, proj, campos, bg=(0., 0., 0.),
            tanfovx=1.0, tanfovy=1.0, sh_degree=0, mode="pinhole", near_cull=0.2, fov_clamp=1.3,
-           lowpass=0.3, pole_eps=1e-3, max_sh_degree=4, dtype=torch.float64):
+           lowpass=0.3, pole_eps=1e-3, max_sh_degree=4, dtype=torch.float64, depth_mode=None, depth_near=0.0,
+           depth_far=0.0, depth_scale=1.0):
     """Differentiable render of one view.  Returns (color[3,H,W], aux dict).
 
     Inputs may require grad.  ``aux['means2D']`` is a dummy leaf whose grad receives the
-    NDC-unit screen-space gradient like upstream's ``means2D`` argument.
+    NDC-unit screen-space gradient like upstream's ``means2D`` argument.  ``depth_mode``: ``aux['depth']`` [H,W] is the
+    differentiable depth channel (per-Gaussian value of sort depth / depth_scale blended with the colour weights,
+    the reference's depth-as-colour pass, cuda_splatting.py:226-269).
     """
     means = means.to(dtype)
     cov6 = cov6.to(dtype)
@@ -158,6 +161,20 @@ def render(means, cov6, opac, *, shs=None, colors=None, H, W, view, proj, campos
     order = sorted([i for i in range(P) if bool(keep[i])], key=lambda i: (float(sortkey[i].detach().float()), i))
     ys, xs = torch.meshgrid(torch.arange(H, dtype=dtype), torch.arange(W, dtype=dtype), indexing="ij")
     tyy, txx = (ys / 16).int(), (xs / 16).int()
+    dval = None
+    if depth_mode is not None:
+        zz = sortkey / depth_scale
+        eps = 1e-10
+        if depth_mode == "disparity":
+            dval = 1 / zz
+        elif depth_mode == "relative_disparity":
+            dn, df = 1 / (depth_near + eps), 1 / (depth_far + eps)
+            dval = 1 - (1 / (zz + eps) - df) / (dn - df + eps)
+        elif depth_mode == "log":
+            dval = zz.minimum(torch.as_tensor(depth_near, dtype=dtype)).maximum(torch.as_tensor(depth_far, dtype=dtype)).log()
+        else:
+            dval = zz
+    D = torch.zeros(H, W, dtype=dtype)
     T = torch.ones(H, W, dtype=dtype)
     C = torch.zeros(3, H, W, dtype=dtype)
     done = torch.zeros(H, W, dtype=torch.bool)
@@ -183,9 +200,12 @@ def render(means, cov6, opac, *, shs=None, colors=None, H, W, view, proj, campos
         ok = ok & ~stop
         w = torch.where(ok, alpha * T, torch.zeros_like(T))
         C = C + rgb[i][:, None, None] * w
+        if dval is not None:
+            D = D + dval[i] * w
         T = torch.where(ok, test_T, T)
         n_contrib = torch.where(ok, count, n_contrib)
     color = C + T * bg[:, None, None]
     aux = dict(means2D=means2D, final_T=T.detach(), n_contrib=n_contrib, keep=keep, px=px.detach(), py=py.detach(),
-               conic=torch.stack([cA, cB, cC], -1).detach(), rgb=rgb.detach(), ex=ex, ey=ey)
+               conic=torch.stack([cA, cB, cC], -1).detach(), rgb=rgb.detach(), ex=ex, ey=ey,
+               depth=D if dval is not None else None)
     return color, aux

@@ -65,3 +65,41 @@ def test_unaligned_sh_pointer_takes_the_fallback_path():
     assert rel_l2(img.detach().cpu().numpy(), o["color"]) < TOL
     assert rel_l2(shs.grad.cpu().numpy(), o["d_shs"]) < TOL
     assert rel_l2(means.grad.cpu().numpy(), o["d_means"]) < TOL
+
+
+@pytest.mark.parametrize("mode,dmode,scale", [("pinhole", "depth", 1.0), ("pinhole", "disparity", 1.0), ("erp", "depth", 1.0),
+                                              ("erp", "relative_disparity", 1.0), ("pinhole", "relative_disparity", 1.6),
+                                              ("erp", "disparity", 0.5)])
+def test_fused_depth_channel_and_its_gradient_match_the_oracle(mode, dmode, scale):
+    """The fourth (depth) channel of the colour pass -- value and all gradients, with colour and depth both in the loss --
+    against the C oracle's depth channel (itself pinned by float64 autograd in tests/test_oracle.py).  scale != 1 checks
+    the in-kernel scene rescale: the oracle gets the scaled scene, the kernels the unscaled one."""
+    import oracle
+    from splatter360_b200.rasterizer import GaussianRasterizer
+    from helpers import make_settings, oracle_kwargs
+    H, W = (64, 80) if mode == "pinhole" else (48, 96)
+    n = 2500
+    case = make_case(n, mode, H, W, seed=13)
+    gen = torch.Generator().manual_seed(5)
+    dL = torch.randn(3, H, W, generator=gen)
+    dD = torch.randn(H, W, generator=gen)
+    near, far = 0.7, 30.0
+    o = oracle.render(case["means"].numpy(), case["cov6"].numpy(), case["opac"].numpy(), shs=case["shs"].numpy(),
+                      dL_dpix=dL.numpy(), dL_ddepth=dD.numpy(), stages=False, depth_mode=dmode, depth_near=near,
+                      depth_far=far, depth_scale=scale, **oracle_kwargs(case))
+    dev = "cuda"
+    # the kernels see the UNSCALED scene and apply scene_scale on load; camera blocks are those of the scaled scene
+    means = (case["means"] / scale).to(dev).requires_grad_()
+    cov6 = (case["cov6"] / scale ** 2).to(dev).requires_grad_()
+    opac = case["opac"].to(dev)[:, None].clone().requires_grad_()
+    shs = case["shs"].to(dev).requires_grad_()
+    s = make_settings(case, dev, depth_mode=dmode, depth_near=near, depth_far=far, scene_scale=scale)
+    color, radii, depth = GaussianRasterizer(s)(means3D=means, means2D=torch.zeros_like(means), shs=shs, colors_precomp=None,
+                                                opacities=opac, cov3D_precomp=cov6)
+    ((color * dL.to(dev)).sum() + (depth * dD.to(dev)).sum()).backward()
+    assert rel_l2(color.detach().cpu().numpy(), o["color"]) < TOL
+    assert rel_l2(depth.detach().cpu().numpy(), o["depth_image"]) < TOL
+    assert rel_l2(means.grad.cpu().numpy() / scale, o["d_means"]) < TOL
+    assert rel_l2(cov6.grad.cpu().numpy() / scale ** 2, o["d_cov6"]) < TOL
+    assert rel_l2(opac.grad.reshape(-1).cpu().numpy(), o["d_opac"]) < TOL
+    assert rel_l2(shs.grad.cpu().numpy(), o["d_shs"]) < TOL

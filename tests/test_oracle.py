@@ -210,3 +210,39 @@ def test_oracle_size_independent_properties(mode):
     g1, g2, g12 = (run_oracle(case, dL=d, stages=False) for d in (d1, d2, 2.0 * d1 - 0.5 * d2))
     for k in ("d_means", "d_cov6", "d_opac", "d_shs"):
         assert rel_l2(g12[k], 2.0 * g1[k] - 0.5 * g2[k]) < 2e-5, k
+
+
+@pytest.mark.parametrize("mode,dmode", [("pinhole", "depth"), ("pinhole", "disparity"), ("pinhole", "relative_disparity"),
+                                        ("erp", "depth"), ("erp", "relative_disparity"), ("pinhole", "log")])
+def test_c_oracle_depth_channel_matches_autograd_oracle(mode, dmode):
+    """Depth channel of the C oracle (value + hand-derived gradient through the blend weights AND through the depth
+    value's dependence on the mean) against float64 autograd: the semantics of the reference's depth-as-colour pass
+    (cuda_splatting.py:226-269), where the 'colour' is a torch function of the means."""
+    from oracle import torch_oracle
+    import oracle
+    H, W = (40, 48) if mode == "pinhole" else (32, 64)
+    case = make_case(100, mode, H, W, seed=9)
+    gen = torch.Generator().manual_seed(3)
+    dL = torch.randn(3, H, W, generator=gen)
+    dD = torch.randn(H, W, generator=gen)
+    dk = dict(depth_mode=dmode, depth_near=0.7, depth_far=30.0, depth_scale=1.6)
+    kw = oracle_kwargs(case)
+    o = oracle.render(case["means"].numpy(), case["cov6"].numpy(), case["opac"].numpy(), shs=case["shs"].numpy(),
+                      dL_dpix=dL.numpy(), dL_ddepth=dD.numpy(), stages=False, **kw, **dk)
+    m = case["means"].double().requires_grad_(); c = case["cov6"].double().requires_grad_()
+    op = case["opac"].double().requires_grad_(); s = case["shs"].double().requires_grad_()
+    col, aux = torch_oracle.render(m, c, op, shs=s, **kw, **dk)
+    ((col * dL.double()).sum() + (aux["depth"] * dD.double()).sum()).backward()
+    assert rel_l2(o["color"], col.detach().numpy()) < 2e-6
+    assert rel_l2(o["depth_image"], aux["depth"].detach().numpy()) < 2e-6
+    for k, v in (("d_means", m.grad), ("d_cov6", c.grad), ("d_opac", op.grad), ("d_shs", s.grad)):
+        assert rel_l2(o[k], v.numpy()) < 5e-6, k
+    # depth alone in the loss
+    o2 = oracle.render(case["means"].numpy(), case["cov6"].numpy(), case["opac"].numpy(), shs=case["shs"].numpy(),
+                       dL_ddepth=dD.numpy(), stages=False, **kw, **dk)
+    for t in (m, c, op, s):
+        t.grad = None
+    col, aux = torch_oracle.render(m, c, op, shs=s, **kw, **dk)
+    (aux["depth"] * dD.double()).sum().backward()
+    for k, v in (("d_means", m.grad), ("d_cov6", c.grad), ("d_opac", op.grad)):
+        assert rel_l2(o2[k], v.numpy()) < 5e-6, k
