@@ -457,6 +457,26 @@ def rasterize_views(means3D, opacities, cov3D_precomp, raster_settings, shs=None
     return _RasterizeViews.apply(means3D, shs, colors_precomp, opacities, cov3D_precomp, raster_settings)
 
 
+def _cpu_copy(args):
+    """Upstream's ``cpu_deep_copy_tuple``: what a debug snapshot holds."""
+    return tuple(a.detach().cpu().clone() if isinstance(a, Tensor) else a for a in args)
+
+
+def _debug_guard(debug: bool, which: str, args, fn):
+    """Upstream's debug convention: with ``settings.debug`` an exception in the native call dumps the
+    CPU copies of its arguments to ``snapshot_fw.dump`` / ``snapshot_bw.dump`` and is re-raised."""
+    if not debug:
+        return fn()
+    cpu_args = _cpu_copy(args)
+    try:
+        return fn()
+    except Exception as ex:
+        torch.save(cpu_args, f"snapshot_{which}.dump")
+        print(f"\nAn error occured in {'forward' if which == 'fw' else 'backward'}. "
+              f"Please forward snapshot_{which}.dump for debugging.")
+        raise ex
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     """Same forward/backward signature as upstream's autograd.Function."""
 
@@ -476,7 +496,9 @@ class _RasterizeGaussians(torch.autograd.Function):
             raise ValueError("shs must be [P,M,3] ([P,3,M] with sh_layout=1)")
         if col_c is not None and col_c.shape != (P, 3):
             raise ValueError("colors_precomp must be [P,3]")
-        color, state = forward_raw(raster_settings, means3D_c, cov6, op, shs_c, col_c)
+        color, state = _debug_guard(
+            bool(raster_settings.debug), "fw", (means3D_c, cov6, op, shs_c, col_c, tuple(raster_settings)),
+            lambda: forward_raw(raster_settings, means3D_c, cov6, op, shs_c, col_c))
         ctx.raster_settings = raster_settings
         ctx.state = state
         ctx.has_sh = shs_c is not None
@@ -494,7 +516,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         col = None if ctx.has_sh else feat
         if grad_out_color is None:   # only the depth channel entered the loss
             grad_out_color = torch.zeros(ctx.out_shape, dtype=torch.float32, device=means3D.device)
-        g = backward_raw(ctx.raster_settings, means3D, cov6, op, shs, col, ctx.state, grad_out_color, grad_depth)
+        g = _debug_guard(
+            bool(ctx.raster_settings.debug), "bw", (means3D, cov6, op, feat, grad_out_color, grad_depth, tuple(ctx.raster_settings)),
+            lambda: backward_raw(ctx.raster_settings, means3D, cov6, op, shs, col, ctx.state, grad_out_color, grad_depth))
         return (g["means3D"], g["means2D"], g["shs"], g["colors"], g["opacities"], None, None, g["cov3D"], None)
 
 

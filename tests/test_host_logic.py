@@ -206,3 +206,19 @@ def test_only_test_infrastructure_touches_the_oracle():
                     if re.search(r"^\s*(import|from)\s+oracle\b|liboracle|run_oracle", src, flags=re.M):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_debug_flag_dumps_a_snapshot_like_upstream(tmp_path, monkeypatch):
+    """settings.debug=True: an exception in the native call writes snapshot_fw.dump (CPU copies of the arguments) and is
+    re-raised (upstream's debug convention); without debug nothing is written."""
+    from splatter360_b200.rasterizer import GaussianRasterizer
+    monkeypatch.chdir(tmp_path)
+    m = torch.zeros(4, 3)
+    kw = dict(means3D=m, means2D=m, opacities=torch.ones(4, 1), colors_precomp=torch.zeros(4, 3), cov3D_precomp=torch.zeros(4, 6))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GaussianRasterizer(_settings())(**kw)
+    assert not os.path.exists(tmp_path / "snapshot_fw.dump")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GaussianRasterizer(_settings(debug=True))(**kw)
+    dump = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
+    assert torch.equal(dump[0], m) and dump[3] is None and torch.equal(dump[4], torch.zeros(4, 3))
