@@ -459,7 +459,8 @@ def rasterize_views(means3D, opacities, cov3D_precomp, raster_settings, shs=None
 
 def _cpu_copy(args):
     """Upstream's ``cpu_deep_copy_tuple``: what a debug snapshot holds."""
-    return tuple(a.detach().cpu().clone() if isinstance(a, Tensor) else a for a in args)
+    return tuple(a.detach().cpu().clone() if isinstance(a, Tensor) else (_cpu_copy(a) if isinstance(a, tuple) else a)
+                 for a in args)
 
 
 def _debug_guard(debug: bool, which: str, args, fn):
