@@ -63,3 +63,23 @@ def test_batched_entry_points_size_queries_and_argument_checks():
     assert lib.s360_multi_forward_project(ctypes.byref(v), _lib.MAX_VIEWS + 1, 10, *([None] * 10)) == -1
     assert lib.s360_multi_backward(ctypes.byref(v), 2, 10, *([None] * 9), None, 0, 0.0, 0.0, *([None] * 7)) == -1
     assert lib.s360_cube2equirec_forward(None, None, 0, 1, 3, 8, 16, 32, None, None, None) == -1
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/splatter360.h must be consumable by a C compiler (the boundary is a C-ABI, no C++ or torch types), and a
+    C program must link against the library and call its pure-host entry points."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "splatter360.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    from splatter360_b200 import _lib
+    _lib.load()
+    src = tmp_path / "link.c"
+    src.write_text('#include <stdio.h>\n#include "splatter360.h"\n'
+                   'int main(void) { printf("%d %zu %s\\n", s360_abi_version(), s360_multi_image_bytes(6, 256, 256), '
+                   's360_error_string(S360_ERR_UNSUPPORTED)); return s360_abi_version() == S360_ABI_VERSION ? 0 : 1; }\n')
+    exe = tmp_path / "link"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:libsplatter360.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == _lib.ABI_VERSION and int(out[1]) > 6 * 256 * 256 * 8

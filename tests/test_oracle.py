@@ -246,3 +246,22 @@ def test_c_oracle_depth_channel_matches_autograd_oracle(mode, dmode):
     (aux["depth"] * dD.double()).sum().backward()
     for k, v in (("d_means", m.grad), ("d_cov6", c.grad), ("d_opac", op.grad)):
         assert rel_l2(o2[k], v.numpy()) < 5e-6, k
+
+
+def test_depth_channel_analytic_constant_depth():
+    """All Gaussians on one plane z = z0 in front of a pinhole camera: the blended depth is z0 * (1 - T_final) exactly
+    (weights sum to 1 - T_final), disparity likewise with 1/z0."""
+    import oracle
+    H, W, n, z0 = 32, 48, 60, 2.5
+    g = torch.Generator().manual_seed(4)
+    means = torch.cat([(torch.rand(n, 2, generator=g) - 0.5) * 3.0, torch.full((n, 1), z0)], -1)
+    cov6 = torch.tensor([0.02, 0, 0, 0.02, 0, 0.02]).repeat(n, 1)
+    opac = 0.2 + 0.6 * torch.rand(n, generator=g)
+    colors = torch.rand(n, 3, generator=g)
+    view = np.eye(4, dtype=np.float32)
+    proj = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, -0.1, 0]], dtype=np.float32)   # w_clip = z
+    for dmode, val in (("depth", z0), ("disparity", 1 / z0)):
+        o = oracle.render(means.numpy(), cov6.numpy(), opac.numpy(), colors=colors.numpy(), H=H, W=W, view=view, proj=proj,
+                          campos=np.zeros(3, np.float32), depth_mode=dmode, stages=True)
+        assert (1 - o["final_T"]).max() > 0.3
+        assert np.allclose(o["depth_image"], val * (1 - o["final_T"]), rtol=2e-5, atol=1e-6)
