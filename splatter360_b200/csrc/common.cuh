@@ -375,6 +375,13 @@ int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_
                            const float* dL_dcolor, const float* dL_ddepth /* [NV,H,W] or NULL */, int depth_mode,
                            float depth_near, float depth_far, float* acc, cudaStream_t st);
 
-constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator (9 used)
+constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator (9 used; a tenth for the depth channel)
+
+// Build switch (prepared, NOT yet measured -- DESIGN.md sec. 7): 1 = the render backward accumulates the moments of
+// q' = (o G) dL/dalpha, i.e. of the unclamped alpha it has already evaluated, instead of q = G dL/dalpha, which saves the
+// second pair of ex2 per survivor; the per-Gaussian backward then drops its opacity factors and divides dL/do by o.
+#ifndef S360_BWD_QPRIME
+#define S360_BWD_QPRIME 0
+#endif
 
 }  // namespace s360

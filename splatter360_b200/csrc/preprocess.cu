@@ -330,9 +330,14 @@ __device__ __forceinline__ void view_backward(const S360View& v, const float* V,
   // dL/dG = o dL/dalpha turns them into the screen-space gradients
   const float det_inv = 1.f / denom;
   const float cA = g.c * det_inv, cB = -g.b * det_inv, cC = g.a * det_inv;   // conic, as in the forward pass
-  const float S1 = op * a0.w, S2 = op * a1.x;
+#if S360_BWD_QPRIME
+  const float mo = 1.f;   // the moments already carry the opacity factor
+#else
+  const float mo = op;
+#endif
+  const float S1 = mo * a0.w, S2 = mo * a1.x;
   const float gu = -cA * S1 - cB * S2, gv = -cC * S2 - cB * S1;
-  const float gA = -0.5f * op * a1.y, gB = -op * a1.z, gC = -0.5f * op * a1.w;
+  const float gA = -0.5f * mo * a1.y, gB = -mo * a1.z, gC = -0.5f * mo * a1.w;
   dm2[0] = gu * 0.5f * W; dm2[1] = gv * 0.5f * H;
   const float inv2 = 1.f / (denom * denom + 0.0000001f);
   const float da = inv2 * (-g.c * g.c * gA + g.b * g.c * gB + (denom - g.a * g.c) * gC);
@@ -464,7 +469,11 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)idx * ACC_STRIDE + 4);
     const float a2 = acc[(size_t)idx * ACC_STRIDE + 8];
     dcol[0] = a0.x; dcol[1] = a0.y; dcol[2] = a0.z;
+#if S360_BWD_QPRIME
+    dop = opac[idx] > 0.f ? a2 / opac[idx] : 0.f;
+#else
     dop = a2;
+#endif
     const float sc = v.scene_scale;
     const float mx = means[3 * idx] * sc, my = means[3 * idx + 1] * sc, mz = means[3 * idx + 2] * sc;
     float cv[6];
@@ -914,7 +923,11 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
       const float* cam = s_cam[view];
       const float4 a0 = *reinterpret_cast<const float4*>(acc + (size_t)slot * ACC_STRIDE);
       const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)slot * ACC_STRIDE + 4);
+#if S360_BWD_QPRIME
+      dop += op > 0.f ? acc[(size_t)slot * ACC_STRIDE + 8] / op : 0.f;
+#else
       dop += acc[(size_t)slot * ACC_STRIDE + 8];
+#endif
       float dmv[3], dm2v[2], dcv[6];
       view_backward<MODE, DEPTH>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dmv, dm2v, dcv, dspec,
                                  DEPTH ? acc[(size_t)slot * ACC_STRIDE + 9] : 0.f);

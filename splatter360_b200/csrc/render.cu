@@ -435,7 +435,8 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const float2 p = __ffma2_rn(__ffma2_rn(make_float2(e.z, e.z), dy, make_float2(u, u)), dy, make_float2(pb, pb));
       // same expressions as the forward pass, so that T / (1 - alpha) undoes exactly what it applied
       const float2 a = __fadd2_rn(p, make_float2(e.w, e.w));
-      const float nal0 = fmaxf(-ALPHA_MAX, -ex2_approx(a.x)), nal1 = fmaxf(-ALPHA_MAX, -ex2_approx(a.y));
+      const float e0 = ex2_approx(a.x), e1 = ex2_approx(a.y);                             // unclamped alpha = o G
+      const float nal0 = fmaxf(-ALPHA_MAX, -e0), nal1 = fmaxf(-ALPHA_MAX, -e1);
       const bool ok0 = (pos < S.lastc0) && (p.x <= 0.f) && (-nal0 >= ALPHA_MIN);
       const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
@@ -453,7 +454,11 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       if (DEPTH) w = __ffma2_rn(make_float2(g.z, g.z), dpd, w);
       const float2 dLda = __ffma2_rn(S.T, w, __fmul2_rn(S.nB, inv));
       S.nB = __ffma2_rn(w, nw, S.nB);
+#if S360_BWD_QPRIME
+      float2 q = __fmul2_rn(make_float2(e0, e1), dLda);   // o G dL/dalpha: the opacity factor is divided out once per Gaussian in K8
+#else
       float2 q = __fmul2_rn(make_float2(ex2_approx(p.x), ex2_approx(p.y)), dLda);          // G dL/dalpha
+#endif
       q.x = ok0 ? q.x : 0.f; q.y = ok1 ? q.y : 0.f;
       // the lane's two pixels share dx: sum them first, then apply the common factor
       const float2 qy = __fmul2_rn(q, dy);
