@@ -34,6 +34,25 @@ def shard_views(num_views: int, rank: Optional[int] = None, world_size: Optional
     return list(range(rank, num_views, world_size))
 
 
+def shard_view_groups(num_views: int, group: int, rank: Optional[int] = None,
+                      world_size: Optional[int] = None) -> List[int]:
+    """Like ``shard_views`` but whole groups of ``group`` consecutive views stay on one rank -- the six cube faces of a
+    panorama (/root/reference/src/model/model_wrapper_erp.py:336-345 renders targets x 6 faces as one view list), so
+    that each rank can render its panoramas in batched passes that share the camera centre (``rasterize_views``).
+    Groups are dealt round-robin; a trailing partial group is a group of its own."""
+    if group <= 0:
+        raise ValueError("group must be positive")
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    n_groups = (num_views + group - 1) // group
+    out: List[int] = []
+    for g in range(rank, n_groups, world_size):
+        out.extend(range(g * group, min((g + 1) * group, num_views)))
+    return out
+
+
 def all_reduce_loss(loss: Tensor, average: bool = False) -> Tensor:
     """Sum (or mean) of a scalar loss over ranks -- the only collective on the hot path."""
     _, ws = world()

@@ -222,3 +222,18 @@ def test_debug_flag_dumps_a_snapshot_like_upstream(tmp_path, monkeypatch):
         GaussianRasterizer(_settings(debug=True))(**kw)
     dump = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
     assert torch.equal(dump[0], m) and dump[3] is None and torch.equal(dump[4], torch.zeros(4, 3))
+
+
+def test_shard_view_groups_keeps_cube_faces_together():
+    from splatter360_b200.parallel import shard_view_groups
+    # 3 target panoramas x 6 faces over 2 ranks: whole panoramas per rank, every view exactly once
+    parts = [shard_view_groups(18, 6, r, 2) for r in range(2)]
+    assert parts[0] == list(range(0, 6)) + list(range(12, 18)) and parts[1] == list(range(6, 12))
+    # 8 ranks, 32 frames of 1 view: identical to round-robin
+    from splatter360_b200.parallel import shard_views
+    assert all(shard_view_groups(32, 1, r, 8) == shard_views(32, r, 8) for r in range(8))
+    # partial trailing group, more ranks than groups
+    parts = [shard_view_groups(14, 6, r, 4) for r in range(4)]
+    assert sorted(sum(parts, [])) == list(range(14)) and parts[2] == [12, 13] and parts[3] == []
+    with pytest.raises(ValueError):
+        shard_view_groups(6, 0, 0, 1)
