@@ -37,6 +37,24 @@ struct ImageState {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Pure per-Gaussian math (projection, covariance, SH, their derivatives) is host + device: the kernels inline it, and
+// tests/host_harness compiles the very same functions for the CPU to check them against the oracle without a GPU.
+#define S360_HD __host__ __device__ __forceinline__
+S360_HD float s360_inf() {
+#ifdef __CUDA_ARCH__
+  return __int_as_float(0x7f800000);
+#else
+  return __builtin_huge_valf();
+#endif
+}
+S360_HD uint32_t s360_float_bits(float x) {
+#ifdef __CUDA_ARCH__
+  return __float_as_uint(x);
+#else
+  uint32_t u; __builtin_memcpy(&u, &x, 4); return u;
+#endif
+}
+
 inline GeomState carve_geom(void* buf, int P) {
   char* p = (char*)buf;
   GeomState g;
@@ -132,7 +150,7 @@ struct DepthSpec {
   float inv_scale;   // 1 / scene_scale
   float near, far;   // unscaled, for relative_disparity / log
 };
-__device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth) {
+S360_HD float depth_value(const DepthSpec& d, float rec_depth) {
   const float z = rec_depth * d.inv_scale;
   if (d.mode == S360_DEPTH_DISPARITY) return 1.f / z;
   if (d.mode == S360_DEPTH_RELATIVE_DISPARITY) {
@@ -144,7 +162,7 @@ __device__ __forceinline__ float depth_value(const DepthSpec& d, float rec_depth
   return z;
 }
 // d depth_value / d rec_depth (what autograd gives through the reference's torch expressions)
-__device__ __forceinline__ float depth_value_grad(const DepthSpec& d, float rec_depth) {
+S360_HD float depth_value_grad(const DepthSpec& d, float rec_depth) {
   const float z = rec_depth * d.inv_scale;
   if (d.mode == S360_DEPTH_DISPARITY) return -d.inv_scale / (z * z);
   if (d.mode == S360_DEPTH_RELATIVE_DISPARITY) {
@@ -190,7 +208,7 @@ struct Geo {
 };
 
 template <int MODE>
-__device__ __forceinline__ void geo_compute(const S360View& v, const float* V, float mx, float my, float mz,
+S360_HD void geo_compute(const S360View& v, const float* V, float mx, float my, float mz,
                                             const float* cov, Geo& g) {
   // R[i][k] = V[4k + i]
   g.t[0] = V[0] * mx + V[4] * my + V[8] * mz + V[12];
@@ -248,49 +266,58 @@ __device__ __forceinline__ void geo_compute(const S360View& v, const float* V, f
 
 // ---------------------------------------------------------------------------------------------
 // real spherical harmonics, 3DGS sign convention, bands 0..4
-__device__ constexpr float SH_C0 = 0.28209479177387814f;
-__device__ constexpr float SH_C1 = 0.4886025119029199f;
-__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
-                                       -1.0925484305920792f, 0.5462742152960396f};
-__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
-                                       0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
-                                       -0.5900435899266435f};
-__device__ constexpr float SH_C4[9] = {2.5033429417967046f,  -1.7701307697799304f, 0.9461746957575601f,
-                                       -0.6690465435572892f, 0.10578554691520431f, -0.6690465435572892f,
-                                       0.47308734787878004f, -1.7701307697799304f, 0.6258357354491761f};
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+// band 2..4 constants as host + device lookups (a namespace-scope constexpr ARRAY is not visible to device code)
+S360_HD constexpr float sh_c2(int i) {
+  constexpr float t[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                          0.5462742152960396f};
+  return t[i];
+}
+S360_HD constexpr float sh_c3(int i) {
+  constexpr float t[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                          -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+  return t[i];
+}
+S360_HD constexpr float sh_c4(int i) {
+  constexpr float t[9] = {2.5033429417967046f, -1.7701307697799304f, 0.9461746957575601f, -0.6690465435572892f,
+                          0.10578554691520431f, -0.6690465435572892f, 0.47308734787878004f, -1.7701307697799304f,
+                          0.6258357354491761f};
+  return t[i];
+}
 
 // basis values for all 25 slots (unused bands are left untouched); returns number of active coeffs
-__device__ __forceinline__ int sh_basis(int deg, float x, float y, float z, float* b) {
+S360_HD int sh_basis(int deg, float x, float y, float z, float* b) {
   b[0] = SH_C0;
   if (deg < 1) return 1;
   b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
   if (deg < 2) return 4;
   const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  b[4] = SH_C2[0] * xy; b[5] = SH_C2[1] * yz; b[6] = SH_C2[2] * (2.f * zz - xx - yy);
-  b[7] = SH_C2[3] * xz; b[8] = SH_C2[4] * (xx - yy);
+  b[4] = sh_c2(0) * xy; b[5] = sh_c2(1) * yz; b[6] = sh_c2(2) * (2.f * zz - xx - yy);
+  b[7] = sh_c2(3) * xz; b[8] = sh_c2(4) * (xx - yy);
   if (deg < 3) return 9;
-  b[9] = SH_C3[0] * y * (3.f * xx - yy);
-  b[10] = SH_C3[1] * xy * z;
-  b[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
-  b[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-  b[13] = SH_C3[4] * x * (4.f * zz - xx - yy);
-  b[14] = SH_C3[5] * z * (xx - yy);
-  b[15] = SH_C3[6] * x * (xx - 3.f * yy);
+  b[9] = sh_c3(0) * y * (3.f * xx - yy);
+  b[10] = sh_c3(1) * xy * z;
+  b[11] = sh_c3(2) * y * (4.f * zz - xx - yy);
+  b[12] = sh_c3(3) * z * (2.f * zz - 3.f * xx - 3.f * yy);
+  b[13] = sh_c3(4) * x * (4.f * zz - xx - yy);
+  b[14] = sh_c3(5) * z * (xx - yy);
+  b[15] = sh_c3(6) * x * (xx - 3.f * yy);
   if (deg < 4) return 16;
-  b[16] = SH_C4[0] * xy * (xx - yy);
-  b[17] = SH_C4[1] * yz * (3.f * xx - yy);
-  b[18] = SH_C4[2] * xy * (7.f * zz - 1.f);
-  b[19] = SH_C4[3] * yz * (7.f * zz - 3.f);
-  b[20] = SH_C4[4] * (zz * (35.f * zz - 30.f) + 3.f);
-  b[21] = SH_C4[5] * xz * (7.f * zz - 3.f);
-  b[22] = SH_C4[6] * (xx - yy) * (7.f * zz - 1.f);
-  b[23] = SH_C4[7] * xz * (xx - 3.f * yy);
-  b[24] = SH_C4[8] * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+  b[16] = sh_c4(0) * xy * (xx - yy);
+  b[17] = sh_c4(1) * yz * (3.f * xx - yy);
+  b[18] = sh_c4(2) * xy * (7.f * zz - 1.f);
+  b[19] = sh_c4(3) * yz * (7.f * zz - 3.f);
+  b[20] = sh_c4(4) * (zz * (35.f * zz - 30.f) + 3.f);
+  b[21] = sh_c4(5) * xz * (7.f * zz - 3.f);
+  b[22] = sh_c4(6) * (xx - yy) * (7.f * zz - 1.f);
+  b[23] = sh_c4(7) * xz * (xx - 3.f * yy);
+  b[24] = sh_c4(8) * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
   return 25;
 }
 
 // partial derivatives of the basis polynomials w.r.t. (x, y, z) taken as independent variables
-__device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
+S360_HD void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
   bx[0] = by[0] = bz[0] = 0.f;
   if (deg < 1) return;
   bx[1] = 0.f; by[1] = -SH_C1; bz[1] = 0.f;
@@ -298,30 +325,30 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
   bx[3] = -SH_C1; by[3] = 0.f; bz[3] = 0.f;
   if (deg < 2) return;
   const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  bx[4] = SH_C2[0] * y; by[4] = SH_C2[0] * x; bz[4] = 0.f;
-  bx[5] = 0.f; by[5] = SH_C2[1] * z; bz[5] = SH_C2[1] * y;
-  bx[6] = SH_C2[2] * -2.f * x; by[6] = SH_C2[2] * -2.f * y; bz[6] = SH_C2[2] * 4.f * z;
-  bx[7] = SH_C2[3] * z; by[7] = 0.f; bz[7] = SH_C2[3] * x;
-  bx[8] = SH_C2[4] * 2.f * x; by[8] = SH_C2[4] * -2.f * y; bz[8] = 0.f;
+  bx[4] = sh_c2(0) * y; by[4] = sh_c2(0) * x; bz[4] = 0.f;
+  bx[5] = 0.f; by[5] = sh_c2(1) * z; bz[5] = sh_c2(1) * y;
+  bx[6] = sh_c2(2) * -2.f * x; by[6] = sh_c2(2) * -2.f * y; bz[6] = sh_c2(2) * 4.f * z;
+  bx[7] = sh_c2(3) * z; by[7] = 0.f; bz[7] = sh_c2(3) * x;
+  bx[8] = sh_c2(4) * 2.f * x; by[8] = sh_c2(4) * -2.f * y; bz[8] = 0.f;
   if (deg < 3) return;
-  bx[9] = SH_C3[0] * 6.f * xy; by[9] = SH_C3[0] * (3.f * xx - 3.f * yy); bz[9] = 0.f;
-  bx[10] = SH_C3[1] * yz; by[10] = SH_C3[1] * xz; bz[10] = SH_C3[1] * xy;
-  bx[11] = SH_C3[2] * -2.f * xy; by[11] = SH_C3[2] * (4.f * zz - xx - 3.f * yy); bz[11] = SH_C3[2] * 8.f * yz;
-  bx[12] = SH_C3[3] * -6.f * xz; by[12] = SH_C3[3] * -6.f * yz; bz[12] = SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy);
-  bx[13] = SH_C3[4] * (4.f * zz - 3.f * xx - yy); by[13] = SH_C3[4] * -2.f * xy; bz[13] = SH_C3[4] * 8.f * xz;
-  bx[14] = SH_C3[5] * 2.f * xz; by[14] = SH_C3[5] * -2.f * yz; bz[14] = SH_C3[5] * (xx - yy);
-  bx[15] = SH_C3[6] * (3.f * xx - 3.f * yy); by[15] = SH_C3[6] * -6.f * xy; bz[15] = 0.f;
+  bx[9] = sh_c3(0) * 6.f * xy; by[9] = sh_c3(0) * (3.f * xx - 3.f * yy); bz[9] = 0.f;
+  bx[10] = sh_c3(1) * yz; by[10] = sh_c3(1) * xz; bz[10] = sh_c3(1) * xy;
+  bx[11] = sh_c3(2) * -2.f * xy; by[11] = sh_c3(2) * (4.f * zz - xx - 3.f * yy); bz[11] = sh_c3(2) * 8.f * yz;
+  bx[12] = sh_c3(3) * -6.f * xz; by[12] = sh_c3(3) * -6.f * yz; bz[12] = sh_c3(3) * (6.f * zz - 3.f * xx - 3.f * yy);
+  bx[13] = sh_c3(4) * (4.f * zz - 3.f * xx - yy); by[13] = sh_c3(4) * -2.f * xy; bz[13] = sh_c3(4) * 8.f * xz;
+  bx[14] = sh_c3(5) * 2.f * xz; by[14] = sh_c3(5) * -2.f * yz; bz[14] = sh_c3(5) * (xx - yy);
+  bx[15] = sh_c3(6) * (3.f * xx - 3.f * yy); by[15] = sh_c3(6) * -6.f * xy; bz[15] = 0.f;
   if (deg < 4) return;
-  bx[16] = SH_C4[0] * (3.f * xx * y - yy * y); by[16] = SH_C4[0] * (xx * x - 3.f * x * yy); bz[16] = 0.f;
-  bx[17] = SH_C4[1] * 6.f * xy * z; by[17] = SH_C4[1] * z * (3.f * xx - 3.f * yy); bz[17] = SH_C4[1] * y * (3.f * xx - yy);
-  bx[18] = SH_C4[2] * y * (7.f * zz - 1.f); by[18] = SH_C4[2] * x * (7.f * zz - 1.f); bz[18] = SH_C4[2] * 14.f * xy * z;
-  bx[19] = 0.f; by[19] = SH_C4[3] * z * (7.f * zz - 3.f); bz[19] = SH_C4[3] * y * (21.f * zz - 3.f);
-  bx[20] = 0.f; by[20] = 0.f; bz[20] = SH_C4[4] * (140.f * zz * z - 60.f * z);
-  bx[21] = SH_C4[5] * z * (7.f * zz - 3.f); by[21] = 0.f; bz[21] = SH_C4[5] * x * (21.f * zz - 3.f);
-  bx[22] = SH_C4[6] * 2.f * x * (7.f * zz - 1.f); by[22] = SH_C4[6] * -2.f * y * (7.f * zz - 1.f);
-  bz[22] = SH_C4[6] * (xx - yy) * 14.f * z;
-  bx[23] = SH_C4[7] * z * (3.f * xx - 3.f * yy); by[23] = SH_C4[7] * -6.f * xy * z; bz[23] = SH_C4[7] * x * (xx - 3.f * yy);
-  bx[24] = SH_C4[8] * (4.f * xx * x - 12.f * x * yy); by[24] = SH_C4[8] * (-12.f * xx * y + 4.f * yy * y); bz[24] = 0.f;
+  bx[16] = sh_c4(0) * (3.f * xx * y - yy * y); by[16] = sh_c4(0) * (xx * x - 3.f * x * yy); bz[16] = 0.f;
+  bx[17] = sh_c4(1) * 6.f * xy * z; by[17] = sh_c4(1) * z * (3.f * xx - 3.f * yy); bz[17] = sh_c4(1) * y * (3.f * xx - yy);
+  bx[18] = sh_c4(2) * y * (7.f * zz - 1.f); by[18] = sh_c4(2) * x * (7.f * zz - 1.f); bz[18] = sh_c4(2) * 14.f * xy * z;
+  bx[19] = 0.f; by[19] = sh_c4(3) * z * (7.f * zz - 3.f); bz[19] = sh_c4(3) * y * (21.f * zz - 3.f);
+  bx[20] = 0.f; by[20] = 0.f; bz[20] = sh_c4(4) * (140.f * zz * z - 60.f * z);
+  bx[21] = sh_c4(5) * z * (7.f * zz - 3.f); by[21] = 0.f; bz[21] = sh_c4(5) * x * (21.f * zz - 3.f);
+  bx[22] = sh_c4(6) * 2.f * x * (7.f * zz - 1.f); by[22] = sh_c4(6) * -2.f * y * (7.f * zz - 1.f);
+  bz[22] = sh_c4(6) * (xx - yy) * 14.f * z;
+  bx[23] = sh_c4(7) * z * (3.f * xx - 3.f * yy); by[23] = sh_c4(7) * -6.f * xy * z; bz[23] = sh_c4(7) * x * (xx - 3.f * yy);
+  bx[24] = sh_c4(8) * (4.f * xx * x - 12.f * x * yy); by[24] = sh_c4(8) * (-12.f * xx * y + 4.f * yy * y); bz[24] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,67 @@
+// harness.cu -- TEST INFRASTRUCTURE.  Compiles the per-Gaussian math the kernels inline (splatter360_b200/csrc/persplat.cuh:
+// project_view, sh_to_rgb, view_backward, depth_value) for the HOST, so that tests/test_host_math.py can check the very
+// code the GPU runs against the CPU oracle without a GPU.  Plain C entry points, host pointers everywhere.
+#include "../../splatter360_b200/csrc/persplat.cuh"
+
+using namespace s360;
+
+extern "C" {
+
+// K1 geometry + SH colour of every Gaussian for one view (view->viewmatrix / projmatrix / campos are HOST pointers here)
+int s360h_project(const S360View* view, const float* means, const float* cov, const float* opac, const float* shs,
+                  float* xy /*[P,2]*/, float* conic_op /*[P,4]*/, float* depth /*[P]*/, int32_t* radii /*[P]*/,
+                  uint32_t* tiles /*[P]*/, float* rgb /*[P,3]*/, uint8_t* clamped /*[P,3]*/) {
+  const S360View& v = *view;
+  const float wf = view_frobenius2(v.viewmatrix);
+  for (int i = 0; i < v.P; i++) {
+    const float sc = v.scene_scale;
+    const float mx = means[3 * i] * sc, my = means[3 * i + 1] * sc, mz = means[3 * i + 2] * sc;
+    float cv[6];
+    load_cov6(v, cov, i, cv);
+    Proj pr;
+    if (v.mode == S360_MODE_PINHOLE) project_view<S360_MODE_PINHOLE>(v, v.viewmatrix, v.projmatrix, mx, my, mz, cv, opac, i, wf, pr);
+    else project_view<S360_MODE_ERP>(v, v.viewmatrix, v.projmatrix, mx, my, mz, cv, opac, i, wf, pr);
+    radii[i] = pr.radius;
+    tiles[i] = pr.tiles;
+    xy[2 * i] = pr.px; xy[2 * i + 1] = pr.py;
+    conic_op[4 * i] = pr.cA; conic_op[4 * i + 1] = pr.cB; conic_op[4 * i + 2] = pr.cC; conic_op[4 * i + 3] = pr.op;
+    depth[i] = pr.sortkey;
+    float col[3] = {0.f, 0.f, 0.f};
+    uint8_t cl = 0;
+    if (pr.upstream_visible && shs) sh_to_rgb(v, shs + (size_t)i * v.M * 3, mx, my, mz, v.campos, col, cl);
+    for (int c = 0; c < 3; c++) { rgb[3 * i + c] = col[c]; clamped[3 * i + c] = (cl >> c) & 1; }
+  }
+  return 0;
+}
+
+// K8 geometry backward of every Gaussian from given moment sums acc[P,9] = {dL/drgb[3], sum q dx, sum q dy, sum q dx^2,
+// sum q dxdy, sum q dy^2, sum q}: dL/dmean (geometry path only, no SH direction term), dL/dmean2D (NDC), dL/dcov6
+int s360h_view_backward(const S360View* view, const float* means, const float* cov, const float* opac, const float* acc,
+                        float* d_means /*[P,3]*/, float* d_means2D /*[P,2]*/, float* d_cov6 /*[P,6]*/) {
+  const S360View& v = *view;
+  const DepthSpec ds = {0, 1.f, 0.f, 0.f};
+  for (int i = 0; i < v.P; i++) {
+    const float sc = v.scene_scale;
+    const float mx = means[3 * i] * sc, my = means[3 * i + 1] * sc, mz = means[3 * i + 2] * sc;
+    float cv[6];
+    load_cov6(v, cov, i, cv);
+    const float* a = acc + 9 * (size_t)i;
+    const float4 a0 = make_float4(a[0], a[1], a[2], a[3]), a1 = make_float4(a[4], a[5], a[6], a[7]);
+    float dm[3], dm2[2], dcv[6];
+    if (v.mode == S360_MODE_PINHOLE) view_backward<S360_MODE_PINHOLE, false>(v, v.viewmatrix, v.projmatrix, mx, my, mz, cv, opac[i], a0, a1, dm, dm2, dcv, ds, 0.f);
+    else view_backward<S360_MODE_ERP, false>(v, v.viewmatrix, v.projmatrix, mx, my, mz, cv, opac[i], a0, a1, dm, dm2, dcv, ds, 0.f);
+    for (int k = 0; k < 3; k++) d_means[3 * i + k] = dm[k] * sc;
+    d_means2D[2 * i] = dm2[0]; d_means2D[2 * i + 1] = dm2[1];
+    for (int k = 0; k < 6; k++) d_cov6[6 * i + k] = dcv[k] * sc * sc;
+  }
+  return 0;
+}
+
+// fused depth channel: per-Gaussian value and its derivative w.r.t. the sort depth
+int s360h_depth_value(int mode, float inv_scale, float near, float far, int n, const float* sort_depth, float* value, float* grad) {
+  const DepthSpec ds = {mode, inv_scale, near, far};
+  for (int i = 0; i < n; i++) { value[i] = depth_value(ds, sort_depth[i]); grad[i] = depth_value_grad(ds, sort_depth[i]); }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+"""CPU tests of the kernels' own per-Gaussian math.  splatter360_b200/csrc/persplat.cuh (projection, EWA covariance, conic,
+extents, tile rectangle, SH -> RGB, geometry backward, depth value) is host + device code: the CUDA kernels inline it, and
+tests/host_harness/harness.cu compiles the SAME functions for the host.  Here they are checked against the C oracle (forward)
+and against finite differences of themselves (backward) -- no GPU needed, no compute call into libsplatter360."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_case, oracle_kwargs, rel_l2, run_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+pytestmark = pytest.mark.skipif(not (os.path.exists(NVCC) or shutil.which("nvcc")), reason="nvcc not available")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    src = os.path.join(HERE, "host_harness", "harness.cu")
+    out = os.path.join(HERE, "host_harness", "libharness.so")
+    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        nvcc = NVCC if os.path.exists(NVCC) else shutil.which("nvcc")
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                        "-o", out, src], check=True, capture_output=True)
+    return ctypes.CDLL(out)
+
+
+def _view(case, P, M, tight_bbox=0, scene_scale=1.0):
+    from splatter360_b200 import _lib
+    keep = [np.ascontiguousarray(case[k].numpy(), dtype=np.float32) for k in ("view", "proj", "campos", "bg")]
+    v = _lib.S360View()
+    v.P, v.M, v.sh_degree = P, M, case["sh_degree"]
+    v.image_height, v.image_width = case["H"], case["W"]
+    v.mode = {"pinhole": 0, "erp": 1}[case["mode"]]
+    v.max_sh_degree, v.tight_bbox = 4, tight_bbox
+    v.tanfovx, v.tanfovy = case["tanfovx"], case["tanfovy"]
+    v.near_cull, v.fov_clamp, v.lowpass, v.pole_eps = 0.2, 1.3, 0.3, 1e-3
+    v.scene_scale, v.sh_layout, v.cov_layout = scene_scale, 0, 0
+    v.viewmatrix, v.projmatrix, v.campos, v.bg = (k.ctypes.data for k in keep)
+    return v, keep
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _project(harness, case, **kw):
+    P, M = case["means"].shape[0], case["shs"].shape[1]
+    v, keep = _view(case, P, M, **kw)
+    ins = [np.ascontiguousarray(case[k].numpy(), dtype=np.float32) for k in ("means", "cov6", "opac", "shs")]
+    out = dict(xy=np.zeros((P, 2), np.float32), conic_opacity=np.zeros((P, 4), np.float32), depth=np.zeros(P, np.float32),
+               radii=np.zeros(P, np.int32), tiles_touched=np.zeros(P, np.uint32), rgb=np.zeros((P, 3), np.float32),
+               clamped=np.zeros((P, 3), np.uint8))
+    rc = harness.s360h_project(ctypes.byref(v), *[_p(a) for a in ins], *[_p(out[k]) for k in
+                               ("xy", "conic_opacity", "depth", "radii", "tiles_touched", "rgb", "clamped")])
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("mode,H,W,n", [("pinhole", 96, 128, 4000), ("erp", 64, 128, 4000), ("pinhole", 37, 53, 900), ("erp", 256, 512, 3000)])
+def test_kernel_projection_math_matches_oracle_on_the_host(harness, mode, H, W, n):
+    """K1 as the GPU runs it (project_view + sh_to_rgb, tight box off = upstream's rectangle) against the oracle's K1."""
+    case = make_case(n, mode, H, W, seed=3)
+    o = run_oracle(case)
+    c = _project(harness, case)
+    vis = o["radii"] > 0
+    assert vis.sum() > n // 20
+    assert np.array_equal(c["radii"], o["radii"])
+    assert np.array_equal(c["tiles_touched"], o["tiles_touched"])
+    for k in ("xy", "depth", "conic_opacity", "rgb"):
+        assert rel_l2(c[k][vis], o[k][vis]) < 1e-5, k
+    assert np.array_equal(c["clamped"][vis], o["clamped"][vis])
+
+
+def test_tight_box_only_removes_tiles(harness):
+    """tight_bbox=1 intersects upstream's rectangle with the alpha >= 1/255 box: never more tiles, same geometry."""
+    case = make_case(3000, "pinhole", 96, 128, seed=4)
+    a, b = _project(harness, case, tight_bbox=0), _project(harness, case, tight_bbox=1)
+    assert (b["tiles_touched"] <= a["tiles_touched"]).all() and (b["tiles_touched"] < a["tiles_touched"]).any()
+    assert np.array_equal(a["radii"], b["radii"]) and np.array_equal(a["xy"], b["xy"])
+
+
+@pytest.mark.parametrize("mode", ["pinhole", "erp"])
+def test_kernel_geometry_backward_is_the_derivative_of_the_kernel_projection(harness, mode):
+    """view_backward turns the moment sums of the render pass into dL/d(mean, cov).  With moments chosen such that the
+    screen-space gradients are (gu, gv, gA, gB, gC), the result must be the derivative of
+    F = gu px + gv py + gA cA + gB cB_true... evaluated with the kernel's own forward projection (central differences in
+    float32, so the tolerance is loose; the exact check is the GPU parity suite)."""
+    H, W, n = (64, 64, 300) if mode == "pinhole" else (64, 128, 40)
+    case = make_case(n, mode, H, W, seed=6, inflate=30.0)
+    base = _project(harness, case)
+    vis = base["radii"] > 0
+    if mode == "pinhole":   # stay inside the field of view: the 1.3 tan(fov) clamp deliberately breaks differentiability
+        vis &= (np.abs(base["xy"][:, 0] - W / 2) < 0.45 * W) & (np.abs(base["xy"][:, 1] - H / 2) < 0.45 * H)
+    idx = np.nonzero(vis)[0][:10]
+    assert len(idx) >= 6
+    rng = np.random.default_rng(0)
+    P, M = n, case["shs"].shape[1]
+    mom = rng.standard_normal((P, 5)).astype(np.float32)          # sum q dx, q dy, q dx^2, q dxdy, q dy^2
+    acc = np.zeros((P, 9), np.float32)
+    acc[:, 3:8] = mom
+    v, keep = _view(case, P, M)
+    ins = [np.ascontiguousarray(case[k].numpy(), dtype=np.float32) for k in ("means", "cov6", "opac")]
+    d_means, d_m2, d_cov = np.zeros((P, 3), np.float32), np.zeros((P, 2), np.float32), np.zeros((P, 6), np.float32)
+    assert harness.s360h_view_backward(ctypes.byref(v), *[_p(a) for a in ins], _p(acc), _p(d_means), _p(d_m2), _p(d_cov)) == 0
+    op = case["opac"].numpy()
+    con = base["conic_opacity"]
+    # what the moments mean: screen-space gradients in pixel units
+    gu = -op * (con[:, 0] * mom[:, 0] + con[:, 1] * mom[:, 1])
+    gv = -op * (con[:, 2] * mom[:, 1] + con[:, 1] * mom[:, 0])
+    gA, gB, gC = -0.5 * op * mom[:, 2], -op * mom[:, 3], -0.5 * op * mom[:, 4]
+
+    def F(c2):
+        pr = _project(harness, c2)
+        return (gu * pr["xy"][:, 0] + gv * pr["xy"][:, 1] + gA * pr["conic_opacity"][:, 0] + gB * pr["conic_opacity"][:, 1]
+                + gC * pr["conic_opacity"][:, 2]).astype(np.float64)
+
+    def fd(key, j, i, h):
+        cp, cm = dict(case), dict(case)
+        cp[key] = case[key].clone(); cm[key] = case[key].clone()
+        cp[key][i, j] += h; cm[key][i, j] -= h
+        return (F(cp)[i] - F(cm)[i]) / (2 * h)
+
+    num_m = np.array([[fd("means", j, i, 2e-3) for j in range(3)] for i in idx])
+    num_c = np.array([[fd("cov6", j, i, 2e-4 * float(case["cov6"][i].abs().max())) for j in range(6)] for i in idx])
+    assert rel_l2(d_means[idx], num_m) < 2e-3
+    assert rel_l2(d_cov[idx], num_c) < 3e-2
+    assert np.allclose(d_m2[idx, 0], gu[idx] * 0.5 * W, rtol=1e-5) and np.allclose(d_m2[idx, 1], gv[idx] * 0.5 * H, rtol=1e-5)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_depth_value_and_its_derivative(harness, mode):
+    near, far, inv_scale = 0.7, 30.0, 1 / 1.6
+    z = np.linspace(0.3, 60.0, 400).astype(np.float32)
+    val, grad = np.zeros_like(z), np.zeros_like(z)
+    assert harness.s360h_depth_value(mode, ctypes.c_float(inv_scale), ctypes.c_float(near), ctypes.c_float(far), len(z), _p(z), _p(val), _p(grad)) == 0
+    zz = z.astype(np.float64) * inv_scale
+    eps = 1e-10
+    ref = [zz, 1 / zz, 1 - (1 / (zz + eps) - 1 / (far + eps)) / (1 / (near + eps) - 1 / (far + eps) + eps),
+           np.log(np.maximum(np.minimum(zz, near), far))][mode]
+    assert np.allclose(val, ref, rtol=2e-6, atol=1e-7)
+    dn, df = 1 / (near + eps), 1 / (far + eps)
+    dref = [np.full_like(zz, inv_scale), -inv_scale / zz ** 2, inv_scale / (zz + eps) ** 2 / (dn - df + eps),
+            np.where((zz <= near) & (np.minimum(zz, near) >= far), inv_scale / zz, 0.0)][mode]
+    assert np.allclose(grad, dref, rtol=2e-6, atol=1e-9)
