@@ -2,6 +2,7 @@
 // project_view, sh_to_rgb, view_backward, depth_value) for the HOST, so that tests/test_host_math.py can check the very
 // code the GPU runs against the CPU oracle without a GPU.  Plain C entry points, host pointers everywhere.
 #include "../../splatter360_b200/csrc/persplat.cuh"
+#include "../../splatter360_b200/csrc/render_cull.cuh"
 
 using namespace s360;
 
@@ -61,6 +62,20 @@ int s360h_view_backward(const S360View* view, const float* means, const float* c
 int s360h_depth_value(int mode, float inv_scale, float near, float far, int n, const float* sort_depth, float* value, float* grad) {
   const DepthSpec ds = {mode, inv_scale, near, far};
   for (int i = 0; i < n; i++) { value[i] = depth_value(ds, sort_depth[i]); grad[i] = depth_value_grad(ds, sort_depth[i]); }
+  return 0;
+}
+
+// render kernels: stage an instance from its 48-B record and run the exact ellipse / 8x8-block test for a block whose
+// centre is block_c; also returns the staged evaluation parameters {A', B', C', log2 o}
+int s360h_cull(int n, const float* rec /*[n,12]*/, const float* block_c /*[n,2]*/, uint8_t* hit, float* ev_out /*[n,4]*/) {
+  for (int i = 0; i < n; i++) {
+    const float* r = rec + 12 * (size_t)i;
+    const float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]), r2 = make_float4(r[8], r[9], r[10], r[11]);
+    float4 cull, ev, col;
+    stage_instance(r0, r1, r2, cull, ev, col);
+    hit[i] = rect_can_contribute(cull, ev, col.w, cull.x - block_c[2 * i], cull.y - block_c[2 * i + 1]) ? 1 : 0;
+    ev_out[4 * i] = ev.x; ev_out[4 * i + 1] = ev.y; ev_out[4 * i + 2] = ev.z; ev_out[4 * i + 3] = ev.w;
+  }
   return 0;
 }
 

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not (os.path.exists(NVCC) or shutil.which("nvcc"
 def harness():
     src = os.path.join(HERE, "host_harness", "harness.cu")
     out = os.path.join(HERE, "host_harness", "libharness.so")
-    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh", "render_cull.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         nvcc = NVCC if os.path.exists(NVCC) else shutil.which("nvcc")
         subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
@@ -148,3 +148,42 @@ def test_depth_value_and_its_derivative(harness, mode):
     dref = [np.full_like(zz, inv_scale), -inv_scale / zz ** 2, inv_scale / (zz + eps) ** 2 / (dn - df + eps),
             np.where((zz <= near) & (np.minimum(zz, near) >= far), inv_scale / zz, 0.0)][mode]
     assert np.allclose(grad, dref, rtol=2e-6, atol=1e-9)
+
+
+def test_block_cull_never_drops_a_contributing_instance(harness):
+    """The render kernels evaluate an instance only for the 8x8 pixel blocks that rect_can_contribute lets through.  Brute
+    force over the 64 pixels (float64): whenever some pixel of the block sees alpha >= 1/255 the test must say yes
+    (image exactness); and it must not be lax -- blocks it lets through without any such pixel are only near misses, and
+    distant Gaussians are rejected."""
+    rng = np.random.default_rng(7)
+    n = 200000
+    # random screen-space Gaussians: cov2D = R diag(s1^2, s2^2) R^T + 0.3 I, conic = inverse; centres around the block
+    s1, s2 = np.exp(rng.uniform(np.log(0.3), np.log(12.0), n)), np.exp(rng.uniform(np.log(0.3), np.log(12.0), n))
+    th = rng.uniform(0, np.pi, n)
+    c, s_ = np.cos(th), np.sin(th)
+    a = c * c * s1 ** 2 + s_ * s_ * s2 ** 2 + 0.3
+    b = c * s_ * (s1 ** 2 - s2 ** 2)
+    d = s_ * s_ * s1 ** 2 + c * c * s2 ** 2 + 0.3
+    det = a * d - b * b
+    cA, cB, cC = d / det, -b / det, a / det
+    op = rng.uniform(0.004, 1.0, n)
+    centre = rng.uniform(-40, 48, (n, 2))
+    block_c = np.tile(np.array([[3.5, 3.5]]), (n, 1))           # pixels 0..7 x 0..7
+    rec = np.zeros((n, 12), np.float32)
+    rec[:, 0:2] = centre; rec[:, 2] = cA; rec[:, 3] = cB; rec[:, 4] = cC; rec[:, 5] = op
+    rec[:, 6] = 1.0; rec[:, 7] = 1.0                              # finite half extents: tight culling enabled
+    hit = np.zeros(n, np.uint8); ev = np.zeros((n, 4), np.float32)
+    assert harness.s360h_cull(n, _p(rec), _p(np.ascontiguousarray(block_c, dtype=np.float32)), _p(hit), _p(ev)) == 0
+    px, py = np.meshgrid(np.arange(8.0), np.arange(8.0))
+    r32 = rec.astype(np.float64)
+    dx = r32[:, 0, None] - px.reshape(1, -1); dy = r32[:, 1, None] - py.reshape(1, -1)
+    power = -0.5 * (r32[:, 2, None] * dx * dx + r32[:, 4, None] * dy * dy) - r32[:, 3, None] * dx * dy
+    alpha = r32[:, 5, None] * np.exp(power)
+    contributes = ((alpha >= 1.0 / 255.0) & (power <= 0)).any(axis=1)
+    assert contributes.sum() > n // 20 and (~contributes).sum() > n // 20
+    assert hit[contributes].all(), "the block test culled an instance that reaches alpha >= 1/255 inside the block"
+    lax = hit.astype(bool) & ~contributes
+    # let through without a contributing pixel: only because the best CONTINUOUS point of the block reaches the threshold
+    assert lax.sum() < 0.25 * hit.sum()
+    best_alpha_pixel = alpha.max(axis=1)
+    assert (best_alpha_pixel[lax] > 0.2 / 255.0).all()
