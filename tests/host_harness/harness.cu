@@ -11,7 +11,7 @@ extern "C" {
 // K1 geometry + SH colour of every Gaussian for one view (view->viewmatrix / projmatrix / campos are HOST pointers here)
 int s360h_project(const S360View* view, const float* means, const float* cov, const float* opac, const float* shs,
                   float* xy /*[P,2]*/, float* conic_op /*[P,4]*/, float* depth /*[P]*/, int32_t* radii /*[P]*/,
-                  uint32_t* tiles /*[P]*/, float* rgb /*[P,3]*/, uint8_t* clamped /*[P,3]*/) {
+                  uint32_t* tiles /*[P]*/, float* rgb /*[P,3]*/, uint8_t* clamped /*[P,3]*/, float* half_extent /*[P,2] or NULL*/) {
   const S360View& v = *view;
   const float wf = view_frobenius2(v.viewmatrix);
   for (int i = 0; i < v.P; i++) {
@@ -27,6 +27,7 @@ int s360h_project(const S360View* view, const float* means, const float* cov, co
     xy[2 * i] = pr.px; xy[2 * i + 1] = pr.py;
     conic_op[4 * i] = pr.cA; conic_op[4 * i + 1] = pr.cB; conic_op[4 * i + 2] = pr.cC; conic_op[4 * i + 3] = pr.op;
     depth[i] = pr.sortkey;
+    if (half_extent) { half_extent[2 * i] = pr.hx; half_extent[2 * i + 1] = pr.hy; }
     float col[3] = {0.f, 0.f, 0.f};
     uint8_t cl = 0;
     if (pr.upstream_visible && shs) sh_to_rgb(v, shs + (size_t)i * v.M * 3, mx, my, mz, v.campos, col, cl);
