@@ -211,3 +211,29 @@ def test_tight_box_never_excludes_a_visible_pixel(harness, mode, H, W):
     inside_edge = (~outside) & ((np.abs(dx) > he[:, 0, None] - 1.5) | (np.abs(dy) > he[:, 1, None] - 1.5))
     small = (he[:, 0] < 55) & (he[:, 1] < 55)
     assert (np.where(inside_edge, alpha, 0).max(axis=1)[small] > 0.5 / 255.0).mean() > 0.9
+
+
+def test_frustum_reject_never_drops_a_visible_gaussian_on_cube_faces(harness):
+    """project_view rejects most (view, Gaussian) pairs with a cheap conservative bound before any covariance math (the
+    batched pass projects every Gaussian into six faces).  Large, elongated Gaussians straddling the frustum edges of all six
+    cube faces: radii and tile counts must still equal the oracle's, which has no such shortcut."""
+    from splatter360_b200 import camera, cubemap, synthetic
+    n, F = 6000, 64
+    sc = synthetic.random_cloud_scene(n, sh_degree=4, seed=19, ref_width=1024, depth_range=(0.3, 3.0))
+    cov = sc.covariances * (40.0 ** 2)
+    cov[::3] = cov[::3] * 25.0                                   # a third of them huge
+    faces = cubemap.cube_face_extrinsics(synthetic.target_pose(2))
+    K = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]])[None].repeat(6, 1, 1)
+    cam = camera.pinhole_camera(faces, K, torch.ones(6), torch.full((6,), 100.0))
+    seen = 0
+    for k in range(6):
+        case = dict(means=sc.means.contiguous(), cov6=synthetic.cov3x3_to_cov6(cov).contiguous(), opac=sc.opacities.contiguous(),
+                    shs=sc.harmonics.permute(0, 2, 1).contiguous(), H=F, W=F, mode="pinhole", sh_degree=4,
+                    view=cam.view_matrix[k].contiguous(), proj=cam.full_projection[k].contiguous(), campos=cam.campos[k].contiguous(),
+                    tanfovx=float(cam.tan_fov_x[k]), tanfovy=float(cam.tan_fov_y[k]), bg=torch.zeros(3))
+        o = run_oracle(case)
+        c = _project(harness, case)
+        assert np.array_equal(c["radii"], o["radii"]), k
+        assert np.array_equal(c["tiles_touched"], o["tiles_touched"]), k
+        seen += int((o["radii"] > 0).sum())
+    assert seen > n          # most Gaussians are seen by more than one face at this size
