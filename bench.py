@@ -295,7 +295,10 @@ def run_ours(args):
     # rank 0 at N=1; it does not enter `value`.
     cube6 = None
     if world == 1 and not args.no_cube6:
-        cube6 = cube6_run(dev, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), poses[Wm + K - 1])
+        try:
+            cube6 = cube6_run(dev, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), poses[Wm + K - 1])
+        except Exception as ex:   # a side measurement must never cost the headline line
+            cube6 = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank != 0:
         if world > 1:
