@@ -284,6 +284,10 @@ int s360_profile_enable(int on); /* returns the previous setting */
  * Synchronises on the recorded events.  ms / counts: host arrays of S360_NUM_STAGES, may be NULL. */
 int s360_profile_read(double* ms, uint64_t* counts, int reset);
 
+/* Work counters of the render kernels (host array of 16 uint64; see render.cu).  Only instrumented builds
+ * (-DS360_COUNTERS=1, tools/counters.py) count; the shipped library returns S360_ERR_UNSUPPORTED and zeros. */
+int s360_debug_counters(uint64_t* out /* host [16] */, int reset, void* stream);
+
 int s360_abi_version(void);
 const char* s360_error_string(int code);
 /* number of kernels launched by this library since load (for bench.py's gpu_launches). */

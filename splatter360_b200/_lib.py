@@ -26,7 +26,7 @@ EXPORTS = [
     "s360_multi_geom_bytes", "s360_multi_preprocess_scratch_bytes", "s360_multi_binning_scratch_bytes",
     "s360_multi_image_bytes", "s360_multi_backward_scratch_bytes",
     "s360_multi_forward_project", "s360_multi_forward_order", "s360_multi_forward_render", "s360_multi_backward",
-    "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward",
+    "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward", "s360_debug_counters",
 ]
 ABI_VERSION = 4
 MAX_VIEWS = 32
@@ -127,6 +127,8 @@ def load() -> ctypes.CDLL:
         getattr(lib, n).argtypes = [vp, vp] + [c_int32] * 6 + [vp, vp, vp]
     lib.s360_debug_unpack_pairs.restype = c_int
     lib.s360_debug_unpack_pairs.argtypes = [c_int32, c_int64] + [vp] * 5
+    lib.s360_debug_counters.restype = c_int
+    lib.s360_debug_counters.argtypes = [vp, c_int, vp]
     if lib.s360_abi_version() != ABI_VERSION:
         raise ImportError("libsplatter360.so ABI version mismatch")
     _lib = lib

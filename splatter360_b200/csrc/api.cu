@@ -170,6 +170,11 @@ int s360_profile_read(double* ms, uint64_t* counts, int reset) {
   return rc;
 }
 
+int s360_debug_counters(uint64_t* out, int reset, void* stream) {
+  if (!out) return S360_ERR_BAD_ARGUMENT;
+  return read_counters((unsigned long long*)out, reset, (cudaStream_t)stream);
+}
+
 uint64_t s360_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* s360_error_string(int code) {

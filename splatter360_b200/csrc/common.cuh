@@ -402,6 +402,8 @@ int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_
                            const float* dL_dcolor, const float* dL_ddepth /* [NV,H,W] or NULL */, int depth_mode,
                            float depth_near, float depth_far, float* acc, cudaStream_t st);
 
+int read_counters(unsigned long long* out, int reset, cudaStream_t st);   // render.cu, instrumented builds only
+
 constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator (9 used; a tenth for the depth channel)
 
 // Build switch (prepared, NOT yet measured -- DESIGN.md sec. 7): 1 = the render backward accumulates the moments of

@@ -72,6 +72,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 constexpr int NWARPS = RT / 32;
 
+// Instrumented build (-DS360_COUNTERS=1, tools/counters.py): how much of the evaluated work is useful.
+//   [0] fwd warp-chunks  [1] fwd (warp, instance) tests  [2] fwd survivors  [3] fwd survivors some pixel takes
+//   [4] fwd (pixel, instance) pairs taken   [5] fwd instances in the tile lists (range sizes)
+//   [8] bwd warp-chunks  [9] bwd tests      [10] bwd survivors   [11] bwd survivors some pixel takes   [12] bwd pairs taken
+#ifndef S360_COUNTERS
+#define S360_COUNTERS 0
+#endif
+#if S360_COUNTERS
+__device__ unsigned long long g_counters[16];
+#define S360_COUNT(var, x) var += (x)
+#else
+#define S360_COUNT(var, x)
+#endif
+int read_counters(unsigned long long* out, int reset, cudaStream_t st) {
+#if S360_COUNTERS
+  cudaStreamSynchronize(st);
+  int rc = (int)cudaMemcpyFromSymbol(out, g_counters, sizeof(unsigned long long) * 16);
+  if (!rc && reset) { unsigned long long z[16] = {0}; rc = (int)cudaMemcpyToSymbol(g_counters, z, sizeof(z)); }
+  return rc;
+#else
+  (void)reset; (void)st;
+  for (int i = 0; i < 16; i++) out[i] = 0;
+  return S360_ERR_UNSUPPORTED;
+#endif
+}
+
 // Warp-autonomous streaming of a tile's instance list: lane j of every warp gathers instance
 // (chunk*32 + j) itself (the four warps of a tile hit the same lines in L1); the ids of the next two chunks are
 // always in flight (S360_*_PREFETCH=1 additionally keeps the next chunk's records in registers), and no CTA-wide
@@ -131,10 +157,14 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   load_records(nx, rec, range.x + lane < range.y);
 #endif
   uint32_t gid2 = (range.x + 32 + lane < range.y) ? point_list[range.x + 32 + lane] : 0u;
+#if S360_COUNTERS
+  unsigned long long c_chunks = 0, c_tests = 0, c_surv = 0, c_hit = 0, c_pairs = 0;
+#endif
 
   for (uint32_t base = range.x; base < range.y; base += 32) {
     if (__all_sync(0xffffffffu, amin0 == INF && amin1 == INF)) break;
     const bool valid = base + lane < range.y;
+    S360_COUNT(c_chunks, 1); S360_COUNT(c_tests, __popc(__ballot_sync(0xffffffffu, valid)));
 #if !S360_FWD_PREFETCH
     load_records(nx, rec, valid);
 #endif
@@ -165,6 +195,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     const bool any_wide = MODE == S360_MODE_ERP && __any_sync(0xffffffffu, hit && huge);
     __syncwarp();
     const int nsv = __popc(mask);
+    S360_COUNT(c_surv, nsv);
     const float4* sv = &s_sv[warp][0][0];
     auto composite = [&](auto wide_tag) {
       constexpr bool WIDE = decltype(wide_tag)::value;
@@ -194,11 +225,22 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
         const uint32_t pos = __float_as_uint(g.w);
         if (nae.x < 0.f) last0 = pos;
         if (nae.y < 0.f) last1 = pos;
+#if S360_COUNTERS
+        { const unsigned b0 = __ballot_sync(0xffffffffu, nae.x < 0.f), b1 = __ballot_sync(0xffffffffu, nae.y < 0.f);
+          c_hit += (b0 | b1) ? 1 : 0; c_pairs += __popc(b0) + __popc(b1); }
+#endif
       }
     };
     if (any_wide) composite(std::true_type{}); else composite(std::false_type{});
     __syncwarp();
   }
+#if S360_COUNTERS
+  if (lane == 0) {
+    atomicAdd(&g_counters[0], c_chunks); atomicAdd(&g_counters[1], c_tests); atomicAdd(&g_counters[2], c_surv);
+    atomicAdd(&g_counters[3], c_hit); atomicAdd(&g_counters[4], c_pairs);
+    if (warp == 0) atomicAdd(&g_counters[5], (unsigned long long)(range.y - range.x));
+  }
+#endif
   // how far this warp had to walk: the backward pass replays at most that much of the tile's list
   {
     const uint32_t walked = __reduce_max_sync(0xffffffffu, max(last0, last1));
@@ -347,9 +389,13 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
 #endif
     if (nchunks > 1) gid2 = point_list[range.x + p - 32u];
   }
+#if S360_COUNTERS
+  unsigned long long c_chunks = 0, c_tests = 0, c_surv = 0, c_hit = 0, c_pairs = 0;
+#endif
   for (int ci = nchunks - 1; ci >= 0; --ci) {
     const uint32_t pos0 = (uint32_t)ci * 32u;
     const bool valid = pos0 + lane < todo;
+    S360_COUNT(c_chunks, 1); S360_COUNT(c_tests, __popc(__ballot_sync(0xffffffffu, valid)));
 #if !S360_BWD_PREFETCH
     load_records(nx, rec, valid);
 #endif
@@ -378,6 +424,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     const bool any_wide = MODE == S360_MODE_ERP && __any_sync(0xffffffffu, hit && huge);
     __syncwarp();
     const int nsv = __popc(mask);
+    S360_COUNT(c_surv, nsv);
     const float4* sv = &s_sv[warp][0][0];
     auto replay = [&](auto wide_tag) {
     constexpr bool WIDE = decltype(wide_tag)::value;
@@ -397,6 +444,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       const bool ok0 = (pos < S.lastc0) && (p.x <= 0.f) && (-nal0 >= ALPHA_MIN);
       const bool ok1 = (pos < S.lastc1) && (p.y <= 0.f) && (-nal1 >= ALPHA_MIN);
       if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+      S360_COUNT(c_hit, 1); S360_COUNT(c_pairs, __popc(__ballot_sync(0xffffffffu, ok0)) + __popc(__ballot_sync(0xffffffffu, ok1)));
       const float4 c = sv[32 + k];
       // A pixel that does not take this instance runs the same recurrences with alpha = 0: T and B stay as they are.
       const float2 nae = make_float2(ok0 ? nal0 : 0.f, ok1 ? nal1 : 0.f);                  // -alpha or 0
@@ -452,6 +500,12 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     if (any_wide) replay(std::true_type{}); else replay(std::false_type{});
     __syncwarp();
   }
+#if S360_COUNTERS
+  if (lane == 0) {
+    atomicAdd(&g_counters[8], c_chunks); atomicAdd(&g_counters[9], c_tests); atomicAdd(&g_counters[10], c_surv);
+    atomicAdd(&g_counters[11], c_hit); atomicAdd(&g_counters[12], c_pairs);
+  }
+#endif
 }
 
 int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_t* point_list, ImageState img,
