@@ -28,8 +28,9 @@
  *   s360_forward_preprocess   K1 project/cull/cov2D/SH  -> geom state, radii, depth-ordered ids,
  *                             per-Gaussian instance offsets, *num_rendered (device u32)
  *   (caller sizes the instance buffers: read *num_rendered, or pass a capacity it trusts)
- *   s360_forward_render       emit (tile,id) instances in depth order -> stable radix sort by tile
- *                             -> tile ranges -> front-to-back compositing
+ *   s360_forward_render       stable bucketing of the depth-ordered instances by tile (count matrix over
+ *                             (chunk of the depth order, tile) -> column scan -> ranked scatter; or, for very
+ *                             large tile counts, emit + stable radix sort) -> tile ranges -> front-to-back compositing
  *   s360_backward             per-tile back-to-front gradient pass + fused per-Gaussian backward
  *                             (optionally also the gradient of the fused depth channel)
  *
@@ -46,7 +47,7 @@
 extern "C" {
 #endif
 
-#define S360_ABI_VERSION 4
+#define S360_ABI_VERSION 5
 
 #define S360_MODE_PINHOLE 0 /* upstream semantics                     */
 #define S360_MODE_ERP 1     /* native equirectangular splatting      */
@@ -105,8 +106,8 @@ typedef struct S360Counters {
 size_t s360_geom_bytes(int32_t P);
 /* transient scratch of s360_forward_preprocess (depth sort + scan). */
 size_t s360_preprocess_scratch_bytes(int32_t P);
-/* transient scratch of s360_forward_render for `instance_capacity` instances. */
-size_t s360_binning_scratch_bytes(int64_t instance_capacity, int32_t image_height, int32_t image_width);
+/* transient scratch of s360_forward_render for P Gaussians and `instance_capacity` instances. */
+size_t s360_binning_scratch_bytes(int32_t P, int64_t instance_capacity, int32_t image_height, int32_t image_width);
 /* image state kept from forward to backward (final transmittance, contributor count, tile ranges). */
 size_t s360_image_bytes(int32_t image_height, int32_t image_width);
 /* transient scratch of s360_backward (per-Gaussian screen-space gradient accumulators). */
@@ -124,7 +125,9 @@ int s360_forward_preprocess(
     void* geom,                  /* s360_geom_bytes(P)                                         */
     int32_t* radii,              /* [P] out                                                    */
     uint32_t* depth_order,       /* [P] out: Gaussian ids sorted by (depth, id)                */
-    uint32_t* inst_offsets,      /* [P] out: exclusive scan of tiles touched, in depth order   */
+    uint32_t* inst_offsets,      /* [P] scratch handed on to s360_forward_render (exclusive scan of tiles touched in
+                                    depth order when the emit + radix-sort binning path is taken; untouched by the
+                                    matrix binning path, which needs no per-Gaussian offsets)                 */
     S360Counters* counters,      /* out (device)                                               */
     void* scratch,               /* s360_preprocess_scratch_bytes(P)                           */
     void* stream);
@@ -153,7 +156,7 @@ int s360_forward_render(
     float* out_depth,            /* [H,W] out or NULL: fused depth channel (gradient: s360_backward's dL_ddepth) */
     int32_t depth_mode,          /* S360_DEPTH_*                                               */
     float depth_near, float depth_far, /* unscaled near / far for relative_disparity and log   */
-    void* scratch,               /* s360_binning_scratch_bytes(instance_capacity,H,W)          */
+    void* scratch,               /* s360_binning_scratch_bytes(P,instance_capacity,H,W)        */
     void* stream);
 
 /* ---- backward (replaces upstream _C.rasterize_gaussians_backward) ---------------------------- */
@@ -193,7 +196,8 @@ int s360_backward(
 #define S360_MAX_VIEWS 32
 size_t s360_multi_geom_bytes(int32_t P, int64_t pair_capacity);
 size_t s360_multi_preprocess_scratch_bytes(int32_t P, int64_t pair_capacity);
-size_t s360_multi_binning_scratch_bytes(int64_t instance_capacity, int32_t V, int32_t image_height, int32_t image_width);
+size_t s360_multi_binning_scratch_bytes(int64_t pair_capacity, int64_t instance_capacity, int32_t V, int32_t image_height,
+                                        int32_t image_width);
 size_t s360_multi_image_bytes(int32_t V, int32_t image_height, int32_t image_width);
 size_t s360_multi_backward_scratch_bytes(int64_t pair_capacity);
 /* K1 for all views -> pair geometry, radii [V,P] (may be NULL), counters (num_rendered final, num_visible = pairs) */

@@ -28,7 +28,7 @@ EXPORTS = [
     "s360_multi_forward_project", "s360_multi_forward_order", "s360_multi_forward_render", "s360_multi_backward",
     "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward", "s360_debug_counters",
 ]
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_VIEWS = 32
 
 STAGES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
@@ -76,7 +76,7 @@ def load() -> ctypes.CDLL:
         getattr(lib, n).restype = c_size_t
         getattr(lib, n).argtypes = [c_int32]
     lib.s360_binning_scratch_bytes.restype = c_size_t
-    lib.s360_binning_scratch_bytes.argtypes = [c_int64, c_int32, c_int32]
+    lib.s360_binning_scratch_bytes.argtypes = [c_int32, c_int64, c_int32, c_int32]
     lib.s360_image_bytes.restype = c_size_t
     lib.s360_image_bytes.argtypes = [c_int32, c_int32]
     vp = c_void_p
@@ -108,7 +108,7 @@ def load() -> ctypes.CDLL:
     lib.s360_multi_preprocess_scratch_bytes.restype = c_size_t
     lib.s360_multi_preprocess_scratch_bytes.argtypes = [c_int32, c_int64]
     lib.s360_multi_binning_scratch_bytes.restype = c_size_t
-    lib.s360_multi_binning_scratch_bytes.argtypes = [c_int64, c_int32, c_int32, c_int32]
+    lib.s360_multi_binning_scratch_bytes.argtypes = [c_int64, c_int64, c_int32, c_int32, c_int32]
     lib.s360_multi_image_bytes.restype = c_size_t
     lib.s360_multi_image_bytes.argtypes = [c_int32, c_int32, c_int32]
     lib.s360_multi_backward_scratch_bytes.restype = c_size_t

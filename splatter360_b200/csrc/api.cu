@@ -1,5 +1,6 @@
 // api.cu -- extern "C" entry points of libsplatter360.so (see include/splatter360.h).
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -61,6 +62,15 @@ struct BinScratch {
   uint32_t *keys_a, *keys_b, *vals_b, *tile_count;
   void* radix;
 };
+// S360_FORCE_RADIX_BINNING=1 (environment, read once): always take the emit + radix-sort path (tests, A/B)
+static bool force_radix() {
+  static const bool f = [] { const char* e = getenv("S360_FORCE_RADIX_BINNING"); return e && e[0] == '1'; }();
+  return f;
+}
+static int64_t tiles_of(int H, int W, int V = 1) { return (int64_t)V * ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE); }
+// n_items: Gaussians (or pair capacity) the binning stage walks
+static bool use_matrix(int64_t n_items, int H, int W, int V = 1) { return !force_radix() && matrix_binning_ok(n_items, tiles_of(H, W, V)); }
+
 static size_t bin_scratch_carve(void* buf, int64_t cap, int H, int W, BinScratch* out, int V = 1) {
   char* p = (char*)buf;
   const size_t arr = align_up((size_t)(cap > 0 ? cap : 1) * 4, 256);
@@ -99,12 +109,14 @@ static bool batch_ok(const S360View* v, int V, int64_t pair_capacity) {
 // ---- stage bodies shared by the single-view and the batched entry points -----------------------------------
 // n_items entries of the (Gaussian- or pair-indexed) geometry state; n_dev optionally overrides the count on device
 static int order_impl(int64_t n_items, const uint32_t* n_dev, GeomState g, const PreScratch& s, uint32_t* depth_order,
-                      uint32_t* inst_offsets, S360Counters* counters, cudaStream_t st) {
+                      uint32_t* inst_offsets, S360Counters* counters, bool matrix, cudaStream_t st) {
   int rc, in_b = 0;
   { StageTimer t(S360_STAGE_DEPTH_SORT, st);
-    // the last of the four passes writes the sorted ids straight into depth_order
-    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, n_items, n_dev, 32, s.radix, st, &in_b, false, depth_order);
+    // the digit histograms were accumulated by K1 (hist_ready); the last of the four passes writes the sorted ids
+    // straight into depth_order
+    rc = radix_sort_pairs(s.keys_a, s.ids_a, s.keys_b, s.ids_b, n_items, n_dev, 32, s.radix, st, &in_b, true, depth_order);
     if (rc) return rc; }
+  if (matrix) return 0;   // matrix binning needs no per-Gaussian offsets; K1 already counted the instances
   StageTimer t(S360_STAGE_SCAN, st);
   return launch_scan_offsets(n_items, n_dev, g, depth_order, inst_offsets, counters, s.block_sums, st);
 }
@@ -117,6 +129,26 @@ static int render_impl(const S360View* view, int V, int64_t n_items, const uint3
   const int H = view->image_height, W = view->image_width;
   if (depth_mode < S360_DEPTH_DEPTH || depth_mode > S360_DEPTH_LOG) return S360_ERR_BAD_ARGUMENT;
   ImageState img = carve_image(image_state, H, W, V);
+  if (use_matrix(n_items, H, W, V)) {
+    // matrix binning (binning.cu): count per (chunk, tile) -> column scan -> tile ranges -> ranked scatter
+    int rc;
+    { StageTimer t(S360_STAGE_EMIT, st);
+      rc = launch_mb_count(*view, V, n_items, n_dev, g, depth_order, scratch, st); }
+    if (rc) return rc;
+    { StageTimer t(S360_STAGE_SCAN, st);
+      rc = launch_mb_colscan(*view, V, n_items, n_dev, scratch, st); }
+    if (rc) return rc;
+    { StageTimer t(S360_STAGE_TILE_RANGES, st);
+      rc = launch_tile_scan(*view, V, mb_tile_totals(scratch, n_items, (int)tiles_of(H, W, V)), 1, instance_capacity,
+                            img.ranges, img.order, img.work, nullptr, 0, st); }
+    if (rc) return rc;
+    { StageTimer t(S360_STAGE_TILE_SORT, st);
+      rc = launch_mb_scatter(*view, V, n_items, n_dev, g, depth_order, counters, instance_capacity, point_list, img.ranges,
+                             scratch, st); }
+    if (rc) return rc;
+    StageTimer t(S360_STAGE_RENDER_FWD, st);
+    return launch_render_forward(*view, V, g, point_list, img, out_color, out_depth, depth_mode, depth_near, depth_far, st);
+  }
   BinScratch s;
   bin_scratch_carve(scratch, instance_capacity, H, W, &s, V);
   const int nbits = tile_bits(H, W, V);
@@ -133,7 +165,8 @@ static int render_impl(const S360View* view, int V, int64_t n_items, const uint3
     rc = launch_emit(*view, V, n_items, n_dev, g, depth_order, inst_offsets, counters, instance_capacity, k0, v0, s.tile_count, st); }
   if (rc) return rc;
   { StageTimer t(S360_STAGE_TILE_RANGES, st);
-    rc = launch_tile_scan(*view, V, s.tile_count, img.ranges, img.order, img.work, hist, passes > 0 ? passes : 1, st); }
+    rc = launch_tile_scan(*view, V, s.tile_count, tile_hist_copies(), instance_capacity, img.ranges, img.order, img.work, hist,
+                          passes > 0 ? passes : 1, st); }
   if (rc) return rc;
   int in_b = 0;
   { StageTimer t(S360_STAGE_TILE_SORT, st);
@@ -189,7 +222,10 @@ const char* s360_error_string(int code) {
 
 size_t s360_geom_bytes(int32_t P) { return geom_bytes(P > 0 ? P : 1); }
 size_t s360_preprocess_scratch_bytes(int32_t P) { return pre_scratch_carve(nullptr, P, nullptr); }
-size_t s360_binning_scratch_bytes(int64_t cap, int32_t H, int32_t W) { return bin_scratch_carve(nullptr, cap, H, W, nullptr); }
+size_t s360_binning_scratch_bytes(int32_t P, int64_t cap, int32_t H, int32_t W) {
+  if (use_matrix(P, H, W)) return matrix_scratch_bytes(P, tiles_of(H, W));
+  return bin_scratch_carve(nullptr, cap, H, W, nullptr);
+}
 size_t s360_image_bytes(int32_t H, int32_t W) { return image_bytes(H, W); }
 size_t s360_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float), 256); }
 
@@ -210,7 +246,8 @@ int s360_forward_project(const S360View* view, const float* means3D, const float
   PreScratch s;
   pre_scratch_carve(scratch, P, &s);
   StageTimer t(S360_STAGE_PREPROCESS, st);
-  return launch_preprocess(*view, means3D, cov3D, opacities, shs, colors_precomp, g, radii, s.keys_a, s.ids_a, counters, st);
+  uint32_t* hist = radix_prepare_hist(s.radix, P, 32, st);   // K1 accumulates the depth-sort digit histograms
+  return launch_preprocess(*view, means3D, cov3D, opacities, shs, colors_precomp, g, radii, s.keys_a, s.ids_a, counters, hist, st);
 }
 
 int s360_forward_order(const S360View* view, const void* geom, uint32_t* depth_order, uint32_t* inst_offsets,
@@ -222,7 +259,7 @@ int s360_forward_order(const S360View* view, const void* geom, uint32_t* depth_o
   GeomState g = carve_geom(const_cast<void*>(geom), P > 0 ? P : 1);
   PreScratch s;
   pre_scratch_carve(scratch, P, &s);
-  return order_impl(P, nullptr, g, s, depth_order, inst_offsets, counters, st);
+  return order_impl(P, nullptr, g, s, depth_order, inst_offsets, counters, use_matrix(P, view->image_height, view->image_width), st);
 }
 
 int s360_forward_preprocess(const S360View* view, const float* means3D, const float* cov3D, const float* opacities,
@@ -283,7 +320,10 @@ int s360_backward(const S360View* view, const float* means3D, const float* cov3D
 // ---- batched multi-view path ---------------------------------------------------------------------------------
 size_t s360_multi_geom_bytes(int32_t P, int64_t pair_capacity) { return geom_multi_bytes(P > 0 ? P : 1, pair_capacity > 0 ? pair_capacity : 1); }
 size_t s360_multi_preprocess_scratch_bytes(int32_t P, int64_t pair_capacity) { return pre_scratch_carve(nullptr, pair_capacity, nullptr, P > 0 ? P : 1); }
-size_t s360_multi_binning_scratch_bytes(int64_t cap, int32_t V, int32_t H, int32_t W) { return bin_scratch_carve(nullptr, cap, H, W, nullptr, V > 0 ? V : 1); }
+size_t s360_multi_binning_scratch_bytes(int64_t pair_capacity, int64_t cap, int32_t V, int32_t H, int32_t W) {
+  if (use_matrix(pair_capacity, H, W, V > 0 ? V : 1)) return matrix_scratch_bytes(pair_capacity, tiles_of(H, W, V > 0 ? V : 1));
+  return bin_scratch_carve(nullptr, cap, H, W, nullptr, V > 0 ? V : 1);
+}
 size_t s360_multi_image_bytes(int32_t V, int32_t H, int32_t W) { return image_bytes(H, W, V > 0 ? V : 1); }
 size_t s360_multi_backward_scratch_bytes(int64_t pair_capacity) { return align_up((size_t)(pair_capacity > 0 ? pair_capacity : 1) * ACC_STRIDE * sizeof(float), 256); }
 
@@ -307,8 +347,9 @@ int s360_multi_forward_project(const S360View* view, int32_t V, int64_t pair_cap
   PreScratch s;
   pre_scratch_carve(scratch, pair_capacity, &s, P > 0 ? P : 1);
   StageTimer t(S360_STAGE_PREPROCESS, st);
+  uint32_t* hist = radix_prepare_hist(s.radix, pair_capacity, 32, st);
   return launch_preprocess_multi(*view, V, pair_capacity, means3D, cov3D, opacities, shs, colors_precomp, g, ps, radii,
-                                 s.keys_a, s.ids_a, counters, s.k1_status, st);
+                                 s.keys_a, s.ids_a, counters, s.k1_status, hist, st);
 }
 
 int s360_multi_forward_order(const S360View* view, int32_t V, int64_t pair_capacity, const void* geom,
@@ -322,7 +363,8 @@ int s360_multi_forward_order(const S360View* view, int32_t V, int64_t pair_capac
   GeomState g = carve_geom_multi(const_cast<void*>(geom), P > 0 ? P : 1, pair_capacity > 0 ? pair_capacity : 1, &ps);
   PreScratch s;
   pre_scratch_carve(scratch, pair_capacity, &s, P > 0 ? P : 1);
-  return order_impl(pair_capacity, &counters->num_visible, g, s, depth_order, inst_offsets, counters, st);
+  return order_impl(pair_capacity, &counters->num_visible, g, s, depth_order, inst_offsets, counters,
+                    use_matrix(pair_capacity, view->image_height, view->image_width, V), st);
 }
 
 int s360_multi_forward_render(const S360View* view, int32_t V, int64_t pair_capacity, const void* geom,

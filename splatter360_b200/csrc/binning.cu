@@ -415,12 +415,289 @@ emit_instances_kernel(int P_cap, const uint32_t* __restrict__ n_dev, int gx, int
   if (overflow) atomicOr(&counters->overflow, 1u);
 }
 
+
+// ================================================================================================
+// Matrix binning: the stable "sort N instances by tile" step WITHOUT materialising (tile, id) keys.
+// The depth order is cut into chunks of MB_CHUNK Gaussians.  (1) mb_count_kernel: one CTA per chunk expands the
+// chunk's tile rectangles and counts instances per tile -> row [chunk][tile] of a count matrix.  (2) mb_colscan_kernel:
+// exclusive prefix along the chunk axis per tile (in place) + tile totals.  (3) tile_scan_kernel: tile totals -> ranges
+// + longest-first schedule.  (4) mb_scatter_kernel: every chunk expands its rectangles again, ranks each instance
+// among the chunk's earlier instances of the same tile (warp w owns a contiguous slice of the chunk: per-warp u16
+// counters, exclusive prefix over the warps, then in-order ranking with ballot-matched peers) and writes the Gaussian id
+// straight to  ranges[tile].x + prefix[chunk][tile] + rank.  Result: point_list sorted by (tile, depth, id), bit-identical
+// to emit + two stable radix passes, with 4 B written per instance instead of 8 B emitted + 2 x 16 B sorted, and no
+// scan of per-Gaussian offsets at all.  Used whenever tiles <= MB_MAX_TILES and the matrix stays small.
+constexpr int MB_CHUNK = 2048;
+constexpr int MB_MAX_TILES = 8192;
+
+bool matrix_binning_ok(int64_t n_items, int64_t tiles) {
+  if (tiles <= 0 || tiles > MB_MAX_TILES || n_items <= 0) return false;
+  const int64_t chunks = (n_items + MB_CHUNK - 1) / MB_CHUNK;
+  return chunks * tiles * 4 <= (256ll << 20);
+}
+size_t matrix_scratch_bytes(int64_t n_items, int64_t tiles) {
+  const int64_t chunks = (n_items + MB_CHUNK - 1) / MB_CHUNK;
+  return align_up((size_t)chunks * tiles * 4, 256) + align_up((size_t)tiles * 4, 256);
+}
+
+// tile id of the k-th cell (row-major) of a packed tile rectangle; erp wraps the column
+__device__ __forceinline__ uint32_t rect_tile(uint32_t rx, uint32_t ry, uint32_t k, int gx, int mode) {
+  const uint32_t nx = rx >> 16;
+  const uint32_t ky = k / nx, kx = k - ky * nx;
+  int tx = (int)(int16_t)(rx & 0xffffu) + (int)kx;
+  if (mode == S360_MODE_ERP) { tx %= gx; if (tx < 0) tx += gx; }
+  return ((ry & 0xffffu) + ky) * (uint32_t)gx + (uint32_t)tx;
+}
+
+// A warp expands the rectangles of 32 consecutive Gaussians of the depth order (lane j holds Gaussian j) into their
+// instances, 32 at a time, in order (Gaussian, then cell): f(tile, gid, valid) is called by all lanes in lock-step.
+// Balanced no matter how many tiles one Gaussian covers (pole-sized rectangles).
+template <class F>
+__device__ __forceinline__ void expand_group(uint32_t gid, uint2 r, uint32_t cnt, int lane, int gx, int mode, F&& f) {
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const uint32_t off = incl - cnt;
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+    const uint32_t pos = p0 + lane;
+    int lo = 0;   // last lane j with off_j <= pos (zero-count lanes share their successor's offset and lose the tie)
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const uint32_t v = __shfl_sync(0xffffffffu, off, (lo + s) & 31);
+      if (lo + s < 32 && v <= pos) lo += s;
+    }
+    const uint32_t o_off = __shfl_sync(0xffffffffu, off, lo);
+    const uint32_t o_rx = __shfl_sync(0xffffffffu, r.x, lo);
+    const uint32_t o_ry = __shfl_sync(0xffffffffu, r.y, lo);
+    const uint32_t o_gid = __shfl_sync(0xffffffffu, gid, lo);
+    const bool valid = pos < total;
+    const uint32_t tile = valid ? rect_tile(o_rx, o_ry, pos - o_off, gx, mode) : 0xffffffffu;
+    f(tile, o_gid, valid);
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+mb_count_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int ntiles, int mode,
+                const uint2* __restrict__ rect, const uint32_t* __restrict__ order, uint32_t* __restrict__ matrix) {
+  extern __shared__ uint32_t s_cnt[];   // [ntiles]
+  constexpr int ROUNDS = MB_CHUNK / (NW * 32);
+  const int n = (int)effective_n(n_cap, n_dev);
+  const int base = (int)blockIdx.x * MB_CHUNK;
+  if (base >= n) return;   // rows of empty chunks are never read (the column scan stops at the same bound)
+  for (int t = threadIdx.x; t < ntiles; t += NW * 32) s_cnt[t] = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t gid[ROUNDS];
+  uint2 rc[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
+    gid[r] = i < n ? order[i] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
+    rc[r] = i < n ? rect[gid[r]] : make_uint2(0u, 0u);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++)
+    expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
+                 [&](uint32_t tile, uint32_t, bool valid) { if (valid) atomicAdd(&s_cnt[tile], 1u); });
+  __syncthreads();
+  uint32_t* row = matrix + (size_t)blockIdx.x * ntiles;
+  for (int t = threadIdx.x; t < ntiles; t += NW * 32) row[t] = s_cnt[t];
+}
+
+// exclusive prefix over the chunks for every tile (in place) + instances per tile.  Block = 32 tiles x 32 chunk segments.
+__global__ void __launch_bounds__(1024)
+mb_colscan_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int ntiles, uint32_t* matrix, uint32_t* __restrict__ tile_total) {
+  __shared__ uint32_t s_seg[32][33];
+  const int n = (int)effective_n(n_cap, n_dev);
+  const int n_chunks = (n + MB_CHUNK - 1) / MB_CHUNK;
+  const int tx = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int t = (int)blockIdx.x * 32 + tx;
+  const int seg_len = (n_chunks + 31) / 32;
+  const int c0 = min(seg * seg_len, n_chunks), c1 = min(c0 + seg_len, n_chunks);
+  uint32_t sum = 0;
+  if (t < ntiles) {
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = matrix[(size_t)(c + k) * ntiles + t];
+#pragma unroll
+      for (int k = 0; k < 8; k++) sum += v[k];
+    }
+    for (; c < c1; c++) sum += matrix[(size_t)c * ntiles + t];
+  }
+  s_seg[seg][tx] = sum;
+  __syncthreads();
+  if (seg == 0) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) { const uint32_t v = s_seg[k][tx]; s_seg[k][tx] = run; run += v; }
+    if (t < ntiles) tile_total[t] = run;
+  }
+  __syncthreads();
+  uint32_t run = s_seg[seg][tx];
+  if (t < ntiles) {
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = matrix[(size_t)(c + k) * ntiles + t];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { matrix[(size_t)(c + k) * ntiles + t] = run; run += v[k]; }
+    }
+    for (; c < c1; c++) { const uint32_t v = matrix[(size_t)c * ntiles + t]; matrix[(size_t)c * ntiles + t] = run; run += v; }
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int ntiles, int tbits, int mode,
+                  const uint2* __restrict__ rect, const uint32_t* __restrict__ order, const uint32_t* __restrict__ prefix,
+                  const uint2* __restrict__ ranges, int64_t capacity, uint32_t* __restrict__ point_list,
+                  S360Counters* counters) {
+  extern __shared__ uint32_t s_mem[];
+  constexpr int ROUNDS = MB_CHUNK / (NW * 32);
+  const int half = (ntiles + 1) >> 1;            // u16 counters, two per word
+  uint32_t* s_base = s_mem;                      // [ntiles]  first slot of this chunk's instances of the tile
+  uint32_t* s_cnt32 = s_mem + ntiles;            // [NW][half] per-warp counters -> exclusive prefixes over the warps
+  const int n = (int)effective_n(n_cap, n_dev);
+  const int base = (int)blockIdx.x * MB_CHUNK;
+  if (base >= n) return;
+  for (int j = threadIdx.x; j < NW * half; j += NW * 32) s_cnt32[j] = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t gid[ROUNDS];
+  uint2 rc[ROUNDS];
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
+    gid[r] = i < n ? order[i] : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++) {
+    const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
+    rc[r] = i < n ? rect[gid[r]] : make_uint2(0u, 0u);
+  }
+  {
+    const uint32_t* prow = prefix + (size_t)blockIdx.x * ntiles;
+    for (int t = threadIdx.x; t < ntiles; t += NW * 32) s_base[t] = ranges[t].x + prow[t];
+  }
+  __syncthreads();
+  // pass 1: instances per (warp, tile); packed u16 pairs take native 32-bit shared-memory adds
+  uint32_t* my32 = s_cnt32 + warp * half;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++)
+    expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
+                 [&](uint32_t tile, uint32_t, bool valid) { if (valid) atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
+  __syncthreads();
+  // exclusive prefix over the warps, both halves of a word at once (a chunk has at most MB_CHUNK instances per tile)
+  for (int j = threadIdx.x; j < half; j += NW * 32) {
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { const uint32_t c = s_cnt32[w * half + j]; s_cnt32[w * half + j] = run; run += c; }
+  }
+  __syncthreads();
+  // pass 2: in-order ranking.  Lanes of one batch that hit the same tile are matched with one ballot per tile-id bit;
+  // the lowest of them advances the warp's counter of that tile by the size of the group.
+  unsigned short* my16 = reinterpret_cast<unsigned short*>(my32);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  bool overflow = false;
+#pragma unroll
+  for (int r = 0; r < ROUNDS; r++)
+    expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode, [&](uint32_t tile, uint32_t g, bool valid) {
+      unsigned peers = __ballot_sync(0xffffffffu, valid);
+      for (int b = 0; b < tbits; b++) {
+        const bool bit = (tile >> b) & 1u;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+      }
+      if (!valid) peers = 1u << lane;
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (valid && lane == leader) {
+        old = my16[tile];
+        my16[tile] = (unsigned short)(old + (uint32_t)__popc(peers));
+      }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      __syncwarp();
+      if (valid) {
+        const uint32_t dst = s_base[tile] + old + (uint32_t)__popc(peers & lt_mask);
+        if ((int64_t)dst < capacity) point_list[dst] = g; else overflow = true;
+      }
+    });
+  if (overflow) atomicOr(&counters->overflow, 1u);
+}
+
+static int mb_tile_bits(int ntiles) { int b = 0; while ((1 << b) < ntiles) b++; return b; }
+
+// scratch: [matrix chunks x tiles][tile totals]; the three launchers below run in this order with the tile scan
+// (launch_tile_scan with copies = 1 on mb_tile_totals) between the column scan and the scatter
+uint32_t* mb_tile_totals(void* scratch, int64_t n_items, int ntiles) {
+  const int64_t chunks = (n_items + MB_CHUNK - 1) / MB_CHUNK;
+  return (uint32_t*)((char*)scratch + align_up((size_t)chunks * ntiles * 4, 256));
+}
+
+int launch_mb_count(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                    const uint32_t* depth_order, void* scratch, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
+  const int ntiles = gx * gy;
+  const int chunks = (int)((n_items + MB_CHUNK - 1) / MB_CHUNK);
+  if (chunks == 0) return 0;
+  mb_count_kernel<8><<<chunks, 256, (size_t)ntiles * 4, st>>>((int)n_items, n_dev, gx, ntiles, v.mode, g.rect, depth_order,
+                                                              (uint32_t*)scratch);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_mb_colscan(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, void* scratch, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
+  const int ntiles = gx * gy;
+  mb_colscan_kernel<<<(ntiles + 31) / 32, 1024, 0, st>>>((int)n_items, n_dev, ntiles, (uint32_t*)scratch,
+                                                         mb_tile_totals(scratch, n_items, ntiles));
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int launch_mb_scatter(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                      const uint32_t* depth_order, S360Counters* counters, int64_t capacity, uint32_t* point_list,
+                      const uint2* ranges, void* scratch, cudaStream_t st) {
+  const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
+  const int ntiles = gx * gy;
+  const int chunks = (int)((n_items + MB_CHUNK - 1) / MB_CHUNK);
+  if (chunks == 0) return 0;
+  // 8 warps per chunk up to 4096 tiles, 4 warps above: shared memory per CTA stays <= 96 KB (two CTAs per SM)
+  const bool wide = ntiles > 4096;
+  const size_t smem = (size_t)ntiles * 4 + (size_t)(wide ? 4 : 8) * ((ntiles + 1) / 2) * 4;
+  const uint32_t* prefix = (const uint32_t*)scratch;
+  if (wide) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mb_scatter_kernel<4><<<chunks, 128, smem, st>>>((int)n_items, n_dev, gx, ntiles, mb_tile_bits(ntiles), v.mode, g.rect,
+                                                    depth_order, prefix, ranges, capacity, point_list, counters);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mb_scatter_kernel<8><<<chunks, 256, smem, st>>>((int)n_items, n_dev, gx, ntiles, mb_tile_bits(ntiles), v.mode, g.rect,
+                                                    depth_order, prefix, ranges, capacity, point_list, counters);
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
 int tile_hist_copies() { return TILE_HIST_COPIES; }
 
 // One block: exclusive scan of the per-tile instance counts -> tile ranges, plus the digit histograms of
 // the (up to two) tile-sort passes, which are just partial sums of the same counts.
+// copies: replicated histograms to sum (TILE_HIST_COPIES after the emission kernel, 1 after the matrix column scan);
+// capacity: ranges are clipped to the instances that were actually stored (overflow of a caller-chosen capacity).
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, int copies, uint32_t capacity, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ order, uint32_t* __restrict__ work, uint32_t* __restrict__ hist, int npasses) {
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
@@ -435,8 +712,7 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __r
     const int i = base + threadIdx.x;
     uint32_t x = 0;
     if (i < ntiles) {
-#pragma unroll
-      for (int c = 0; c < TILE_HIST_COPIES; c++) x += tile_count[(size_t)c * ntiles + i];
+      for (int c = 0; c < copies; c++) x += tile_count[(size_t)c * ntiles + i];
     }
     uint32_t incl = x;
 #pragma unroll
@@ -451,7 +727,7 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __r
     const uint32_t carry = s_carry;
     if (i < ntiles) {
       const uint32_t start = carry + woff + incl - x;
-      ranges[i] = x ? make_uint2(start, start + x) : make_uint2(0u, 0u);
+      ranges[i] = x ? make_uint2(min(start, capacity), min(start + x, capacity)) : make_uint2(0u, 0u);
       atomicAdd(&s_bucket[1023u - min(x >> 5, 1023u)], 1u);   // bucket 0 = heaviest
       if (x) {
         atomicAdd(&s_hist[0][i & 0xff], x);
@@ -463,7 +739,8 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __r
     if (threadIdx.x == 1023) s_carry = carry + woff + incl;
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < npasses * RS_BINS; i += 1024) hist[i] = (&s_hist[0][0])[i];
+  if (hist != nullptr)
+    for (int i = threadIdx.x; i < npasses * RS_BINS; i += 1024) hist[i] = (&s_hist[0][0])[i];
   // exclusive scan of the 1024 buckets (one per thread), then every tile claims a slot in its bucket
   {
     const uint32_t x = s_bucket[threadIdx.x];
@@ -482,8 +759,7 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, uint2* __r
     __syncthreads();
     for (int i = threadIdx.x; i < ntiles; i += 1024) {
       uint32_t c = 0;
-#pragma unroll
-      for (int k = 0; k < TILE_HIST_COPIES; k++) c += tile_count[(size_t)k * ntiles + i];
+      for (int k = 0; k < copies; k++) c += tile_count[(size_t)k * ntiles + i];
       const uint32_t pos = atomicAdd(&s_bucket[1023u - min(c >> 5, 1023u)], 1u);
       order[pos] = (uint32_t)i;
       work[i] = 0u;
@@ -540,10 +816,11 @@ int launch_emit(const S360View& v, int NV, int64_t n_items, const uint32_t* n_de
   return (int)cudaGetLastError();
 }
 
-int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, uint2* ranges, uint32_t* order,
-                     uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st) {
+int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, int copies, int64_t capacity, uint2* ranges,
+                     uint32_t* order, uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st) {
   const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
-  tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, ranges, order, work, hist, npasses);
+  const uint32_t cap = (uint32_t)(capacity < 0xffffffffll ? capacity : 0xffffffffll);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, copies, cap, ranges, order, work, hist, npasses);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -355,7 +355,7 @@ S360_HD void sh_basis_grad(int deg, float x, float y, float z, float* bx, float*
 // host-side launchers (defined in the .cu files, called from api.cu)
 int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
                       const float* shs, const float* colors, GeomState g, int32_t* radii,
-                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st);
+                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, uint32_t* hist, cudaStream_t st);
 int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* opac, const float* shs,
                                GeomState g, const int32_t* radii, const float* acc, float* d_means,
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
@@ -365,7 +365,7 @@ int launch_mark_visible(const S360View& v, const float* means, uint8_t* present,
 int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
                             const float* opac, const float* shs, const float* colors, GeomState g, PairState ps,
                             int32_t* radii, uint32_t* depth_keys, uint32_t* ids, S360Counters* counters,
-                            uint32_t* status, cudaStream_t st);
+                            uint32_t* status, uint32_t* hist, cudaStream_t st);
 int launch_zero_acc(float* acc, const uint32_t* n_dev, int64_t cap, cudaStream_t st);
 int launch_preprocess_multi_backward(const S360View& v, int NV, const float* means, const float* cov, const float* opac,
                                      const float* shs, GeomState g, PairState ps, const float* acc, float* d_means,
@@ -390,8 +390,19 @@ int launch_emit(const S360View& v, int NV, int64_t n_items, const uint32_t* n_de
                 const uint32_t* depth_order, const uint32_t* offsets, S360Counters* counters, int64_t capacity,
                 uint32_t* keys, uint32_t* vals, uint32_t* tile_count, cudaStream_t st);
 int tile_hist_copies();
-int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, uint2* ranges, uint32_t* order,
-                     uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st);
+int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, int copies, int64_t capacity, uint2* ranges,
+                     uint32_t* order, uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st);
+// matrix binning (binning.cu): depth order -> point_list sorted by (tile, depth, id) + tile ranges + schedule, without
+// materialising (tile, id) keys; usable when matrix_binning_ok(items, tiles)
+bool matrix_binning_ok(int64_t n_items, int64_t tiles);
+size_t matrix_scratch_bytes(int64_t n_items, int64_t tiles);
+uint32_t* mb_tile_totals(void* scratch, int64_t n_items, int ntiles);
+int launch_mb_count(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                    const uint32_t* depth_order, void* scratch, cudaStream_t st);
+int launch_mb_colscan(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, void* scratch, cudaStream_t st);
+int launch_mb_scatter(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
+                      const uint32_t* depth_order, S360Counters* counters, int64_t capacity, uint32_t* point_list,
+                      const uint2* ranges, void* scratch, cudaStream_t st);
 int launch_tile_order(const S360View& v, int NV, const uint32_t* work, uint32_t* order, cudaStream_t st);
 
 // out_color [NV,3,H,W], out_depth [NV,H,W], dL_dcolor [NV,3,H,W]

@@ -17,9 +17,15 @@ __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
                   const float* __restrict__ opac, const float* __restrict__ shs,
                   const float* __restrict__ colors, GeomState gs, int32_t* __restrict__ radii,
-                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, S360Counters* counters) {
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, S360Counters* counters,
+                  uint32_t* __restrict__ hist) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
   __shared__ uint64_t s_bar;
+  // digit histograms of the four depth-sort passes, accumulated here so that the sort needs no pass of its own over
+  // the keys (hist: [4][256] global counters, zeroed by the caller; may be NULL)
+  __shared__ uint32_t s_hist[4 * 256];
+  for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) s_hist[i] = 0;
+  __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = v.P;
   const int row = v.M * 3;                                   // floats per Gaussian
@@ -63,6 +69,10 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     gs.rect[idx] = rect;
     depth_keys[idx] = key;
     ids[idx] = (uint32_t)idx;
+    if (hist != nullptr) {
+#pragma unroll
+      for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * 256 + ((key >> (8 * p)) & 0xffu)], 1u);
+    }
   }
   // block totals -> one atomic each.  The instance total is known here already (the scan only orders it), which
   // lets the host size the instance buffers while the depth sort is still running.
@@ -80,6 +90,12 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     if (threadIdx.x == 0) {
       if (s_cnt[0]) atomicAdd(&counters->num_visible, s_cnt[0]);
       if (s_cnt[1]) atomicAdd(&counters->num_rendered, s_cnt[1]);
+    }
+    if (hist != nullptr) {   // the barriers above ordered every thread's shared-memory atomics before this read
+      for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+      }
     }
   }
 
@@ -114,17 +130,18 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
 
 int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
                       const float* shs, const float* colors, GeomState g, int32_t* radii,
-                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st) {
+                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, uint32_t* hist, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
   if (smem > 200 * 1024) return S360_ERR_UNSUPPORTED;
+  // opt in to the dynamic size whenever dynamic + static shared memory may pass the 48 KB default
   if (v.mode == S360_MODE_PINHOLE) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters, hist);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
+    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters, hist);
   }
   count_launch();
   return (int)cudaGetLastError();
@@ -260,7 +277,7 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
 #define S360_LAUNCH_K8(MODE_, DEPTH_) do { \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     preprocess_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
   if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_K8(S360_MODE_PINHOLE, true); else S360_LAUNCH_K8(S360_MODE_PINHOLE, false); }
   else { if (has_depth) S360_LAUNCH_K8(S360_MODE_ERP, true); else S360_LAUNCH_K8(S360_MODE_ERP, false); }
@@ -394,11 +411,13 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
                    const float* __restrict__ cov3D, const float* __restrict__ opac, const float* __restrict__ shs,
                    const float* __restrict__ colors, GeomState gs, PairState ps,
                    const uint32_t* __restrict__ block_base, uint32_t* __restrict__ depth_keys,
-                   uint32_t* __restrict__ ids) {
+                   uint32_t* __restrict__ ids, uint32_t* __restrict__ hist) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
   __shared__ uint64_t s_bar;
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
   __shared__ uint32_t s_w[PRE_THREADS / 32];
+  __shared__ uint32_t s_hist[4 * 256];   // digit histograms of the pair depth keys (see preprocess_kernel)
+  for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) s_hist[i] = 0;
   const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
   const int P = v.P;
   const int gy = (v.image_height + TILE - 1) / TILE;
@@ -446,7 +465,7 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
   uint32_t slot = block_base[blockIdx.x] + woff + incl - cnt;
   // every thread waits for the bulk copy: no thread may leave while the TMA still writes this CTA's shared memory
   if (shs && bulk_ok) mbar_wait(&s_bar, 0);
-  if (idx >= P) return;
+  if (idx < P) {
   ps.base[idx] = slot;
   uint32_t kept = mask;
   float col[3] = {0.f, 0.f, 0.f};
@@ -474,14 +493,26 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
     gs.clamped[slot] = pr.cl | clc;
     depth_keys[slot] = pr.key;
     ids[slot] = slot;
+    if (hist != nullptr) {
+#pragma unroll
+      for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * 256 + ((pr.key >> (8 * p)) & 0xffu)], 1u);
+    }
   }
   if (kept != mask) ps.mask[idx] = kept;
+  }
+  if (hist != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) {
+      const uint32_t c = s_hist[i];
+      if (c) atomicAdd(&hist[i], c);
+    }
+  }
 }
 
 int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
                             const float* opac, const float* shs, const float* colors, GeomState g, PairState ps,
                             int32_t* radii, uint32_t* depth_keys, uint32_t* ids, S360Counters* counters,
-                            uint32_t* status, cudaStream_t st) {
+                            uint32_t* status, uint32_t* hist, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
@@ -494,11 +525,11 @@ int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, co
     multi_count_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, NV, means, cov, opac, ps, radii, block_count, counters);
   multi_scan_kernel<<<1, 1024, 0, st>>>(grid, block_count, cap, ps, counters);
   if (v.mode == S360_MODE_PINHOLE) {
-    if (smem > 40 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    multi_write_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
+    if (smem > 32 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    multi_write_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids, hist);
   } else {
-    if (smem > 40 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    multi_write_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
+    if (smem > 32 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    multi_write_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids, hist);
   }
   count_launch(3);
   return (int)cudaGetLastError();

@@ -198,7 +198,7 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
                 N, nvis = int(host_counts[0].item()) & 0xFFFFFFFF, int(host_counts[2].item()) & 0xFFFFFFFF
         cap = max(N, 1)
         point_list = torch.empty(cap, dtype=torch.int32, device=device)
-        bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(cap, H, W), **u8)
+        bin_scratch = torch.empty(lib.s360_binning_scratch_bytes(P, cap, H, W), **u8)
         image_state = torch.empty(lib.s360_image_bytes(H, W), **u8)
         color = torch.empty((3, H, W), dtype=torch.float32, device=device)
         depth = None
@@ -355,7 +355,7 @@ def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, 
                 return forward_views_raw(settings, means3D, cov, opacities, shs, colors, want_radii, npairs)
         cap = max(N, 1)
         point_list = torch.empty(cap, **i32)
-        bin_scratch = torch.empty(lib.s360_multi_binning_scratch_bytes(cap, V, H, W), **u8)
+        bin_scratch = torch.empty(lib.s360_multi_binning_scratch_bytes(pcap, cap, V, H, W), **u8)
         image_state = torch.empty(lib.s360_multi_image_bytes(V, H, W), **u8)
         color = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
         depth = None

@@ -31,7 +31,9 @@ def test_view_struct_layout_and_sizes():
     assert lib.s360_geom_bytes(1000) >= 1000 * (48 + 8 + 1)
     assert lib.s360_image_bytes(512, 1024) >= 512 * 1024 * 8 + 2048 * 8
     assert lib.s360_backward_scratch_bytes(10) >= 10 * 9 * 4
-    assert lib.s360_binning_scratch_bytes(1 << 20, 512, 1024) >= 3 * 4 * (1 << 20)
+    # matrix binning: (chunks of 2048 Gaussians) x tiles counters; beyond 8192 tiles: emit + radix sort (keys, ids, alternates)
+    assert lib.s360_binning_scratch_bytes(1 << 20, 1 << 22, 512, 1024) >= 4 * 512 * 2048
+    assert lib.s360_binning_scratch_bytes(1 << 20, 1 << 20, 2048, 4096) >= 3 * 4 * (1 << 20)
     assert lib.s360_preprocess_scratch_bytes(1 << 20) >= 4 * 4 * (1 << 20)
     assert b"bad argument" in lib.s360_error_string(-1)
     assert lib.s360_launch_count() >= 0
@@ -54,7 +56,7 @@ def test_batched_entry_points_size_queries_and_argument_checks():
     assert lib.s360_multi_preprocess_scratch_bytes(P, cap) >= 4 * 4 * cap + 4 * (P // 128 + 1)
     assert lib.s360_multi_image_bytes(V, 256, 256) >= V * (256 * 256 * 8 + 256 * 8)
     assert lib.s360_multi_image_bytes(1, 512, 1024) == lib.s360_image_bytes(512, 1024)
-    assert lib.s360_multi_binning_scratch_bytes(1 << 20, 1, 512, 1024) == lib.s360_binning_scratch_bytes(1 << 20, 512, 1024)
+    assert lib.s360_multi_binning_scratch_bytes(1 << 20, 1 << 21, 1, 512, 1024) == lib.s360_binning_scratch_bytes(1 << 20, 1 << 21, 512, 1024)
     assert lib.s360_multi_backward_scratch_bytes(cap) >= cap * 9 * 4
     v = _lib.S360View()
     v.P, v.image_height, v.image_width, v.mode, v.scene_scale = 10, 16, 16, 0, 1.0
