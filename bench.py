@@ -168,13 +168,17 @@ def run_ours(args):
     bg = torch.zeros(3, device=dev)
     target = torch.rand(3, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(seed))
     from splatter360_b200.parallel import AsyncLossReducer
+    from splatter360_b200.rasterizer import CapacityTracker
     reducer = AsyncLossReducer(dev)   # NCCL all-reduce of the scalar loss, issued async: step i+1 does not wait for it
+    # sync-free steady state: the instance buffers of step i are sized from the counts of earlier steps (+25 %); the
+    # device-side overflow flag of every step is collected asynchronously and checked after the timed region
+    tracker = None if args.exact_counts else CapacityTracker()
 
     def step(i):
         s = GaussianRasterizationSettings(
             image_height=H, image_width=W, tanfovx=1.0, tanfovy=1.0, bg=bg, scale_modifier=1.0,
             viewmatrix=cams.view_matrix[i], projmatrix=cams.full_projection[i], sh_degree=SH_DEGREE,
-            campos=cams.campos[i], prefiltered=False, debug=False, projection="erp")
+            campos=cams.campos[i], prefiltered=False, debug=False, projection="erp", capacity_tracker=tracker)
         m2d = torch.zeros_like(means, requires_grad=True)
         for t in (means, cov6, opac, shs):
             t.grad = None
@@ -208,6 +212,12 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    overflow_steps = []
+    if tracker is not None:
+        tracker.flush()
+        overflow_steps = [int(x) for x in tracker.overflowed]
+        if overflow_steps:
+            raise SystemExit(f"bench invalid: instance capacity overflowed at steps {overflow_steps} (CapacityTracker margin too small)")
     clocks = sampler.stop() if sampler else None
     _lib.profile_enable(False)
     launches = _lib.launch_count() - l0
@@ -247,10 +257,12 @@ def run_ours(args):
             return dict(means=host["means"], cov=host["cov"], sh=host["sh"], op=host["op"], target=host["target"],
                         pose=host["poses"][i:i + 1])
 
+        e2e_tracker = None if args.exact_counts else CapacityTracker()
+
         def e2e_compute(d):
             m, c, sh, o = (d[k].requires_grad_() for k in ("means", "cov", "sh", "op"))
             img = render_erp(d["pose"], near, far, (H, W), bg[None], m[None], c[None], sh[None], o[None],
-                             scale_invariant=False)
+                             scale_invariant=False, capacity_tracker=e2e_tracker)
             loss = mse_loss(img[0], d["target"])
             loss.backward()
             if world > 1:
@@ -365,10 +377,259 @@ def run_ours(args):
                    "views_per_step_per_gpu": 1,
                    "l2_policy": "inputs (356 MB/view) and gradient outputs (369 MB/view) are larger than the 126 MB L2",
                    "sharding": "one independent view per GPU per step; NCCL all-reduce of the scalar loss only",
-                   "api": "diff_gaussian_rasterization-compatible GaussianRasterizer autograd call, inputs resident in HBM"},
+                   "api": "diff_gaussian_rasterization-compatible GaussianRasterizer autograd call, inputs resident in HBM",
+                   "instance_buffers": ("exact: count read back every view" if tracker is None else
+                                        "sync-free: CapacityTracker (capacity = 1.25 x largest count seen; device overflow flag of every timed step checked, none set)")},
         "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu_baseline, "parity": parity, "final_loss": final_loss, "cube6_reference_style": cube6,
     }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
+def _dist_setup(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local_rank, dev
+
+
+def _timed(fn, K, Wm, world, dev):
+    """Wm warm-up calls, then K timed calls bracketed by barrier + synchronize; device time, max over ranks (ms)."""
+    import torch
+    import torch.distributed as dist
+    for i in range(Wm):
+        fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(K):
+        fn(Wm + i)
+    b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_config5(args):
+    """BASELINE.json configs[4]: 3M Gaussians, 1024x2048 ERP video path, forward only, 4 target frames per GPU
+    (32 frames on 8 GPUs), the SAME scene on every GPU (/root/reference/src/model/model_wrapper_erp.py:412-432 renders
+    the interpolated trajectory of one scene).  value: frames rendered from the HBM-resident scene.  e2e: the scene
+    starts in pinned host memory on rank 0 ONLY, is uploaded once and broadcast over NVLink (NCCL), every rank renders
+    its 4 frames and copies them to pinned host memory (where the reference's video writer takes them)."""
+    import torch
+    import torch.distributed as dist
+    from splatter360_b200 import _lib, camera, parallel, synthetic
+    from splatter360_b200 import rasterizer as R
+    rank, world, local_rank, dev = _dist_setup(args)
+    _lib.load()
+    Hv, Wv, Pv, F = 1024, 2048, 3_000_000, 4
+    K, Wm = args.steps, max(args.warmup, 3)
+    sc = synthetic.random_cloud_scene(Pv, seed=1234 + 5, ref_width=2048, device=dev)
+    means = sc.means.contiguous(); cov6 = synthetic.cov3x3_to_cov6(sc.covariances).contiguous()
+    opac = sc.opacities.contiguous(); shs = sc.harmonics.permute(0, 2, 1).contiguous()
+    n_frames = F * world
+    poses = synthetic.trajectory(n_frames * (K + Wm), seed=0).to(dev)
+    cams = camera.erp_camera(poses)
+    bg = torch.zeros(3, device=dev)
+    tracker = None if args.exact_counts else R.CapacityTracker()
+
+    def settings(j):
+        return R.GaussianRasterizationSettings(
+            image_height=Hv, image_width=Wv, tanfovx=1.0, tanfovy=1.0, bg=bg, scale_modifier=1.0, viewmatrix=cams.view_matrix[j],
+            projmatrix=cams.full_projection[j], sh_degree=SH_DEGREE, campos=cams.campos[j], prefiltered=False, debug=False,
+            projection="erp", capacity_tracker=tracker)
+
+    def my_frames(i):   # frames of step i rendered by this rank (round-robin over the ranks)
+        return [i * n_frames + f for f in parallel.shard_views(n_frames, rank, world)]
+
+    def step(i, scene=None):
+        m, c, o, sh = scene if scene is not None else (means, cov6, opac, shs)
+        return [R.forward_raw(settings(j), m, c, o, sh, None)[0] for j in my_frames(i)]
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    _lib.profile_read(reset=True)
+    l0 = None
+
+    def timed_step(i):
+        nonlocal l0
+        if i == Wm:
+            _lib.profile_read(reset=True); _lib.profile_enable(True); l0 = _lib.launch_count()
+        step(i)
+
+    total_ms = _timed(timed_step, K, Wm, world, dev)
+    _lib.profile_enable(False)
+    launches = _lib.launch_count() - l0
+    stages = _lib.profile_read(reset=True)
+    if tracker is not None:
+        tracker.flush()
+        if tracker.overflowed:
+            raise SystemExit(f"bench invalid: instance capacity overflowed at calls {tracker.overflowed}")
+    clocks = sampler.stop() if sampler else None
+    with torch.no_grad():
+        _, st = R.forward_raw(settings(0)._replace(capacity_tracker=None), means, cov6, opac, shs, None)
+        N, P_vis = st.num_rendered, st.num_visible
+        del st
+
+    # ---- e2e: rank 0 holds the scene in pinned host memory; upload once, NCCL broadcast, render, frames to pinned host
+    e2e = None
+    if not args.no_e2e:
+        host = None
+        if rank == 0:
+            host = [t.detach().cpu().pin_memory() for t in (means, cov6, opac, shs)]
+        bufs = [torch.empty_like(t) for t in (means, cov6, opac, shs)]
+        out_host = [torch.empty((3, Hv, Wv), dtype=torch.float32).pin_memory() for _ in range(F)]
+        e2e_tracker = None if args.exact_counts else R.CapacityTracker()
+
+        def e2e_step(i):
+            if rank == 0:
+                for b_, h_ in zip(bufs, host):
+                    b_.copy_(h_, non_blocking=True)
+            parallel.broadcast_scene(bufs, src=0)
+            frames = [R.forward_raw(settings(j)._replace(capacity_tracker=e2e_tracker), bufs[0], bufs[1], bufs[2], bufs[3], None)[0]
+                      for j in my_frames(i)]
+            for h_, f_ in zip(out_host, frames):
+                h_.copy_(f_, non_blocking=True)
+            torch.cuda.current_stream().synchronize()   # the frames are on the host when the step ends
+
+        Ke = max(3, min(K, 10))
+        e2e_ms = _timed(e2e_step, Ke, 2, world, dev) / Ke
+        scene_bytes = sum(t.numel() * 4 for t in bufs)
+        e2e = {"value": Pv * n_frames / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": e2e_ms, "steps": Ke,
+               "frames_per_s": n_frames / (e2e_ms * 1e-3),
+               "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(n_frames * 3 * Hv * Wv * 4),
+               "broadcast_bytes_per_rank": int(scene_bytes) if world > 1 else 0,
+               "api": "pinned host scene on rank 0 -> one H2D upload -> parallel.broadcast_scene (NCCL over NVLink) -> "
+                      "rasterizer.forward_raw per frame -> frames to pinned host; all inside the timed region"}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = total_ms / K
+    value = Pv * n_frames * K / (total_ms * 1e-3)
+    peak, peak_src = load_peaks()
+    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items() if v[1]}
+    npix = Hv * Wv
+    alg = {"preprocess": 340 * Pv + 48 * P_vis + 21 * Pv, "render_fwd": 52 * N + 20 * npix}
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    ach = alg.get(dom, 0) / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms.get(dom) else 0.0
+    out = {"metric": "gaussians_per_s_fwd", "value": value, "unit": "Gaussians/s", "n_gpus": world, "steps": K, "warmup": Wm,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "frames_per_s": n_frames * K / (total_ms * 1e-3),
+           "config": {"workload": "configs[4]: 3,000,000 random-cloud Gaussians (SH deg 4), 1024x2048 native-ERP video path, "
+                                  "forward only, 4 target frames per GPU per step, scene replicated on every GPU",
+                      "P": Pv, "image": [Hv, Wv], "frames_per_gpu": F, "sharding": "frames round-robin over the ranks; the scene is "
+                      "broadcast once per step in the e2e leg; no collective in the render path",
+                      "l2_policy": "the scene (1.02 GB) is larger than the 126 MB L2"},
+           "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,
+           "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": peak_src, "stages_ms": stage_ms, "instances": {"P": Pv, "P_visible": P_vis, "N": N}},
+           "cpu_baseline": None}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_config4(args):
+    """BASELINE.json configs[3]: the HM3D evaluation shape -- per GPU one scene of 1,048,576 pixel-aligned Gaussians and one
+    512x1024 target panorama rendered the REFERENCE's way: six 256x256 pinhole faces (DecoderSplattingCUDA, here in one
+    batched pass) + Cube2Equirec, MSE loss on the panorama, backward to the Gaussians.  Weak scaling: N scenes on N GPUs."""
+    import torch
+    import torch.distributed as dist
+    from splatter360_b200 import _lib, cubemap, synthetic
+    from splatter360_b200.decoder import DecoderSplattingCUDA, Gaussians
+    from splatter360_b200.loss import mse_loss
+    from splatter360_b200.parallel import AsyncLossReducer
+    rank, world, local_rank, dev = _dist_setup(args)
+    _lib.load()
+    K, Wm = args.steps, max(args.warmup, 3)
+    Fw = H // 2
+    sc = build_scene(dev, 1234 + 4 + 1000 * rank)
+    P = sc.means.shape[0]
+    g = Gaussians(sc.means[None].contiguous().requires_grad_(), sc.covariances[None].contiguous().requires_grad_(),
+                  sc.harmonics[None].contiguous().requires_grad_(), sc.opacities[None].contiguous().requires_grad_())
+    poses = synthetic.trajectory(K + Wm, seed=rank).to(dev)
+    faces = cubemap.cube_face_extrinsics(poses)                       # [steps, 6, 4, 4]
+    Kf = torch.tensor([[0.5, 0, 0.5], [0, 0.5, 0.5], [0, 0, 1.0]], device=dev).expand(1, 6, 3, 3)
+    near = torch.ones(1, 6, device=dev); far = torch.full((1, 6), 100.0, device=dev)
+    dec = DecoderSplattingCUDA(sync_free=not args.exact_counts).to(dev)
+    c2e = cubemap.Cube2Equirec(Fw, H, W).to(dev)
+    target = torch.rand(1, 3, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+    reducer = AsyncLossReducer(dev)
+
+    def step(i):
+        for t in (g.means, g.covariances, g.harmonics, g.opacities):
+            t.grad = None
+        out = dec(g, faces[i][None], Kf, near, far, (Fw, Fw))
+        pano = c2e.from_faces(out.color)                               # [1, 3, H, W]
+        loss = mse_loss(pano, target)
+        loss.backward()
+        reducer.submit(loss)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = None
+
+    def timed_step(i):
+        nonlocal l0
+        if i == Wm:
+            _lib.profile_read(reset=True); _lib.profile_enable(True); l0 = _lib.launch_count()
+        step(i)
+
+    total_ms = _timed(timed_step, K, Wm, world, dev)
+    reducer.flush()
+    _lib.profile_enable(False)
+    launches = _lib.launch_count() - l0
+    stages = _lib.profile_read(reset=True)
+    ovf = []
+    if dec.capacity_trackers:
+        for t in dec.capacity_trackers.values():
+            t.flush(); ovf += t.overflowed
+    if ovf:
+        raise SystemExit(f"bench invalid: pair / instance capacity overflowed at calls {ovf}")
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = total_ms / K
+    peak, peak_src = load_peaks()
+    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stages.items() if v[1]}
+    out = {"metric": "gaussians_per_s_fwd_bwd", "value": P * world * K / (total_ms * 1e-3), "unit": "Gaussians/s", "n_gpus": world,
+           "steps": K, "warmup": Wm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "views_per_s": world * K / (total_ms * 1e-3),
+           "config": {"workload": "configs[3]: HM3D evaluation shape, per GPU one scene of 1,048,576 pixel-aligned Gaussians -> one "
+                                  "512x1024 target panorama as six 256x256 pinhole faces (one batched pass) + Cube2Equirec, "
+                                  "MSE loss, forward + backward", "P": P, "image": [H, W], "faces": [6, Fw, Fw],
+                      "sharding": "one scene / target per GPU; NCCL all-reduce of the scalar loss only",
+                      "api": "DecoderSplattingCUDA.forward (reference decoder contract) + cubemap.Cube2Equirec + loss.mse_loss",
+                      "l2_policy": "inputs (369 MB/scene) and gradients are larger than the 126 MB L2"},
+           "e2e": None, "gpu_launches": int(launches) * world, "clocks": clocks,
+           "roofline": {"bound": "hbm", "kernel": max(stage_ms, key=lambda k: stage_ms[k]) if stage_ms else None, "achieved": None,
+                        "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src, "stages_ms": stage_ms},
+           "cpu_baseline": None, "final_loss": float(reducer.latest().item())}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -546,9 +807,17 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cube6", action="store_true")
+    ap.add_argument("--exact-counts", action="store_true", help="read the instance count back every view (no CapacityTracker)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="BASELINE.json config: 3 (default, the headline line), 4 (reference-style six faces + stitch, one "
+                         "scene per GPU), 5 (3M Gaussians, 1024x2048 video path, 4 frames per GPU, replicated scene)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 4:
+        run_config4(args)
+    elif args.config == 5:
+        run_config5(args)
     else:
         run_ours(args)
 

@@ -22,7 +22,7 @@ import torch
 from torch import Tensor, nn
 
 from .camera import erp_camera, get_fov, get_projection_matrix
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
+from .rasterizer import CapacityTracker, GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
 
@@ -42,7 +42,7 @@ def _triu6(cov: Tensor) -> Tensor:
 
 def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fov_y, image_shape, background_color,
                      gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
-                     projection, scene_scale, depth=None):
+                     projection, scene_scale, depth=None, capacity_tracker=None):
     """Per batch item: one rasterizer call.  The reference's per-call layout copies (SH transpose
     cuda_splatting.py:75, triu gather :115,123) and its 1/near rescale copies (:64-71) are not materialised: the
     kernels read harmonics [g,3,d_sh] and covariances [g,3,3] directly and apply the scale on load, and return the
@@ -65,7 +65,8 @@ def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fo
             prefiltered=False, debug=False, projection=projection,
             scene_scale=float(scene_scale[i]), sh_layout=1, cov_layout=1,
             depth_mode=None if depth is None else depth[0],
-            depth_near=0.0 if depth is None else float(depth[1][i]), depth_far=0.0 if depth is None else float(depth[2][i]))
+            depth_near=0.0 if depth is None else float(depth[1][i]), depth_far=0.0 if depth is None else float(depth[2][i]),
+            capacity_tracker=capacity_tracker[i] if isinstance(capacity_tracker, (list, tuple)) else capacity_tracker)
         out = GaussianRasterizer(settings)(
             means3D=gaussian_means[i], means2D=mean_gradients,
             shs=gaussian_sh_coefficients[i] if use_sh else None,
@@ -83,11 +84,12 @@ def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fo
 def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
                 background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                 gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
-                use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None):
+                use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None, capacity_tracker=None):
     """Pinhole render of a batch: [b,3,h,w].  Argument meaning identical to the reference.
 
     ``fused_depth_mode`` (extension): also return the depth image [b,h,w] that ``render_depth_cuda`` would produce,
-    accumulated as a fourth, differentiable channel of the same pass."""
+    accumulated as a fourth, differentiable channel of the same pass.  ``capacity_tracker`` (extension): a
+    ``rasterizer.CapacityTracker`` (or one per batch item) -- sync-free sizing of the instance buffers in a render loop."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b = extrinsics.shape[0]
     depth = None if fused_depth_mode is None else (fused_depth_mode, near.tolist(), far.tolist())
@@ -107,7 +109,7 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
     full_projection = view_matrix @ projection_matrix
     return _rasterize_batch(extrinsics, view_matrix, full_projection, host[0], host[1], image_shape,
                             background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
-                            gaussian_opacities, degree, use_sh, "pinhole", host[2], depth)
+                            gaussian_opacities, degree, use_sh, "pinhole", host[2], depth, capacity_tracker)
 
 
 def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, near: Tensor, far: Tensor,
@@ -174,7 +176,7 @@ def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
 def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
                background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
-               use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None):
+               use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None, capacity_tracker=None):
     """One equirectangular render per batch item: [b,3,h,w] (plus the fused radial-distance image [b,h,w] when
     ``fused_depth_mode`` is given).
 
@@ -197,7 +199,7 @@ def render_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape
     ones = [1.0] * b
     return _rasterize_batch(extrinsics_sphere, cam.view_matrix, cam.full_projection, ones, ones, image_shape,
                             background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
-                            gaussian_opacities, degree, use_sh, "erp", scales, depth)
+                            gaussian_opacities, degree, use_sh, "erp", scales, depth, capacity_tracker)
 
 
 def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
@@ -224,9 +226,11 @@ MAX_VIEWS_PER_PASS = 12   # two sets of cube faces; the pair buffers grow with v
 
 def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
                      gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh, projection,
-                     depth_mode, max_views):
+                     depth_mode, max_views, capacity_trackers=None):
     """cam_ext / view_matrix / full_projection: [b,v,4,4]; host: per (b,v) tuples (tanx, tany, scale, near, far) on the
-    host.  Consecutive views of one batch item that share those scalars go through one ``rasterize_views`` pass."""
+    host.  Consecutive views of one batch item that share those scalars go through one ``rasterize_views`` pass.
+    capacity_trackers: dict that receives one ``CapacityTracker`` per (batch item, first view of the pass): sync-free
+    sizing of the pair / instance buffers when the same decoder call is repeated (training steps, video frames)."""
     b, v = view_matrix.shape[:2]
     h, w = image_shape
     colors = torch.empty((b, v, 3, h, w), dtype=torch.float32, device=view_matrix.device)
@@ -242,7 +246,8 @@ def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, b
                 image_height=h, image_width=w, tanfovx=tanx, tanfovy=tany, bg=background_color[i], scale_modifier=1.0,
                 viewmatrix=view_matrix[i, j:k], projmatrix=full_projection[i, j:k], sh_degree=degree,
                 campos=cam_ext[i, j:k, :3, 3], prefiltered=False, debug=False, projection=projection,
-                scene_scale=scale, sh_layout=1, cov_layout=1, depth_mode=depth_mode, depth_near=near, depth_far=far)
+                scene_scale=scale, sh_layout=1, cov_layout=1, depth_mode=depth_mode, depth_near=near, depth_far=far,
+                capacity_tracker=None if capacity_trackers is None else capacity_trackers.setdefault((i, j), CapacityTracker()))
             out = rasterize_views(
                 gaussian_means[i], gaussian_opacities[i], gaussian_covariances[i], settings,
                 shs=gaussian_sh_coefficients[i] if use_sh else None,
@@ -259,7 +264,7 @@ def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
                       background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                       gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
                       use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None,
-                      max_views_per_pass: int = MAX_VIEWS_PER_PASS):
+                      max_views_per_pass: int = MAX_VIEWS_PER_PASS, capacity_trackers: Optional[dict] = None):
     """``render_cuda`` for all views at once: extrinsics [b,v,4,4], intrinsics [b,v,3,3], near/far [b,v]; Gaussians
     [b,g,...] as in ``render_cuda``.  Returns [b,v,3,h,w] (+ [b,v,h,w] depth with ``fused_depth_mode``).
 
@@ -285,14 +290,14 @@ def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     host = [[tuple(x) for x in row] for row in host]
     return _rasterize_views(extrinsics, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
                             gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
-                            "pinhole", fused_depth_mode, max_views_per_pass)
+                            "pinhole", fused_depth_mode, max_views_per_pass, capacity_trackers)
 
 
 def render_erp_views(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image_shape: tuple[int, int],
                      background_color: Tensor, gaussian_means: Tensor, gaussian_covariances: Tensor,
                      gaussian_sh_coefficients: Tensor, gaussian_opacities: Tensor, scale_invariant: bool = True,
                      use_sh: bool = True, fused_depth_mode: Optional[DepthRenderingMode] = None,
-                     max_views_per_pass: int = 4):
+                     max_views_per_pass: int = 4, capacity_trackers: Optional[dict] = None):
     """``render_erp`` for all views at once: extrinsics_sphere [b,v,4,4], near/far [b,v] -> [b,v,3,h,w]."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b, v = extrinsics_sphere.shape[:2]
@@ -308,7 +313,7 @@ def render_erp_views(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image
     host = [[tuple(x) for x in row] for row in host]
     return _rasterize_views(extrinsics_sphere, view_matrix, view_matrix, host, image_shape, background_color,
                             gaussian_means, gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree,
-                            use_sh, "erp", fused_depth_mode, max_views_per_pass)
+                            use_sh, "erp", fused_depth_mode, max_views_per_pass, capacity_trackers)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,13 +335,25 @@ class DecoderOutput:
 
 class DecoderSplattingCUDA(nn.Module):
     """Same forward contract as the reference decoder (decoder_splatting_cuda.py:34-97); constructed from a
-    background colour instead of the Hydra dataset config."""
+    background colour instead of the Hydra dataset config.
 
-    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True, fused_depth: bool = True) -> None:
+    Differences from the reference's per-view ``GaussianRasterizer`` calls, all switchable:
+    ``batched_views=True`` renders the views of a batch item in one pass -- identical images, gradients summed like
+    autograd does, but NO per-view ``radii`` and NO ``means2D`` screen-space gradient (the densification inputs of
+    upstream 3DGS; splatter360 never reads them, cuda_splatting.py:125-126 discards radii); ``fused_depth=True`` takes
+    the depth image from a fourth channel of the colour pass instead of a second rasterisation.  The ``"log"`` depth
+    mode reproduces the reference's clamp literally (``minimum(near).maximum(far)``, cuda_splatting.py:245), which for
+    near < far evaluates to log(far) everywhere.  ``sync_free=True`` sizes the pair / instance buffers from earlier
+    calls (``CapacityTracker``) instead of reading the counts back every call.  ``batched_views=False, fused_depth=False``
+    is the reference's call pattern."""
+
+    def __init__(self, background_color=(0.0, 0.0, 0.0), batched_views: bool = True, fused_depth: bool = True,
+                 sync_free: bool = False) -> None:
         super().__init__()
         self.register_buffer("background_color", torch.tensor(background_color, dtype=torch.float32), persistent=False)
         self.batched_views = batched_views   # False: one rasterizer call per view, like the reference
         self.fused_depth = fused_depth       # False: separate depth-as-colour pass, like the reference
+        self.capacity_trackers = {} if sync_free else None
 
     def forward(self, gaussians: Gaussians, extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tensor,
                 image_shape: tuple[int, int], depth_mode: Optional[DepthRenderingMode] = None) -> DecoderOutput:
@@ -350,7 +367,8 @@ class DecoderSplattingCUDA(nn.Module):
             # all views of a batch item in one rasterizer pass (the reference loops them, decoder_splatting_cuda.py:47-59)
             out = render_cuda_views(extrinsics, intrinsics, near, far, image_shape, bg, gaussians.means,
                                     gaussians.covariances, gaussians.harmonics, gaussians.opacities,
-                                    fused_depth_mode=depth_mode if fused else None)
+                                    fused_depth_mode=depth_mode if fused else None,
+                                    capacity_trackers=self.capacity_trackers)
             colors, depth = out if fused else (out, None)
         else:
             colors = torch.zeros((b, v, 3, *image_shape), dtype=torch.float32, device=extrinsics.device)

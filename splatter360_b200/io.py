@@ -48,12 +48,17 @@ class HostSceneFeeder:
         """Start the asynchronous upload of a dict of (ideally pinned) host tensors; returns immediately."""
         out, nbytes = {}, 0
         cur = torch.cuda.current_stream(self.device)
+        # ring buffers are allocated on the CONSUMER's stream (outside the copy-stream context): the caching allocator
+        # then ties their blocks to the stream that reads them, so a dropped feeder cannot hand a block to another
+        # consumer-stream allocation while rasterizer kernels still read it (ADVICE r01)
+        slots = {k: self._slot(k, t) for k, t in host.items()}
         free = torch.cuda.Event()
         free.record(cur)                       # the slot's previous reader was enqueued before this point
         self.stream.wait_event(free)
         with torch.cuda.stream(self.stream):
             for k, t in host.items():
-                dst = self._slot(k, t)
+                dst = slots[k]
+                dst.record_stream(self.stream)  # ... and the copy stream writes them
                 dst.copy_(t, non_blocking=True)
                 out[k] = dst.detach()          # fresh tensor object on the same storage: no autograd state carried over
                 nbytes += t.numel() * t.element_size()

@@ -112,6 +112,18 @@ def all_reduce_gradients(grads: Iterable[Optional[Tensor]]) -> None:
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
 
+def broadcast_scene(tensors: Sequence[Tensor], src: int = 0) -> None:
+    """Replicate one scene's Gaussian tensors (means, covariances, opacities, harmonics: 340-352 B per Gaussian) from
+    rank ``src`` to every rank, in place.  For the replicated-scene configurations (the video path renders many frames
+    of ONE scene, /root/reference/src/model/model_wrapper_erp.py:412-432) this replaces one PCIe upload per GPU by one
+    upload plus a broadcast over NVLink / NVSwitch (NCCL; gloo in the CPU tests)."""
+    _, ws = world()
+    if ws == 1:
+        return
+    for t in tensors:
+        dist.broadcast(t, src=src)
+
+
 def gather_views(local: Tensor, num_views: int) -> Tensor:
     """Reassemble the [num_views, ...] stack from the round-robin shards ``local`` [len(shard), ...] held by each
     rank (evaluation / video paths that need every frame on every rank)."""

@@ -60,6 +60,7 @@ class GaussianRasterizationSettings(NamedTuple):
     depth_near: float = 0.0            # unscaled near / far used by relative_disparity and log
     depth_far: float = 0.0
     pair_capacity: Optional[int] = None   # batched path only: slots for (view, Gaussian) pairs; None = V * P (never overflows)
+    capacity_tracker: Optional[object] = None   # a CapacityTracker: sync-free instance_capacity learnt from earlier calls
 
 
 _MODES = {"pinhole": _lib.MODE_PINHOLE, "erp": _lib.MODE_ERP}
@@ -162,6 +163,9 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
     P = means3D.shape[0]
     M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
     H, W = int(settings.image_height), int(settings.image_width)
+    tracker = settings.capacity_tracker
+    if tracker is not None and settings.instance_capacity is None:
+        settings = tracker.settings(settings)   # capacity from earlier calls once a count has arrived; else exact path
     with torch.cuda.device(device):
         view, keep = _make_view(settings, P, M, device)
         u8 = dict(dtype=torch.uint8, device=device)
@@ -213,11 +217,84 @@ def forward_raw(settings: GaussianRasterizationSettings, means3D: Tensor, cov6: 
             ctypes.c_int64(N), _ptr(point_list), _ptr(image_state), _ptr(color), _ptr(depth),
             ctypes.c_int32(dmode), ctypes.c_float(settings.depth_near), ctypes.c_float(settings.depth_far),
             _ptr(bin_scratch), st))
+        if tracker is not None:
+            tracker.observe(counters)
         if settings.debug:
             torch.cuda.synchronize(device)
     del keep
     return color, ForwardState(geom, radii, point_list, image_state, N if settings.instance_capacity is None else -1, nvis,
                                depth, counters)
+
+
+class CapacityTracker:
+    """Sync-free sizing of the instance buffers for a render loop (training steps, video frames).
+
+    The exact path reads the instance count N back after K1 (one small host wait per view).  A loop whose views change
+    slowly can skip that wait: render step i with ``instance_capacity`` = (largest N seen so far) x ``margin``, and
+    learn step i's own N -- and whether it overflowed -- from an asynchronous copy of the 16-byte device counters that
+    is polled WITHOUT blocking at later steps.
+
+        tracker = CapacityTracker()
+        for ...:
+            s = tracker.settings(s)                      # sets instance_capacity once a count is known
+            out = GaussianRasterizer(s)(...)             # or forward_raw
+            tracker.observe(state_or_counters)           # async D2H of the counters, no wait
+        tracker.flush(); assert not tracker.overflowed   # one wait at the end (or whenever the results are consumed)
+
+    Until the first count has arrived the settings are returned unchanged (exact path).  An overflow can only be
+    detected after the fact: ``overflowed`` lists the steps whose buffers were too small (their images / gradients are
+    incomplete and should be redone -- with the grown capacity the retry succeeds)."""
+
+    def __init__(self, margin: float = 1.25, min_capacity: int = 4096) -> None:
+        self.margin, self.min_capacity = float(margin), int(min_capacity)
+        self.capacity: Optional[int] = None
+        self.pair_capacity: Optional[int] = None   # batched path: (view, Gaussian) pairs
+        self.max_seen = 0
+        self.max_pairs = 0
+        self.overflowed: list = []
+        self._pending: list = []
+        self._step = 0
+
+    def settings(self, s: GaussianRasterizationSettings, pairs: bool = False) -> GaussianRasterizationSettings:
+        self.poll()
+        if self.capacity is None:
+            return s
+        if pairs:
+            return s._replace(instance_capacity=self.capacity, pair_capacity=self.pair_capacity)
+        return s._replace(instance_capacity=self.capacity)
+
+    def observe(self, counters) -> None:
+        """``counters``: the device int32[4] of a forward call (ForwardState.counters) or the state itself."""
+        c = getattr(counters, "counters", counters)
+        host = torch.empty(4, dtype=torch.int32).pin_memory()
+        host.copy_(c, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(c.device))
+        self._pending.append((self._step, host, ev))
+        self._step += 1
+
+    def _take(self, step, host) -> None:
+        n, ovf, npairs = int(host[0].item()) & 0xFFFFFFFF, int(host[1].item()), int(host[2].item()) & 0xFFFFFFFF
+        self.max_seen, self.max_pairs = max(self.max_seen, n), max(self.max_pairs, npairs)
+        want = max(self.min_capacity, int(self.max_seen * self.margin) + 1)
+        if self.capacity is None or want > self.capacity:
+            self.capacity = want
+        want = max(self.min_capacity, int(self.max_pairs * self.margin) + 1)
+        if self.pair_capacity is None or want > self.pair_capacity:
+            self.pair_capacity = want
+        if ovf & 3:
+            self.overflowed.append(step)
+
+    def poll(self) -> None:
+        while self._pending and self._pending[0][2].query():
+            step, host, _ = self._pending.pop(0)
+            self._take(step, host)
+
+    def flush(self) -> None:
+        for step, host, ev in self._pending:
+            ev.synchronize()
+            self._take(step, host)
+        self._pending = []
 
 
 def overflowed(state: ForwardState) -> bool:
@@ -304,8 +381,11 @@ def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, 
     P = means3D.shape[0]
     M = (shs.shape[2] if settings.sh_layout else shs.shape[1]) if shs is not None else 0
     H, W = int(settings.image_height), int(settings.image_width)
+    tracker = settings.capacity_tracker
+    if tracker is not None and settings.instance_capacity is None and settings.pair_capacity is None:
+        settings = tracker.settings(settings, pairs=True)
     if settings.pair_capacity is not None:
-        pcap = int(settings.pair_capacity)
+        pcap = min(int(settings.pair_capacity), V * P)
     elif _pair_capacity_override is not None:
         pcap = int(_pair_capacity_override)
     elif settings.projection == "erp" or settings.instance_capacity is not None:
@@ -370,6 +450,8 @@ def forward_views_raw(settings: GaussianRasterizationSettings, means3D: Tensor, 
             ctypes.c_int64(N), _ptr(point_list), _ptr(image_state), _ptr(color), _ptr(depth),
             ctypes.c_int32(dmode), ctypes.c_float(settings.depth_near), ctypes.c_float(settings.depth_far),
             _ptr(bin_scratch), st))
+        if tracker is not None:
+            tracker.observe(counters)
         if settings.debug:
             torch.cuda.synchronize(device)
     del keep

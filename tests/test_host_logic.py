@@ -111,6 +111,10 @@ def _worker(rank, ws, port, q):
             sums.append(float(red.latest()))
     red.flush()
     sums.append(float(red.latest()))
+    # replicated-scene broadcast (video path): rank 0 holds the scene, every rank ends up with it
+    scene = [torch.arange(12, dtype=torch.float32).reshape(4, 3) * (1.0 if rank == 0 else 0.0), torch.full((4,), float(rank))]
+    parallel.broadcast_scene(scene, src=0)
+    sums.append(float(scene[0].sum()) + float(scene[1].sum()))
     q.put((rank, idx, full[:, 0, 0, 0].tolist(), float(total), g[0][0, 0].item(), sums))
     dist.destroy_process_group()
 
@@ -131,7 +135,7 @@ def test_world_size_2_gloo_sharding_and_loss_allreduce():
         assert r[2] == [0.0, 1.0, 2.0, 3.0, 4.0]          # every rank reassembles all views
         assert abs(r[3] - (0 + 1 + 4 + 9 + 16)) < 1e-5     # loss all-reduce = single-process sum
         assert r[4] == 3.0                                  # gradient all-reduce: 1 + 2
-        assert r[5] == [6.0, 12.0, 15.0]                    # async reducer: (1 + 2) * step for steps 2, 4, 5
+        assert r[5] == [6.0, 12.0, 15.0, 66.0]              # async reducer: (1 + 2) * step for steps 2, 4, 5; broadcast scene
 
 
 def test_batched_decoder_groups_views_and_builds_the_reference_cameras(monkeypatch):
