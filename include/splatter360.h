@@ -254,6 +254,27 @@ int s360_cube2equirec_backward(const float* dL_dout /*[B,C,H,W]*/, const float* 
  * depth_to_distance_map_batch (/root/reference/src/geometry/z_depth_to_distance.py:4-34) applied between change_order
  * and the stitch exactly as its depth video does (model_wrapper_erp.py:447-463). */
 
+/* ---- fused Gaussian adapter: encoder head outputs -> rasterizer inputs in one pass.
+ * Replaces GaussianAdapterERP.forward (/root/reference/src/model/encoder/common/gaussian_adapter_erp.py:49-119): scale
+ * activation, quaternion normalisation, build_covariance (gaussians.py:8-44), rotation of the covariance into the world frame,
+ * ERP unprojection of the depth (sphere_projection.py:6-87, hm3d convention), SH mask and SH rotation (sh_rotation.py:10-30).
+ * One Gaussian per context pixel, in (batch x view, row, col) order: G = views * H * W.
+ *   raw      [G, 7 + 3 d_sh]  scale features 3 | quaternion xyzw 4 | SH [3][d_sh],  d_sh = (sh_degree + 1)^2, sh_degree <= 4
+ *   depth    [G]
+ *   pose     [views, 12]      camera-to-world R (row-major 3x3) and t of the context view
+ *   sh_rot   [views, 165]     the SH rotation the reference applies (Wigner D^0..D^4 of R, row-major blocks of size 1, 9, 25,
+ *                             49, 81), each column pre-multiplied by the reference's SH mask 0.1 * 0.25^l (1 for l = 0)
+ *   outputs  means [G,3], covariances [G,3,3], harmonics [G,3,d_sh]; scales [G,3] / rotations [G,4] (normalised xyzw) may be NULL
+ * Backward: cotangents (any may be NULL = zero) -> dL_draw [G, 7 + 3 d_sh], dL_ddepth [G].  means_grad = 0 reproduces the
+ * reference, whose unprojection runs under torch.no_grad() (sphere_projection.py:14): the means carry no gradient. */
+int s360_adapter_forward(int32_t views, int32_t H, int32_t W, int32_t sh_degree, float scale_min, float scale_max,
+                         const float* raw, const float* depth, const float* pose, const float* sh_rot, float* means,
+                         float* covariances, float* harmonics, float* scales, float* rotations, void* stream);
+int s360_adapter_backward(int32_t views, int32_t H, int32_t W, int32_t sh_degree, float scale_min, float scale_max,
+                          int32_t means_grad, const float* raw, const float* depth, const float* pose, const float* sh_rot,
+                          const float* dL_dmeans, const float* dL_dcovariances, const float* dL_dharmonics, float* dL_draw,
+                          float* dL_ddepth, void* stream);
+
 /* ---- debugging / introspection ---------------------------------------------------------------- */
 /* Unpack the geometry state for per-stage parity tests.  Any output may be NULL. */
 int s360_debug_unpack_geom(int32_t P, const void* geom, float* xy /*[P,2]*/, float* depth /*[P]*/,

@@ -27,6 +27,7 @@ EXPORTS = [
     "s360_multi_image_bytes", "s360_multi_backward_scratch_bytes",
     "s360_multi_forward_project", "s360_multi_forward_order", "s360_multi_forward_render", "s360_multi_backward",
     "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward", "s360_debug_counters",
+    "s360_adapter_forward", "s360_adapter_backward",
 ]
 ABI_VERSION = 5
 MAX_VIEWS = 32
@@ -127,6 +128,10 @@ def load() -> ctypes.CDLL:
         getattr(lib, n).argtypes = [vp, vp] + [c_int32] * 6 + [vp, vp, vp]
     lib.s360_debug_unpack_pairs.restype = c_int
     lib.s360_debug_unpack_pairs.argtypes = [c_int32, c_int64] + [vp] * 5
+    lib.s360_adapter_forward.restype = c_int
+    lib.s360_adapter_forward.argtypes = [c_int32, c_int32, c_int32, c_int32, c_float, c_float] + [vp] * 10
+    lib.s360_adapter_backward.restype = c_int
+    lib.s360_adapter_backward.argtypes = [c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_int32] + [vp] * 10
     lib.s360_debug_counters.restype = c_int
     lib.s360_debug_counters.argtypes = [vp, c_int, vp]
     if lib.s360_abi_version() != ABI_VERSION:

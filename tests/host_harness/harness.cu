@@ -3,6 +3,7 @@
 // code the GPU runs against the CPU oracle without a GPU.  Plain C entry points, host pointers everywhere.
 #include "../../splatter360_b200/csrc/persplat.cuh"
 #include "../../splatter360_b200/csrc/render_cull.cuh"
+#include "../../splatter360_b200/csrc/adapter_math.cuh"
 
 using namespace s360;
 
@@ -76,6 +77,37 @@ int s360h_cull(int n, const float* rec /*[n,12]*/, const float* block_c /*[n,2]*
     stage_instance(r0, r1, r2, cull, ev, col);
     hit[i] = rect_can_contribute(cull, ev, col.w, cull.x - block_c[2 * i], cull.y - block_c[2 * i + 1]) ? 1 : 0;
     ev_out[4 * i] = ev.x; ev_out[4 * i + 1] = ev.y; ev_out[4 * i + 2] = ev.z; ev_out[4 * i + 3] = ev.w;
+  }
+  return 0;
+}
+
+// fused Gaussian adapter: forward and backward of every Gaussian with the kernels' own per-Gaussian functions
+// (raw [G, 7 + 3 d_sh], pose [views, 12], rot [views, 165]; cotangents g_* -> d_raw, d_depth)
+int s360h_adapter(int views, int H, int W, int sh_degree, float smin, float smax, int means_grad, const float* raw,
+                  const float* depth, const float* pose, const float* rot, float* means, float* cov, float* harmonics,
+                  const float* g_means, const float* g_cov, const float* g_sh, float* d_raw, float* d_depth) {
+  AdapterCfg c;
+  c.H = H; c.W = W; c.sh_degree = sh_degree; c.d_sh = (sh_degree + 1) * (sh_degree + 1);
+  c.scale_min = smin; c.scale_max = smax; c.pixel_size = 1.f / (float)(W > H ? W : H); c.eps = 1e-8f; c.means_grad = means_grad;
+  const int C = 7 + 3 * c.d_sh;
+  for (long g = 0; g < (long)views * H * W; g++) {
+    const long bv = g / ((long)H * W);
+    const int pix = (int)(g - bv * H * W), row = pix / W, col = pix - row * W;
+    AdapterFwd f;
+    adapter_forward_one(c, raw + g * C, depth[g], pose + bv * AD_POSE_F, row, col, means + 3 * g, cov + 9 * g, f);
+    for (int ch = 0; ch < 3; ch++) {
+      float* sh = harmonics + g * 3 * c.d_sh + ch * c.d_sh;
+      for (int k = 0; k < c.d_sh; k++) sh[k] = raw[g * C + 7 + ch * c.d_sh + k];
+      adapter_rotate_sh<false>(sh_degree, rot + bv * AD_ROT_F, sh);
+    }
+    if (d_raw) {
+      adapter_backward_one(c, raw + g * C, depth[g], pose + bv * AD_POSE_F, f, g_means + 3 * g, g_cov + 9 * g, d_raw + g * C, d_depth[g]);
+      for (int ch = 0; ch < 3; ch++) {
+        float* o = d_raw + g * C + 7 + ch * c.d_sh;
+        for (int k = 0; k < c.d_sh; k++) o[k] = g_sh[g * 3 * c.d_sh + ch * c.d_sh + k];
+        adapter_rotate_sh<true>(sh_degree, rot + bv * AD_ROT_F, o);
+      }
+    }
   }
   return 0;
 }

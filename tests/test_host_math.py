@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not (os.path.exists(NVCC) or shutil.which("nvcc"
 def harness():
     src = os.path.join(HERE, "host_harness", "harness.cu")
     out = os.path.join(HERE, "host_harness", "libharness.so")
-    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh", "render_cull.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh", "render_cull.cuh", "adapter_math.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         nvcc = NVCC if os.path.exists(NVCC) else shutil.which("nvcc")
         subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
