@@ -440,18 +440,26 @@ size_t matrix_scratch_bytes(int64_t n_items, int64_t tiles) {
   return align_up((size_t)chunks * tiles * 4, 256) + align_up((size_t)tiles * 4, 256);
 }
 
-// tile id of the k-th cell (row-major) of a packed tile rectangle; erp wraps the column
+// tile id of the k-th cell (row-major) of a packed tile rectangle; erp wraps the column.  The matrix path holds at most
+// MB_MAX_TILES cells per rectangle, so row = floor((k + 0.5) / nx) is exact in float arithmetic (distance of the quotient
+// to the next integer >= 0.5 / nx, error of the approximate reciprocal <= 8192 / nx * 3e-7) and the erp column needs at
+// most one wrap (x0 >= -gx, x0 + nx <= 2 gx).
 __device__ __forceinline__ uint32_t rect_tile(uint32_t rx, uint32_t ry, uint32_t k, int gx, int mode) {
   const uint32_t nx = rx >> 16;
-  const uint32_t ky = k / nx, kx = k - ky * nx;
+  float inv;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)nx));
+  const uint32_t ky = (uint32_t)(((float)k + 0.5f) * inv), kx = k - ky * nx;
   int tx = (int)(int16_t)(rx & 0xffffu) + (int)kx;
-  if (mode == S360_MODE_ERP) { tx %= gx; if (tx < 0) tx += gx; }
+  if (mode == S360_MODE_ERP) { if (tx < 0) tx += gx; else if (tx >= gx) tx -= gx; }
   return ((ry & 0xffffu) + ky) * (uint32_t)gx + (uint32_t)tx;
 }
 
 // A warp expands the rectangles of 32 consecutive Gaussians of the depth order (lane j holds Gaussian j) into their
-// instances, 32 at a time, in order (Gaussian, then cell): f(tile, gid, valid) is called by all lanes in lock-step.
-// Balanced no matter how many tiles one Gaussian covers (pole-sized rectangles).
+// instances, 32 at a time, IN ORDER (Gaussian, then cell): f(tile, gid, valid) is called by all lanes in lock-step.
+// Balanced no matter how many tiles one Gaussian covers (pole-sized rectangles).  The owner of output slot `pos` is the
+// last Gaussian-lane whose first slot is <= pos: Gaussians without tiles sort to the END of the depth order (their key is
+// 0xFFFFFFFF), so the lanes with tiles form a prefix and  owner = #heads before the batch + #heads inside it up to pos - 1
+// (one OR-reduction of the head bits + one ballot per batch); any other pattern takes a 5-step shuffle search.
 template <class F>
 __device__ __forceinline__ void expand_group(uint32_t gid, uint2 r, uint32_t cnt, int lane, int gx, int mode, F&& f) {
   uint32_t incl = cnt;
@@ -462,14 +470,25 @@ __device__ __forceinline__ void expand_group(uint32_t gid, uint2 r, uint32_t cnt
   }
   const uint32_t off = incl - cnt;
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned nz = __ballot_sync(0xffffffffu, cnt > 0u);
+  const bool prefix = (nz & (nz + 1u)) == 0u;
   for (uint32_t p0 = 0; p0 < total; p0 += 32) {
     const uint32_t pos = p0 + lane;
-    int lo = 0;   // last lane j with off_j <= pos (zero-count lanes share their successor's offset and lose the tie)
+    int lo;
+    if (prefix) {
+      const uint32_t rel = off - p0;   // wraps for heads before the batch: not < 32
+      const unsigned heads = __reduce_or_sync(0xffffffffu, (cnt > 0u && rel < 32u) ? (1u << rel) : 0u);
+      const int before = __popc(__ballot_sync(0xffffffffu, cnt > 0u && off < p0));
+      lo = before + __popc(heads & ((2u << lane) - 1u)) - 1;
+    } else {
+      lo = 0;   // last lane j with off_j <= pos (zero-count lanes share their successor's offset and lose the tie)
 #pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-      const uint32_t v = __shfl_sync(0xffffffffu, off, (lo + s) & 31);
-      if (lo + s < 32 && v <= pos) lo += s;
+      for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, off, (lo + s) & 31);
+        if (lo + s < 32 && v <= pos) lo += s;
+      }
     }
+    lo &= 31;
     const uint32_t o_off = __shfl_sync(0xffffffffu, off, lo);
     const uint32_t o_rx = __shfl_sync(0xffffffffu, r.x, lo);
     const uint32_t o_ry = __shfl_sync(0xffffffffu, r.y, lo);
@@ -477,6 +496,26 @@ __device__ __forceinline__ void expand_group(uint32_t gid, uint2 r, uint32_t cnt
     const bool valid = pos < total;
     const uint32_t tile = valid ? rect_tile(o_rx, o_ry, pos - o_off, gx, mode) : 0xffffffffu;
     f(tile, o_gid, valid);
+  }
+}
+
+// Order-free expansion (counting only): every lane walks the cells of its own rectangle -- no search, no division; a
+// round whose largest rectangle is pole-sized falls back to the balanced expansion above.
+template <class F>
+__device__ __forceinline__ void expand_unordered(uint32_t gid, uint2 r, uint32_t cnt, int lane, int gx, int mode, F&& f) {
+  const uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
+  if (mx > 48u) {
+    expand_group(gid, r, cnt, lane, gx, mode, [&](uint32_t tile, uint32_t, bool valid) { if (valid) f(tile); });
+    return;
+  }
+  const int nx = (int)(r.x >> 16), x0 = (int)(int16_t)(r.x & 0xffffu);
+  uint32_t rowbase = (r.y & 0xffffu) * (uint32_t)gx;
+  int cx = 0;
+  for (uint32_t k = 0; k < cnt; k++) {
+    int tx = x0 + cx;
+    if (mode == S360_MODE_ERP) { if (tx < 0) tx += gx; else if (tx >= gx) tx -= gx; }
+    f(rowbase + (uint32_t)tx);
+    if (++cx == nx) { cx = 0; rowbase += (uint32_t)gx; }
   }
 }
 
@@ -506,8 +545,7 @@ mb_count_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int ntile
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
-    expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
-                 [&](uint32_t tile, uint32_t, bool valid) { if (valid) atomicAdd(&s_cnt[tile], 1u); });
+    expand_unordered(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode, [&](uint32_t tile) { atomicAdd(&s_cnt[tile], 1u); });
   __syncthreads();
   uint32_t* row = matrix + (size_t)blockIdx.x * ntiles;
   for (int t = threadIdx.x; t < ntiles; t += NW * 32) row[t] = s_cnt[t];
@@ -595,8 +633,8 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int nti
   uint32_t* my32 = s_cnt32 + warp * half;
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
-    expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
-                 [&](uint32_t tile, uint32_t, bool valid) { if (valid) atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
+    expand_unordered(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
+                     [&](uint32_t tile) { atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
   __syncthreads();
   // exclusive prefix over the warps, both halves of a word at once (a chunk has at most MB_CHUNK instances per tile)
   for (int j = threadIdx.x; j < half; j += NW * 32) {

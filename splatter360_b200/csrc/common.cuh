@@ -351,11 +351,67 @@ S360_HD void sh_basis_grad(int deg, float x, float y, float z, float* bx, float*
   bx[24] = sh_c4(8) * (4.f * xx * x - 12.f * x * yy); by[24] = sh_c4(8) * (-12.f * xx * y + 4.f * yy * y); bz[24] = 0.f;
 }
 
+// f(k, b_k) for every active basis function, one at a time (no 25-float array live); returns the number of coefficients
+template <class F>
+S360_HD int sh_basis_each(int deg, float x, float y, float z, F&& f) {
+  f(0, SH_C0);
+  if (deg < 1) return 1;
+  f(1, -SH_C1 * y); f(2, SH_C1 * z); f(3, -SH_C1 * x);
+  if (deg < 2) return 4;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  f(4, sh_c2(0) * xy); f(5, sh_c2(1) * yz); f(6, sh_c2(2) * (2.f * zz - xx - yy)); f(7, sh_c2(3) * xz); f(8, sh_c2(4) * (xx - yy));
+  if (deg < 3) return 9;
+  f(9, sh_c3(0) * y * (3.f * xx - yy)); f(10, sh_c3(1) * xy * z); f(11, sh_c3(2) * y * (4.f * zz - xx - yy));
+  f(12, sh_c3(3) * z * (2.f * zz - 3.f * xx - 3.f * yy)); f(13, sh_c3(4) * x * (4.f * zz - xx - yy));
+  f(14, sh_c3(5) * z * (xx - yy)); f(15, sh_c3(6) * x * (xx - 3.f * yy));
+  if (deg < 4) return 16;
+  f(16, sh_c4(0) * xy * (xx - yy)); f(17, sh_c4(1) * yz * (3.f * xx - yy)); f(18, sh_c4(2) * xy * (7.f * zz - 1.f));
+  f(19, sh_c4(3) * yz * (7.f * zz - 3.f)); f(20, sh_c4(4) * (zz * (35.f * zz - 30.f) + 3.f)); f(21, sh_c4(5) * xz * (7.f * zz - 3.f));
+  f(22, sh_c4(6) * (xx - yy) * (7.f * zz - 1.f)); f(23, sh_c4(7) * xz * (xx - 3.f * yy));
+  f(24, sh_c4(8) * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy)));
+  return 25;
+}
+
+// d += sum_k grad b_k(x, y, z) * s(k): the direction gradient of an SH colour, term by term, so that no 3 x 25 array of
+// basis derivatives is ever live (the batched K8+K9 kernel spilled on exactly those arrays).  s(k) is a callable.
+template <class S>
+S360_HD void sh_grad_dot(int deg, float x, float y, float z, S&& s, float* d) {
+#define S360_T(k, BX, BY, BZ) { const float sk = s(k); d[0] += (BX) * sk; d[1] += (BY) * sk; d[2] += (BZ) * sk; }
+  if (deg < 1) return;
+  S360_T(1, 0.f, -SH_C1, 0.f) S360_T(2, 0.f, 0.f, SH_C1) S360_T(3, -SH_C1, 0.f, 0.f)
+  if (deg < 2) return;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  S360_T(4, sh_c2(0) * y, sh_c2(0) * x, 0.f)
+  S360_T(5, 0.f, sh_c2(1) * z, sh_c2(1) * y)
+  S360_T(6, sh_c2(2) * -2.f * x, sh_c2(2) * -2.f * y, sh_c2(2) * 4.f * z)
+  S360_T(7, sh_c2(3) * z, 0.f, sh_c2(3) * x)
+  S360_T(8, sh_c2(4) * 2.f * x, sh_c2(4) * -2.f * y, 0.f)
+  if (deg < 3) return;
+  S360_T(9, sh_c3(0) * 6.f * xy, sh_c3(0) * (3.f * xx - 3.f * yy), 0.f)
+  S360_T(10, sh_c3(1) * yz, sh_c3(1) * xz, sh_c3(1) * xy)
+  S360_T(11, sh_c3(2) * -2.f * xy, sh_c3(2) * (4.f * zz - xx - 3.f * yy), sh_c3(2) * 8.f * yz)
+  S360_T(12, sh_c3(3) * -6.f * xz, sh_c3(3) * -6.f * yz, sh_c3(3) * (6.f * zz - 3.f * xx - 3.f * yy))
+  S360_T(13, sh_c3(4) * (4.f * zz - 3.f * xx - yy), sh_c3(4) * -2.f * xy, sh_c3(4) * 8.f * xz)
+  S360_T(14, sh_c3(5) * 2.f * xz, sh_c3(5) * -2.f * yz, sh_c3(5) * (xx - yy))
+  S360_T(15, sh_c3(6) * (3.f * xx - 3.f * yy), sh_c3(6) * -6.f * xy, 0.f)
+  if (deg < 4) return;
+  S360_T(16, sh_c4(0) * (3.f * xx * y - yy * y), sh_c4(0) * (xx * x - 3.f * x * yy), 0.f)
+  S360_T(17, sh_c4(1) * 6.f * xy * z, sh_c4(1) * z * (3.f * xx - 3.f * yy), sh_c4(1) * y * (3.f * xx - yy))
+  S360_T(18, sh_c4(2) * y * (7.f * zz - 1.f), sh_c4(2) * x * (7.f * zz - 1.f), sh_c4(2) * 14.f * xy * z)
+  S360_T(19, 0.f, sh_c4(3) * z * (7.f * zz - 3.f), sh_c4(3) * y * (21.f * zz - 3.f))
+  S360_T(20, 0.f, 0.f, sh_c4(4) * (140.f * zz * z - 60.f * z))
+  S360_T(21, sh_c4(5) * z * (7.f * zz - 3.f), 0.f, sh_c4(5) * x * (21.f * zz - 3.f))
+  S360_T(22, sh_c4(6) * 2.f * x * (7.f * zz - 1.f), sh_c4(6) * -2.f * y * (7.f * zz - 1.f), sh_c4(6) * (xx - yy) * 14.f * z)
+  S360_T(23, sh_c4(7) * z * (3.f * xx - 3.f * yy), sh_c4(7) * -6.f * xy * z, sh_c4(7) * x * (xx - 3.f * yy))
+  S360_T(24, sh_c4(8) * (4.f * xx * x - 12.f * x * yy), sh_c4(8) * (-12.f * xx * y + 4.f * yy * y), 0.f)
+#undef S360_T
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launchers (defined in the .cu files, called from api.cu)
 int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
                       const float* shs, const float* colors, GeomState g, int32_t* radii,
-                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, uint32_t* hist, cudaStream_t st);
+                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st);
 int launch_preprocess_backward(const S360View& v, const float* means, const float* cov, const float* opac, const float* shs,
                                GeomState g, const int32_t* radii, const float* acc, float* d_means,
                                float* d_means2D, float* d_cov, float* d_opac, float* d_shs, float* d_colors,
@@ -365,7 +421,7 @@ int launch_mark_visible(const S360View& v, const float* means, uint8_t* present,
 int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
                             const float* opac, const float* shs, const float* colors, GeomState g, PairState ps,
                             int32_t* radii, uint32_t* depth_keys, uint32_t* ids, S360Counters* counters,
-                            uint32_t* status, uint32_t* hist, cudaStream_t st);
+                            uint32_t* status, cudaStream_t st);
 int launch_zero_acc(float* acc, const uint32_t* n_dev, int64_t cap, cudaStream_t st);
 int launch_preprocess_multi_backward(const S360View& v, int NV, const float* means, const float* cov, const float* opac,
                                      const float* shs, GeomState g, PairState ps, const float* acc, float* d_means,

@@ -17,15 +17,9 @@ __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
                   const float* __restrict__ opac, const float* __restrict__ shs,
                   const float* __restrict__ colors, GeomState gs, int32_t* __restrict__ radii,
-                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, S360Counters* counters,
-                  uint32_t* __restrict__ hist) {
+                  uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids, S360Counters* counters) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
   __shared__ uint64_t s_bar;
-  // digit histograms of the four depth-sort passes, accumulated here so that the sort needs no pass of its own over
-  // the keys (hist: [4][256] global counters, zeroed by the caller; may be NULL)
-  __shared__ uint32_t s_hist[4 * 256];
-  for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) s_hist[i] = 0;
-  __syncthreads();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = v.P;
   const int row = v.M * 3;                                   // floats per Gaussian
@@ -69,10 +63,6 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     gs.rect[idx] = rect;
     depth_keys[idx] = key;
     ids[idx] = (uint32_t)idx;
-    if (hist != nullptr) {
-#pragma unroll
-      for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * 256 + ((key >> (8 * p)) & 0xffu)], 1u);
-    }
   }
   // block totals -> one atomic each.  The instance total is known here already (the scan only orders it), which
   // lets the host size the instance buffers while the depth sort is still running.
@@ -90,12 +80,6 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     if (threadIdx.x == 0) {
       if (s_cnt[0]) atomicAdd(&counters->num_visible, s_cnt[0]);
       if (s_cnt[1]) atomicAdd(&counters->num_rendered, s_cnt[1]);
-    }
-    if (hist != nullptr) {   // the barriers above ordered every thread's shared-memory atomics before this read
-      for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) {
-        const uint32_t c = s_hist[i];
-        if (c) atomicAdd(&hist[i], c);
-      }
     }
   }
 
@@ -130,7 +114,7 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
 
 int launch_preprocess(const S360View& v, const float* means, const float* cov, const float* opac,
                       const float* shs, const float* colors, GeomState g, int32_t* radii,
-                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, uint32_t* hist, cudaStream_t st) {
+                      uint32_t* depth_keys, uint32_t* ids, S360Counters* counters, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
@@ -138,10 +122,10 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
   // opt in to the dynamic size whenever dynamic + static shared memory may pass the 48 KB default
   if (v.mode == S360_MODE_PINHOLE) {
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters, hist);
+    preprocess_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
   } else {
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters, hist);
+    preprocess_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, colors, g, radii, depth_keys, ids, counters);
   }
   count_launch();
   return (int)cudaGetLastError();
@@ -411,13 +395,11 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
                    const float* __restrict__ cov3D, const float* __restrict__ opac, const float* __restrict__ shs,
                    const float* __restrict__ colors, GeomState gs, PairState ps,
                    const uint32_t* __restrict__ block_base, uint32_t* __restrict__ depth_keys,
-                   uint32_t* __restrict__ ids, uint32_t* __restrict__ hist) {
+                   uint32_t* __restrict__ ids) {
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
   __shared__ uint64_t s_bar;
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
   __shared__ uint32_t s_w[PRE_THREADS / 32];
-  __shared__ uint32_t s_hist[4 * 256];   // digit histograms of the pair depth keys (see preprocess_kernel)
-  for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) s_hist[i] = 0;
   const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
   const int P = v.P;
   const int gy = (v.image_height + TILE - 1) / TILE;
@@ -465,7 +447,7 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
   uint32_t slot = block_base[blockIdx.x] + woff + incl - cnt;
   // every thread waits for the bulk copy: no thread may leave while the TMA still writes this CTA's shared memory
   if (shs && bulk_ok) mbar_wait(&s_bar, 0);
-  if (idx < P) {
+  if (idx >= P) return;
   ps.base[idx] = slot;
   uint32_t kept = mask;
   float col[3] = {0.f, 0.f, 0.f};
@@ -493,26 +475,14 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
     gs.clamped[slot] = pr.cl | clc;
     depth_keys[slot] = pr.key;
     ids[slot] = slot;
-    if (hist != nullptr) {
-#pragma unroll
-      for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p * 256 + ((pr.key >> (8 * p)) & 0xffu)], 1u);
-    }
   }
   if (kept != mask) ps.mask[idx] = kept;
-  }
-  if (hist != nullptr) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 4 * 256; i += PRE_THREADS) {
-      const uint32_t c = s_hist[i];
-      if (c) atomicAdd(&hist[i], c);
-    }
-  }
 }
 
 int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, const float* means, const float* cov,
                             const float* opac, const float* shs, const float* colors, GeomState g, PairState ps,
                             int32_t* radii, uint32_t* depth_keys, uint32_t* ids, S360Counters* counters,
-                            uint32_t* status, uint32_t* hist, cudaStream_t st) {
+                            uint32_t* status, cudaStream_t st) {
   if (v.P == 0) return 0;
   const int grid = (v.P + PRE_THREADS - 1) / PRE_THREADS;
   const size_t smem = shs ? (size_t)PRE_THREADS * v.M * 3 * sizeof(float) : 0;
@@ -526,10 +496,10 @@ int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, co
   multi_scan_kernel<<<1, 1024, 0, st>>>(grid, block_count, cap, ps, counters);
   if (v.mode == S360_MODE_PINHOLE) {
     if (smem > 32 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    multi_write_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids, hist);
+    multi_write_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
   } else {
     if (smem > 32 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    multi_write_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids, hist);
+    multi_write_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
   }
   count_launch(3);
   return (int)cudaGetLastError();
@@ -556,18 +526,10 @@ __device__ __forceinline__ void sh_dir_backward(const S360View& v, const float* 
   const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
   const float dx = ox * inv, dy = oy * inv, dz = oz * inv;
   const int deg = min(v.sh_degree, v.max_sh_degree);
-  float bx[25], by[25], bz[25];
-  const int n = (deg + 1) * (deg + 1);
-  sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
   const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
   float ddir[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int k = 0; k < 25; k++) {
-    if (k < n) {
-      const float s = sh[ks * k] * drgb[0] + sh[ks * k + cs] * drgb[1] + sh[ks * k + 2 * cs] * drgb[2];
-      ddir[0] += bx[k] * s; ddir[1] += by[k] * s; ddir[2] += bz[k] * s;
-    }
-  }
+  sh_grad_dot(deg, dx, dy, dz,
+              [&](int k) { return sh[ks * k] * drgb[0] + sh[ks * k + cs] * drgb[1] + sh[ks * k + 2 * cs] * drgb[2]; }, ddir);
   const float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
   dm[0] += (ddir[0] - dx * dot) * inv;
   dm[1] += (ddir[1] - dy * dot) * inv;
@@ -579,21 +541,15 @@ __device__ __forceinline__ void sh_coeff_backward(const S360View& v, float* sh, 
                                                   const float* campos, const float* drgb, bool first) {
   const float ox = mx - campos[0], oy = my - campos[1], oz = mz - campos[2];
   const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
-  float b[25];
   const int deg = min(v.sh_degree, v.max_sh_degree);
-  const int n = sh_basis(deg, ox * inv, oy * inv, oz * inv, b);
   const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
   if (first) {
-#pragma unroll
-    for (int k = 0; k < 25; k++) {
-      if (k < n) { sh[ks * k] = b[k] * drgb[0]; sh[ks * k + cs] = b[k] * drgb[1]; sh[ks * k + 2 * cs] = b[k] * drgb[2]; }
-    }
+    const int n = sh_basis_each(deg, ox * inv, oy * inv, oz * inv, [&](int k, float b) {
+      sh[ks * k] = b * drgb[0]; sh[ks * k + cs] = b * drgb[1]; sh[ks * k + 2 * cs] = b * drgb[2]; });
     for (int k = n; k < v.M; k++) { sh[ks * k] = 0.f; sh[ks * k + cs] = 0.f; sh[ks * k + 2 * cs] = 0.f; }
   } else {
-#pragma unroll
-    for (int k = 0; k < 25; k++) {
-      if (k < n) { sh[ks * k] += b[k] * drgb[0]; sh[ks * k + cs] += b[k] * drgb[1]; sh[ks * k + 2 * cs] += b[k] * drgb[2]; }
-    }
+    sh_basis_each(deg, ox * inv, oy * inv, oz * inv, [&](int k, float b) {
+      sh[ks * k] += b * drgb[0]; sh[ks * k + cs] += b * drgb[1]; sh[ks * k + 2 * cs] += b * drgb[2]; });
   }
 }
 
