@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "render_cull.cuh"
 
 namespace s360 {
 static std::atomic<uint64_t> g_launches{0};
@@ -431,8 +432,10 @@ __global__ void unpack_geom_kernel(int P, GeomState g, float* xy, float* depth, 
   if (tiles) tiles[i] = t;
   if (xy) { xy[2 * i] = a.x; xy[2 * i + 1] = a.y; }
   if (depth) depth[i] = c.w;
-  if (conop) { conop[4 * i] = a.z; conop[4 * i + 1] = a.w; conop[4 * i + 2] = b.x; conop[4 * i + 3] = b.y; }
-  if (rgb) { rgb[3 * i] = c.x; rgb[3 * i + 1] = c.y; rgb[3 * i + 2] = c.z; }
+  float co[4], col[3];
+  unpack_record(a, b, c, co, col);
+  if (conop) { conop[4 * i] = co[0]; conop[4 * i + 1] = co[1]; conop[4 * i + 2] = co[2]; conop[4 * i + 3] = co[3]; }
+  if (rgb) { rgb[3 * i] = col[0]; rgb[3 * i + 1] = col[1]; rgb[3 * i + 2] = col[2]; }
   if (clamped) { const uint8_t cl = g.clamped[i]; clamped[3 * i] = cl & 1; clamped[3 * i + 1] = (cl >> 1) & 1; clamped[3 * i + 2] = (cl >> 2) & 1; }
 }
 

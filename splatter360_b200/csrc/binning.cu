@@ -41,8 +41,18 @@ rs_global_hist_kernel(const uint32_t* __restrict__ keys, int64_t n_cap, const ui
   const int64_t n = effective_n(n_cap, n_dev);
   for (int i = threadIdx.x; i < 4 * RS_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
   __syncthreads();
+  // four keys per load (the key buffers are 256-byte aligned); the tail is handled key by key
   const int64_t stride = (int64_t)gridDim.x * RS_THREADS;
-  for (int64_t j = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; j < n; j += stride) {
+  const int64_t n4 = n >> 2;
+  const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
+  for (int64_t j = (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; j < n4; j += stride) {
+    const uint4 k = keys4[j];
+    for (int p = 0; p < npasses; p++) {
+      atomicAdd(&s_hist[p][(k.x >> (8 * p)) & 0xffu], 1u); atomicAdd(&s_hist[p][(k.y >> (8 * p)) & 0xffu], 1u);
+      atomicAdd(&s_hist[p][(k.z >> (8 * p)) & 0xffu], 1u); atomicAdd(&s_hist[p][(k.w >> (8 * p)) & 0xffu], 1u);
+    }
+  }
+  for (int64_t j = (n4 << 2) + (int64_t)blockIdx.x * RS_THREADS + threadIdx.x; j < n; j += stride) {
     const uint32_t k = keys[j];
     for (int p = 0; p < npasses; p++) atomicAdd(&s_hist[p][(k >> (8 * p)) & 0xffu], 1u);
   }
@@ -145,16 +155,32 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   } else {
     *reinterpret_cast<volatile uint32_t*>(my_status) = total | ST_AGG;
   }
+  // Look-back over a WINDOW of predecessors per step: the loads of a window are independent and in flight together.  A
+  // sort of a million keys is a single wave of CTAs that all publish their counts at about the same time, so the last
+  // CTA has to walk over ~half the grid before it meets an inclusive prefix; one predecessor per L2 round trip made that
+  // walk (not the ranking or the scatter) the critical path of every pass.
   uint32_t excl = 0;
   if (bid > 0) {
+    constexpr int LB = 8;
     int64_t j = (int64_t)bid - 1;
-    while (true) {
-      const uint32_t sv = vstatus[(size_t)j * RS_BINS + d];
-      const uint32_t flag = sv & ~ST_MASK;
-      if (flag == 0u) continue;          // predecessor has not published yet
-      excl += sv & ST_MASK;
-      if (flag == ST_PREFIX) break;
-      --j;
+    bool done = false;
+    while (!done) {
+      uint32_t sv[LB];
+#pragma unroll
+      for (int i = 0; i < LB; i++) {   // entries before block 0 read as an empty inclusive prefix
+        sv[i] = 2u << 30;
+        if (j - i >= 0) sv[i] = vstatus[(size_t)(j - i) * RS_BINS + d];
+      }
+      int used = 0;
+#pragma unroll
+      for (int i = 0; i < LB; i++) {
+        const uint32_t flag = sv[i] & ~ST_MASK;
+        if (done || used < i || flag == 0u) continue;   // stop at the first predecessor that has not published yet
+        excl += sv[i] & ST_MASK;
+        used = i + 1;
+        if (flag == ST_PREFIX) done = true;
+      }
+      j -= used;   // used == 0: spin on the same window
     }
     *reinterpret_cast<volatile uint32_t*>(my_status) = (excl + total) | ST_PREFIX;
   }
@@ -429,6 +455,9 @@ emit_instances_kernel(int P_cap, const uint32_t* __restrict__ n_dev, int gx, int
 // scan of per-Gaussian offsets at all.  Used whenever tiles <= MB_MAX_TILES and the matrix stays small.
 constexpr int MB_CHUNK = 2048;
 constexpr int MB_MAX_TILES = 8192;
+#ifndef S360_MB_BALLOT_MATCH
+#define S360_MB_BALLOT_MATCH 0
+#endif
 
 bool matrix_binning_ok(int64_t n_items, int64_t tiles) {
   if (tiles <= 0 || tiles > MB_MAX_TILES || n_items <= 0) return false;
@@ -643,28 +672,29 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int nti
     for (int w = 0; w < NW; w++) { const uint32_t c = s_cnt32[w * half + j]; s_cnt32[w * half + j] = run; run += c; }
   }
   __syncthreads();
-  // pass 2: in-order ranking.  Lanes of one batch that hit the same tile are matched with one ballot per tile-id bit;
-  // the lowest of them advances the warp's counter of that tile by the size of the group.
+  // pass 2: in-order ranking.  Lanes of one batch that hit the same tile are found with MATCH.ANY (S360_MB_BALLOT_MATCH=1:
+  // one ballot per tile-id bit instead -- measured 3x more instructions per batch); all of them read the warp's counter of
+  // that tile (shared-memory broadcast), the lowest one then advances it by the size of the group.
   unsigned short* my16 = reinterpret_cast<unsigned short*>(my32);
   const unsigned lt_mask = (1u << lane) - 1u;
   bool overflow = false;
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
     expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode, [&](uint32_t tile, uint32_t g, bool valid) {
+#if S360_MB_BALLOT_MATCH
       unsigned peers = __ballot_sync(0xffffffffu, valid);
       for (int b = 0; b < tbits; b++) {
         const bool bit = (tile >> b) & 1u;
         const unsigned bal = __ballot_sync(0xffffffffu, bit);
         peers &= bit ? bal : ~bal;
       }
-      if (!valid) peers = 1u << lane;
-      const int leader = __ffs(peers) - 1;
+#else
+      const unsigned peers = __match_any_sync(0xffffffffu, tile);   // lanes past the end carry 0xffffffff and match each other
+#endif
       uint32_t old = 0;
-      if (valid && lane == leader) {
-        old = my16[tile];
-        my16[tile] = (unsigned short)(old + (uint32_t)__popc(peers));
-      }
-      old = __shfl_sync(0xffffffffu, old, leader);
+      if (valid) old = my16[tile];
+      __syncwarp();
+      if (valid && (peers & lt_mask) == 0u) my16[tile] = (unsigned short)(old + (uint32_t)__popc(peers));
       __syncwarp();
       if (valid) {
         const uint32_t dst = s_base[tile] + old + (uint32_t)__popc(peers & lt_mask);

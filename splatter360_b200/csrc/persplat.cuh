@@ -33,6 +33,21 @@ S360_HD void store_dcov(const S360View& v, float* __restrict__ d_cov, int idx, c
   }
 }
 
+// atan2 for the equirectangular pixel coordinates.  CUDA's atan2f is good to ~3 ulp; on a 1024-wide panorama that is
+// 1e-4 px, and for sub-pixel splats the screen-space gradient sums (q dx over ~9 pixels, almost cancelling) amplify a centre
+// error by 10-100x.  The double-precision atan2 rounded to float is correctly rounded (what the oracle's libm delivers) and
+// costs nothing measurable in the HBM-bound K1 (S360_ERP_ATAN2_F64=0 restores atan2f).
+#ifndef S360_ERP_ATAN2_F64
+#define S360_ERP_ATAN2_F64 1
+#endif
+S360_HD float s360_atan2(float y, float x) {
+#if defined(__CUDA_ARCH__) && S360_ERP_ATAN2_F64
+  return (float)atan2((double)y, (double)x);
+#else
+  return atan2f(y, x);
+#endif
+}
+
 // Result of projecting one Gaussian into one view (K1 geometry; shared by the single-view and the batched kernel).
 struct Proj {
   bool upstream_visible;   // upstream's radius > 0 (tile rectangle non-empty before the tight box)
@@ -122,8 +137,8 @@ S360_HD void project_view(const S360View& v, const float* V, const float* PM, fl
       ey = (int)ceilf(3.f * sqrtf(g.c));
       if (ex > W / 2) ex = W / 2;
       const float su = -(float)W / (2.f * PI_F), sv = -(float)H / PI_F;
-      o.px = su * atan2f(g.t[0], g.t[2]) + 0.5f * W - 0.5f;
-      o.py = sv * atan2f(g.t[1], sqrtf(g.t[0] * g.t[0] + g.t[2] * g.t[2])) + 0.5f * H - 0.5f;
+      o.px = su * s360_atan2(g.t[0], g.t[2]) + 0.5f * W - 0.5f;
+      o.py = sv * s360_atan2(g.t[1], sqrtf(g.t[0] * g.t[0] + g.t[2] * g.t[2])) + 0.5f * H - 0.5f;
     }
     const float px = o.px, py = o.py;
     // upstream tile rectangle

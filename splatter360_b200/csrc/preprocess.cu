@@ -7,6 +7,7 @@
 // /root/reference/src/model/decoder/cuda_splatting.py:113-124.
 #include "common.cuh"
 #include "persplat.cuh"
+#include "render_cull.cuh"
 
 namespace s360 {
 
@@ -105,9 +106,11 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
     col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
   }
   if (want_color) {
-    gs.rec[3 * (size_t)idx + 0] = make_float4(px, py, cA, cB);
-    gs.rec[3 * (size_t)idx + 1] = make_float4(cC, op, hx, hy);
-    gs.rec[3 * (size_t)idx + 2] = make_float4(col[0], col[1], col[2], sortkey);
+    float4 r0, r1, r2;
+    pack_record(px, py, cA, cB, cC, op, hx, hy, col, sortkey, v.image_width, r0, r1, r2);
+    gs.rec[3 * (size_t)idx + 0] = r0;
+    gs.rec[3 * (size_t)idx + 1] = r1;
+    gs.rec[3 * (size_t)idx + 2] = r2;
     gs.clamped[idx] = cl;
   }
 }
@@ -468,9 +471,11 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
       col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
       col_view = view;
     }
-    gs.rec[3 * (size_t)slot + 0] = make_float4(pr.px, pr.py, pr.cA, pr.cB);
-    gs.rec[3 * (size_t)slot + 1] = make_float4(pr.cC, pr.op, pr.hx, pr.hy);
-    gs.rec[3 * (size_t)slot + 2] = make_float4(col[0], col[1], col[2], pr.sortkey);
+    float4 r0, r1, r2;
+    pack_record(pr.px, pr.py, pr.cA, pr.cB, pr.cC, pr.op, pr.hx, pr.hy, col, pr.sortkey, v.image_width, r0, r1, r2);
+    gs.rec[3 * (size_t)slot + 0] = r0;
+    gs.rec[3 * (size_t)slot + 1] = r1;
+    gs.rec[3 * (size_t)slot + 2] = r2;
     gs.rect[slot] = make_uint2(pr.rect.x, pr.rect.y + (uint32_t)(view * gy));   // tile row on the stacked image
     gs.clamped[slot] = pr.cl | clc;
     depth_keys[slot] = pr.key;

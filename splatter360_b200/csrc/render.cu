@@ -171,7 +171,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     float4 cull, ev, col;
     stage_instance(nx.r0, nx.r1, nx.r2, cull, ev, col);
     const float thr = col.w;
-    const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
+    const bool huge = MODE == S360_MODE_ERP && record_is_wide(nx.r1, nx.r2, halfW);
     const float dval = DEPTH ? -depth_value(dspec, nx.r2.w) : 0.f;   // per-Gaussian value of the fused depth channel (negated like rgb)
     // keep the pipeline full: records of the next chunk, ids of the one after
     nx.gid = gid2;
@@ -402,7 +402,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     float4 cull, ev, col;
     stage_instance(nx.r0, nx.r1, nx.r2, cull, ev, col);
     const float thr = col.w;
-    const bool huge = MODE == S360_MODE_ERP && !(nx.r1.z < halfW - (float)WARP_W);
+    const bool huge = MODE == S360_MODE_ERP && record_is_wide(nx.r1, nx.r2, halfW);
     col.w = __uint_as_float(nx.gid);
     const float nx_depth = nx.r2.w;      // sort depth of this lane's instance (fused depth channel)
     nx.gid = gid2;                       // chunks below the last one are always full

@@ -71,8 +71,10 @@ int s360h_depth_value(int mode, float inv_scale, float near, float far, int n, c
 // centre is block_c; also returns the staged evaluation parameters {A', B', C', log2 o}
 int s360h_cull(int n, const float* rec /*[n,12]*/, const float* block_c /*[n,2]*/, uint8_t* hit, float* ev_out /*[n,4]*/) {
   for (int i = 0; i < n; i++) {
+    // rec: {x, y, conicA, conicB, conicC, opacity, hx, hy, r, g, b, depth}, packed the way K1 packs it
     const float* r = rec + 12 * (size_t)i;
-    const float4 r0 = make_float4(r[0], r[1], r[2], r[3]), r1 = make_float4(r[4], r[5], r[6], r[7]), r2 = make_float4(r[8], r[9], r[10], r[11]);
+    float4 r0, r1, r2;
+    pack_record(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], r + 8, r[11], 1 << 20, r0, r1, r2);
     float4 cull, ev, col;
     stage_instance(r0, r1, r2, cull, ev, col);
     hit[i] = rect_can_contribute(cull, ev, col.w, cull.x - block_c[2 * i], cull.y - block_c[2 * i + 1]) ? 1 : 0;
