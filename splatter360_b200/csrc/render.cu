@@ -284,18 +284,22 @@ int launch_render_forward(const S360View& v, int NV, GeomState g, const uint32_t
 
 // ------------------------------------------------------------------------------------------------
 // Sum eight per-lane values across the warp with a transposed butterfly: after the call every lane
-// holds the complete sum of value index ((lane >> 2) & 7).  9 shuffles instead of 40.
+// holds the complete sum of value index ((lane >> 2) & 7).  9 shuffles instead of 40.  The "which half do I keep" choices
+// are bit-selects with per-lane masks (m16 / m8 / m4 = all ones where that lane-id bit is set): one LOP3 each and no
+// predicate -- with predicates the compiler re-derived three of them per survivor (ISETP), the loop has only seven.
+__device__ __forceinline__ float bsel(float a, float b, uint32_t m) {   // m ? a : b
+  return __uint_as_float((__float_as_uint(a) & m) | (__float_as_uint(b) & ~m));
+}
 __device__ __forceinline__ float warp_reduce8(float v0, float v1, float v2, float v3, float v4, float v5,
-                                              float v6, float v7, int lane) {
+                                              float v6, float v7, uint32_t m16, uint32_t m8, uint32_t m4) {
   const unsigned F = 0xffffffffu;
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-  float w0 = (h16 ? v4 : v0) + __shfl_xor_sync(F, h16 ? v0 : v4, 16);
-  float w1 = (h16 ? v5 : v1) + __shfl_xor_sync(F, h16 ? v1 : v5, 16);
-  float w2 = (h16 ? v6 : v2) + __shfl_xor_sync(F, h16 ? v2 : v6, 16);
-  float w3 = (h16 ? v7 : v3) + __shfl_xor_sync(F, h16 ? v3 : v7, 16);
-  float u0 = (h8 ? w2 : w0) + __shfl_xor_sync(F, h8 ? w0 : w2, 8);
-  float u1 = (h8 ? w3 : w1) + __shfl_xor_sync(F, h8 ? w1 : w3, 8);
-  float s = (h4 ? u1 : u0) + __shfl_xor_sync(F, h4 ? u0 : u1, 4);
+  float w0 = bsel(v4, v0, m16) + __shfl_xor_sync(F, bsel(v0, v4, m16), 16);
+  float w1 = bsel(v5, v1, m16) + __shfl_xor_sync(F, bsel(v1, v5, m16), 16);
+  float w2 = bsel(v6, v2, m16) + __shfl_xor_sync(F, bsel(v2, v6, m16), 16);
+  float w3 = bsel(v7, v3, m16) + __shfl_xor_sync(F, bsel(v3, v7, m16), 16);
+  float u0 = bsel(w2, w0, m8) + __shfl_xor_sync(F, bsel(w0, w2, m8), 8);
+  float u1 = bsel(w3, w1, m8) + __shfl_xor_sync(F, bsel(w1, w3, m8), 8);
+  float s = bsel(u1, u0, m4) + __shfl_xor_sync(F, bsel(u0, u1, m4), 4);
   s += __shfl_xor_sync(F, s, 2);
   s += __shfl_xor_sync(F, s, 1);
   return s;  // value index = 4*bit4 + 2*bit3 + bit2 of the lane id = (lane >> 2) & 7
@@ -373,6 +377,11 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   // dx, dy accurate to an ulp of the (small) distance even at coordinates in the thousands
   const float offx = pxf - wcx;
   const float2 npy = make_float2(-(pyf - wcy), -(pyf + 4.f - wcy));
+  // lane roles of the per-survivor reduction: butterfly masks, and which accumulator slot this lane adds to
+  // (lanes 0, 4, .., 28 hold sums 0..7, lane 1 the ninth, lane 17 the depth channel's tenth; -1: none)
+  const uint32_t m16 = (lane & 16) ? 0xffffffffu : 0u, m8 = (lane & 8) ? 0xffffffffu : 0u, m4 = (lane & 4) ? 0xffffffffu : 0u;
+  const uint32_t m_tail = (lane == 1 || lane == 17) ? 0xffffffffu : 0u;
+  const int red_slot = (lane & 3) == 0 ? ((lane >> 2) & 7) : lane == 1 ? 8 : (DEPTH && lane == 17) ? 9 : -1;
   // instances [0, todo) of this tile's list can matter to this warp's 64 pixels
   const uint32_t todo = __reduce_max_sync(0xffffffffu, max(S.lastc0, S.lastc1));
   const int nchunks = (int)((todo + 31u) >> 5);
@@ -474,14 +483,13 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       v[8] = q.x + q.y;
       v[4] = qy.x + qy.y;
       v[3] = v[8] * dx; v[5] = v[3] * dx; v[6] = v[4] * dx; v[7] = t7.x + t7.y;
-      const float s8 = warp_reduce8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], lane);
+      const float s8 = warp_reduce8(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], m16, m8, m4);
       float v8 = v[8];
       if (DEPTH) {
         // tenth sum: dL/d(depth value) = sum alpha T dL/dD; shares the butterfly of the ninth (upper half-warp)
         const float2 t3 = __fmul2_rn(nw, dpd);
         const float v9 = -(t3.x + t3.y);
-        const bool up = lane & 16;
-        v8 = (up ? v9 : v8) + __shfl_xor_sync(0xffffffffu, up ? v8 : v9, 16);
+        v8 = bsel(v9, v8, m16) + __shfl_xor_sync(0xffffffffu, bsel(v8, v9, m16), 16);
       } else
       v8 += __shfl_xor_sync(0xffffffffu, v8, 16);
       v8 += __shfl_xor_sync(0xffffffffu, v8, 8);
@@ -492,9 +500,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
       // lanes 0,4,..,28 hold sums 0..7, lane 1 holds sum 8.  Conversion to gradients happens once per
       // Gaussian in preprocess_backward_kernel.
       float* dst = acc + (size_t)__float_as_uint(c.w) * ACC_STRIDE;
-      if ((lane & 3) == 0) atomicAdd(dst + ((lane >> 2) & 7), s8);
-      if (lane == 1) atomicAdd(dst + 8, v8);
-      if (DEPTH && lane == 17) atomicAdd(dst + 9, v8);
+      if (red_slot >= 0) atomicAdd(dst + red_slot, bsel(v8, s8, m_tail));   // one RED per role lane
     }
     };
     if (any_wide) replay(std::true_type{}); else replay(std::false_type{});

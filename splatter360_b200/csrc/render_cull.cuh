@@ -24,19 +24,14 @@ constexpr float CULL_MARGIN = 0.004f;                  // log2 units; covers fp3
 // a chunk is three 128-bit loads and a handful of moves instead of a log2, two IEEE reciprocals and ~25 multiplies
 // (measured: the per-chunk prologue was 21 % of the forward kernel's instructions):
 //   r0 = {x, y, A', B'}   r1 = {C', log2 o, kx, ky}   r2 = {r, g, b, depth}
-//   sign bit of r2.x: tight culling disabled for this Gaussian;  sign bit of r2.y: wider than half the panorama (erp)
+//   A' and C' are strictly negative (cov2D + 0.3 I is positive definite), so their sign bits carry two flags:
+//   A' stored POSITIVE: tight culling disabled for this Gaussian;  C' stored POSITIVE: wider than half the panorama (erp).
+//   (Colours cannot carry flags: precomputed colours -- the depth-as-colour pass -- may be negative.)
 // S360_REC_STAGED = 0: r0 = {x, y, conicA, conicB}  r1 = {conicC, opacity, hx, hy}  r2 = {r, g, b, depth} (round 1).
 #ifndef S360_REC_STAGED
 #define S360_REC_STAGED 1
 #endif
 
-S360_HD float s360_neg(float x) {   // set the sign bit (also of +0)
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(__float_as_uint(x) | 0x80000000u);
-#else
-  uint32_t u; __builtin_memcpy(&u, &x, 4); u |= 0x80000000u; __builtin_memcpy(&x, &u, 4); return x;
-#endif
-}
 S360_HD bool s360_signbit(float x) { return (s360_float_bits(x) >> 31) != 0u; }
 
 // hx, hy: half extents of the alpha >= 1/255 box (+inf: tight culling off); image_width only matters in erp mode
@@ -45,11 +40,11 @@ S360_HD void pack_record(float px, float py, float cA, float cB, float cC, float
 #if S360_REC_STAGED
   (void)hy;
   const float A = -0.5f * LOG2E * cA, B = -LOG2E * cB, C = -0.5f * LOG2E * cC;
-  r0 = make_float4(px, py, A, B);
-  r1 = make_float4(C, log2f(op), -0.5f * B / A, -0.5f * B / C);
   const bool nocull = !(hx < 3.0e38f);
   const bool huge = !(hx < 0.5f * (float)image_width - (float)WARP_W);
-  r2 = make_float4(nocull ? s360_neg(col[0]) : col[0], huge ? s360_neg(col[1]) : col[1], col[2], depth);
+  r0 = make_float4(px, py, nocull ? fabsf(A) : -fabsf(A), B);
+  r1 = make_float4(huge ? fabsf(C) : -fabsf(C), log2f(op), -0.5f * B / A, -0.5f * B / C);
+  r2 = make_float4(col[0], col[1], col[2], depth);
 #else
   (void)image_width;
   r0 = make_float4(px, py, cA, cB);
@@ -61,9 +56,9 @@ S360_HD void pack_record(float px, float py, float cA, float cB, float cC, float
 // inverse of pack_record for the debug unpackers: conic, opacity, colour
 S360_HD void unpack_record(const float4& r0, const float4& r1, const float4& r2, float* conic_op, float* rgb) {
 #if S360_REC_STAGED
-  conic_op[0] = r0.z / (-0.5f * LOG2E); conic_op[1] = r0.w / -LOG2E; conic_op[2] = r1.x / (-0.5f * LOG2E);
+  conic_op[0] = fabsf(r0.z) / (0.5f * LOG2E); conic_op[1] = r0.w / -LOG2E; conic_op[2] = fabsf(r1.x) / (0.5f * LOG2E);
   conic_op[3] = exp2f(r1.y);
-  rgb[0] = fabsf(r2.x); rgb[1] = fabsf(r2.y); rgb[2] = r2.z;
+  rgb[0] = r2.x; rgb[1] = r2.y; rgb[2] = r2.z;
 #else
   conic_op[0] = r0.z; conic_op[1] = r0.w; conic_op[2] = r1.x; conic_op[3] = r1.y;
   rgb[0] = r2.x; rgb[1] = r2.y; rgb[2] = r2.z;
@@ -73,8 +68,8 @@ S360_HD void unpack_record(const float4& r0, const float4& r1, const float4& r2,
 // erp: does this Gaussian need the per-pixel seam wrap (wider than half the panorama minus a warp block)?
 S360_HD bool record_is_wide(const float4& r1, const float4& r2, float halfW) {
 #if S360_REC_STAGED
-  (void)r1; (void)halfW;
-  return s360_signbit(r2.y);
+  (void)r2; (void)halfW;
+  return !s360_signbit(r1.x);
 #else
   (void)r2;
   return !(r1.z < halfW - (float)WARP_W);
@@ -87,10 +82,10 @@ S360_HD bool record_is_wide(const float4& r1, const float4& r2, float halfW) {
 S360_HD void stage_instance(const float4& r0, const float4& r1, const float4& r2, float4& cull,
                                                float4& ev, float4& col) {
 #if S360_REC_STAGED
-  ev = make_float4(r0.z, r0.w, r1.x, r1.y);
+  ev = make_float4(-fabsf(r0.z), r0.w, -fabsf(r1.x), r1.y);
   cull = make_float4(r0.x, r0.y, r1.z, r1.w);
-  const float thr = s360_signbit(r2.x) ? -s360_inf() : (LOG2_ALPHA_MIN - CULL_MARGIN) - r1.y;
-  col = make_float4(fabsf(r2.x), fabsf(r2.y), r2.z, thr);
+  const float thr = s360_signbit(r0.z) ? (LOG2_ALPHA_MIN - CULL_MARGIN) - r1.y : -s360_inf();
+  col = make_float4(r2.x, r2.y, r2.z, thr);
 #else
   const float A = -0.5f * LOG2E * r0.z, B = -LOG2E * r0.w, C = -0.5f * LOG2E * r1.x;
 #ifdef __CUDA_ARCH__

@@ -306,3 +306,21 @@ def test_float32_noise_floor_of_the_gradients(tmp_path):
     assert rel_l2(res["fma"][0]["color"], res["base"][0]["color"]) < 2e-5
     assert worst_smooth < 3e-5, worst_smooth
     assert worst_white > 2 * worst_smooth, (worst_white, worst_smooth)
+
+
+@pytest.mark.parametrize("mode,H,W", [("pinhole", 48, 64), ("erp", 32, 64)])
+def test_float64_build_of_the_c_oracle_matches_autograd_oracle(mode, H, W):
+    """oracle.render(..., f64=True): the same C source with every float as double -- the reference the float32 paths are
+    measured against at the BASELINE sizes.  Against float64 autograd it agrees to the float32 rounding of the algorithm's
+    constants (0.3f, 1.3f, the SH constants keep their float32 values in the C build)."""
+    case = make_case(120, mode, H, W, seed=5)
+    dL = torch.randn(3, H, W, generator=torch.Generator().manual_seed(2))
+    o64 = run_oracle(case, dL=dL, f64=True)
+    o32 = run_oracle(case, dL=dL)
+    col, aux, g = _torch_oracle(case, dL)
+    assert o64["color"].dtype == np.float64
+    assert rel_l2(o64["color"], col) < 2e-7
+    assert np.array_equal(o64["inst_gid"], o32["inst_gid"]) and np.array_equal(o64["radii"], o32["radii"])
+    for k, v in g.items():
+        assert rel_l2(o64[k], v) < 2e-6, k
+        assert rel_l2(o64[k], v) < rel_l2(o32[k], v), k     # and it is closer to autograd than the float32 build
