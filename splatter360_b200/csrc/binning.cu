@@ -719,8 +719,10 @@ int launch_mb_count(const S360View& v, int NV, int64_t n_items, const uint32_t* 
   const int ntiles = gx * gy;
   const int chunks = (int)((n_items + MB_CHUNK - 1) / MB_CHUNK);
   if (chunks == 0) return 0;
-  mb_count_kernel<8><<<chunks, 256, (size_t)ntiles * 4, st>>>((int)n_items, n_dev, gx, ntiles, v.mode, g.rect, depth_order,
-                                                              (uint32_t*)scratch);
+  // 16 warps per chunk: the per-warp work (rounds of 32 Gaussians, each a chain of shuffles and shared-memory atomics) is
+  // latency-bound, so more and shorter chains win (8 warps: 25 us, measured)
+  mb_count_kernel<16><<<chunks, 512, (size_t)ntiles * 4, st>>>((int)n_items, n_dev, gx, ntiles, v.mode, g.rect, depth_order,
+                                                               (uint32_t*)scratch);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -741,19 +743,16 @@ int launch_mb_scatter(const S360View& v, int NV, int64_t n_items, const uint32_t
   const int ntiles = gx * gy;
   const int chunks = (int)((n_items + MB_CHUNK - 1) / MB_CHUNK);
   if (chunks == 0) return 0;
-  // 8 warps per chunk up to 4096 tiles, 4 warps above: shared memory per CTA stays <= 96 KB (two CTAs per SM)
-  const bool wide = ntiles > 4096;
-  const size_t smem = (size_t)ntiles * 4 + (size_t)(wide ? 4 : 8) * ((ntiles + 1) / 2) * 4;
+  // warps per chunk: as many as the per-warp tile counters (u16 x tiles each) allow within ~100 KB of shared memory
+  const int nw = ntiles <= 2048 ? 16 : ntiles <= 4096 ? 8 : 4;
+  const size_t smem = (size_t)ntiles * 4 + (size_t)nw * ((ntiles + 1) / 2) * 4;
   const uint32_t* prefix = (const uint32_t*)scratch;
-  if (wide) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mb_scatter_kernel<4><<<chunks, 128, smem, st>>>((int)n_items, n_dev, gx, ntiles, mb_tile_bits(ntiles), v.mode, g.rect,
-                                                    depth_order, prefix, ranges, capacity, point_list, counters);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    mb_scatter_kernel<8><<<chunks, 256, smem, st>>>((int)n_items, n_dev, gx, ntiles, mb_tile_bits(ntiles), v.mode, g.rect,
-                                                    depth_order, prefix, ranges, capacity, point_list, counters);
-  }
+#define S360_SCATTER(NW_) do { \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    mb_scatter_kernel<NW_><<<chunks, NW_ * 32, smem, st>>>((int)n_items, n_dev, gx, ntiles, mb_tile_bits(ntiles), v.mode, g.rect, \
+                                                         depth_order, prefix, ranges, capacity, point_list, counters); } while (0)
+  if (nw == 16) S360_SCATTER(16); else if (nw == 8) S360_SCATTER(8); else S360_SCATTER(4);
+#undef S360_SCATTER
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -24,6 +24,8 @@ struct GeomState {
   float4* rec;        // [P*3]
   uint2* rect;        // [P] packed tile rect: x = (x0 & 0xffff) | nx << 16 ; y = y0 | ny << 16
   uint8_t* clamped;   // [P] bits 0..2 SH clamp per channel, bit 3 = jacobian clamp x, bit 4 = clamp y
+  float* sh_jac;      // [P*9] d rgb_c / d dir_a of the SH colour (single-view path; NULL in the batched path): K1 has the SH
+                      // block in shared memory anyway, and with these 36 B the backward never reads the 300-B SH row again
 };
 
 struct ImageState {
@@ -55,18 +57,25 @@ S360_HD uint32_t s360_float_bits(float x) {
 #endif
 }
 
-inline GeomState carve_geom(void* buf, int P) {
+inline size_t geom_base_bytes(int P) {
+  return align_up((size_t)P * REC_F4 * sizeof(float4), 256) + align_up((size_t)P * sizeof(uint2), 256) +
+         align_up((size_t)P, 256);
+}
+inline GeomState carve_geom_base(void* buf, int P) {
   char* p = (char*)buf;
   GeomState g;
   g.rec = (float4*)p;      p += align_up((size_t)P * REC_F4 * sizeof(float4), 256);
   g.rect = (uint2*)p;      p += align_up((size_t)P * sizeof(uint2), 256);
   g.clamped = (uint8_t*)p; p += align_up((size_t)P, 256);
+  g.sh_jac = nullptr;
   return g;
 }
-inline size_t geom_bytes(int P) {
-  return align_up((size_t)P * REC_F4 * sizeof(float4), 256) + align_up((size_t)P * sizeof(uint2), 256) +
-         align_up((size_t)P, 256);
+inline GeomState carve_geom(void* buf, int P) {
+  GeomState g = carve_geom_base(buf, P);
+  g.sh_jac = (float*)((char*)buf + geom_base_bytes(P));
+  return g;
 }
+inline size_t geom_bytes(int P) { return geom_base_bytes(P) + align_up((size_t)P * 9 * sizeof(float), 256); }
 // Per-Gaussian bookkeeping of the batched multi-view path: which views the Gaussian has a pair in, and where its
 // pairs start in the compacted pair buffers (pair of view v = base + popc(mask & ((1 << v) - 1))).
 struct PairState {
@@ -76,14 +85,14 @@ struct PairState {
 };
 // geometry state of the batched path: pair-indexed GeomState for `cap` pairs followed by the per-Gaussian PairState
 inline GeomState carve_geom_multi(void* buf, int P, int64_t cap, PairState* ps) {
-  GeomState g = carve_geom(buf, (int)cap);
-  char* p = (char*)buf + geom_bytes((int)cap);
+  GeomState g = carve_geom_base(buf, (int)cap);
+  char* p = (char*)buf + geom_base_bytes((int)cap);
   ps->base = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
   ps->mask = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
   ps->count = (uint32_t*)p;
   return g;
 }
-inline size_t geom_multi_bytes(int P, int64_t cap) { return geom_bytes((int)cap) + 2 * align_up((size_t)P * 4, 256) + 256; }
+inline size_t geom_multi_bytes(int P, int64_t cap) { return geom_base_bytes((int)cap) + 2 * align_up((size_t)P * 4, 256) + 256; }
 
 // V views are laid out as one stacked image: pixel state [V][H][W], tiles [V][gy][gx] (V = 1: the single view)
 inline ImageState carve_image(void* buf, int H, int W, int V = 1) {
@@ -405,6 +414,17 @@ S360_HD void sh_grad_dot(int deg, float x, float y, float z, S&& s, float* d) {
   S360_T(23, sh_c4(7) * z * (3.f * xx - 3.f * yy), sh_c4(7) * -6.f * xy * z, sh_c4(7) * x * (xx - 3.f * yy))
   S360_T(24, sh_c4(8) * (4.f * xx * x - 12.f * x * yy), sh_c4(8) * (-12.f * xx * y + 4.f * yy * y), 0.f)
 #undef S360_T
+}
+
+// J[c][a] = sum_k (d b_k / d a) sh(k, c): Jacobian of the three SH colour channels w.r.t. the (unnormalised) view direction;
+// sh(k, c) is a callable.  The three inlined copies share the basis-derivative expressions.
+template <class S>
+S360_HD void sh_colour_jacobian(int deg, float x, float y, float z, S&& sh, float* J /* [3][3] */) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    J[3 * c] = J[3 * c + 1] = J[3 * c + 2] = 0.f;
+    sh_grad_dot(deg, x, y, z, [&](int k) { return sh(k, c); }, J + 3 * c);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

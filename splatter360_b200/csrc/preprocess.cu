@@ -100,7 +100,19 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
         for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];
         __syncthreads();
       }
-      if (want_color) sh_to_rgb(v, s_sh + threadIdx.x * row, mx, my, mz, cam.cam, col, cl);
+      if (want_color) {
+        const float* sh = s_sh + threadIdx.x * row;
+        sh_to_rgb(v, sh, mx, my, mz, cam.cam, col, cl);
+        // d rgb / d direction for the backward pass (36 B per Gaussian instead of re-reading the 300-B SH row there)
+        float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
+        const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
+        const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
+        float J[9];
+        sh_colour_jacobian(min(v.sh_degree, v.max_sh_degree), ox * inv, oy * inv, oz * inv,
+                           [&](int k, int c) { return sh[ks * k + cs * c]; }, J);
+#pragma unroll
+        for (int k = 0; k < 9; k++) gs.sh_jac[9 * (size_t)idx + k] = J[k];
+      }
     }
   } else if (want_color) {
     col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
@@ -136,38 +148,30 @@ int launch_preprocess(const S360View& v, const float* means, const float* cov, c
 
 // ------------------------------------------------------------------------------------------------
 // K8 + K9 fused.  acc[idx*12 + 0..8] = {dL/dr, dL/dg, dL/db, and the moments sum(q dx), sum(q dy), sum(q dx^2),
-// sum(q dx dy), sum(q dy^2), sum(q)} with q = G dL/dalpha, accumulated by render_backward_kernel
+// sum(q dx dy), sum(q dy^2), sum(q)} with q = G dL/dalpha, accumulated by render_backward_kernel.
+// The SH coefficients are NOT read here: dL/dSH = basis(dir) x dL/drgb needs only the direction, and the direction
+// gradient of the colour uses the 3x3 Jacobian K1 stored (gs.sh_jac) -- 36 B instead of the 300-B SH row per Gaussian.
+// The CTA's dL/dSH block (128 x 300 B) is assembled in shared memory and leaves by one TMA bulk store.
 template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_backward_kernel(const S360View v, const float* __restrict__ means, const float* __restrict__ cov3D,
-                           const float* __restrict__ opac, const float* __restrict__ shs, GeomState gs, const int32_t* __restrict__ radii,
+                           const float* __restrict__ opac, const bool has_sh, GeomState gs, const int32_t* __restrict__ radii,
                            const float* __restrict__ acc, float* __restrict__ d_means,
                            float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
                            float* __restrict__ d_shs, float* __restrict__ d_colors, const DepthSpec dspec) {
-  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
-  __shared__ uint64_t s_bar;
+  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: dL/dSH of this CTA
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = v.P;
   const int row = v.M * 3;
   const int rows = min(PRE_THREADS, P - blockIdx.x * PRE_THREADS);
-  const float* sh_src = shs ? shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
-  float* dsh_dst = shs ? d_shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
+  float* dsh_dst = has_sh ? d_shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
   const uint32_t sh_bytes = (uint32_t)rows * row * 4u;
-  const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u) &&
-                       ((reinterpret_cast<uintptr_t>(dsh_dst) & 15u) == 0u);
+  const bool bulk_ok = has_sh && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(dsh_dst) & 15u) == 0u);
   const bool vis = idx < P && radii[idx] > 0;
   bool need = false;
-  if (shs) {
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  if (has_sh) {
     need = __syncthreads_or(vis);
-    if (need) {
-      if (bulk_ok) {
-        if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, sh_bytes); bulk_load(s_sh, sh_src, sh_bytes, &s_bar); }
-      } else {
-        for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];
-        __syncthreads();
-      }
-    } else {
+    if (!need) {
       // nothing visible in this block: the SH gradient block is all zeros
       for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) dsh_dst[i] = 0.f;
     }
@@ -194,42 +198,35 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
     const float op = opac[idx];
     view_backward<MODE, DEPTH>(v, V, cam.PM, mx, my, mz, cv, op, a0, a1, dm, dm2, dcov, dspec,
                                DEPTH ? acc[(size_t)idx * ACC_STRIDE + 9] : 0.f);
-    if (shs != nullptr) {
+    if (has_sh) {
       const float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
       const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
       const float dx = ox * inv, dy = oy * inv, dz = oz * inv;
       const int deg = min(v.sh_degree, v.max_sh_degree);
-      float b[25], bx[25], by[25], bz[25];
-      const int n = sh_basis(deg, dx, dy, dz, b);
-      sh_basis_grad(deg, dx, dy, dz, bx, by, bz);
       const uint8_t cl = gs.clamped[idx];
       const float drgb[3] = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
-      if (bulk_ok) mbar_wait(&s_bar, 0);
-      float* sh = s_sh + threadIdx.x * row;      // this thread's row: read SH, overwrite with dL/dSH
-      const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
-      float ddir[3] = {0.f, 0.f, 0.f};
+      // direction gradient of the colour through K1's Jacobian, then through the normalisation
+      const float* J = gs.sh_jac + 9 * (size_t)idx;
+      float ddir[3];
 #pragma unroll
-      for (int k = 0; k < 25; k++) {
-        if (k < n) {
-          const float s = sh[ks * k] * drgb[0] + sh[ks * k + cs] * drgb[1] + sh[ks * k + 2 * cs] * drgb[2];
-          ddir[0] += bx[k] * s; ddir[1] += by[k] * s; ddir[2] += bz[k] * s;
-          sh[ks * k] = b[k] * drgb[0]; sh[ks * k + cs] = b[k] * drgb[1]; sh[ks * k + 2 * cs] = b[k] * drgb[2];
-        }
-      }
-      for (int k = n; k < v.M; k++) { sh[ks * k] = 0.f; sh[ks * k + cs] = 0.f; sh[ks * k + 2 * cs] = 0.f; }
+      for (int a = 0; a < 3; a++) ddir[a] = J[a] * drgb[0] + J[3 + a] * drgb[1] + J[6 + a] * drgb[2];
       const float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
       dm[0] += (ddir[0] - dx * dot) * inv;
       dm[1] += (ddir[1] - dy * dot) * inv;
       dm[2] += (ddir[2] - dz * dot) * inv;
+      // dL/dSH row: basis(dir) x dL/drgb, zeros beyond the active degree
+      float* sh = s_sh + threadIdx.x * row;
+      const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
+      const int n = sh_basis_each(deg, dx, dy, dz, [&](int k, float b) {
+        sh[ks * k] = b * drgb[0]; sh[ks * k + cs] = b * drgb[1]; sh[ks * k + 2 * cs] = b * drgb[2]; });
+      for (int k = n; k < v.M; k++) { sh[ks * k] = 0.f; sh[ks * k + cs] = 0.f; sh[ks * k + 2 * cs] = 0.f; }
     }
-  } else if (shs != nullptr && need && idx < P) {
-    if (bulk_ok) mbar_wait(&s_bar, 0);
+  } else if (has_sh && need && idx < P) {
     float* sh = s_sh + threadIdx.x * row;
     for (int k = 0; k < row; k++) sh[k] = 0.f;
   }
-  if (shs != nullptr && need) {
+  if (has_sh && need) {
     if (bulk_ok) {
-      if (idx >= P) mbar_wait(&s_bar, 0);
       fence_async_smem();
       __syncthreads();
       if (threadIdx.x == 0) { bulk_store(dsh_dst, s_sh, sh_bytes); bulk_store_wait_read(); }
@@ -247,7 +244,7 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
   store_dcov(v, d_cov, idx, dcov, gsc * gsc);
   d_opac[idx] = dop;
   if (d_colors != nullptr) {
-    const bool pre = shs == nullptr;
+    const bool pre = !has_sh;
 #pragma unroll
     for (int k = 0; k < 3; k++) d_colors[3 * idx + k] = pre ? dcol[k] : 0.f;
   }
@@ -265,7 +262,7 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
 #define S360_LAUNCH_K8(MODE_, DEPTH_) do { \
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    preprocess_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
+    preprocess_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs != nullptr, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
   if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_K8(S360_MODE_PINHOLE, true); else S360_LAUNCH_K8(S360_MODE_PINHOLE, false); }
   else { if (has_depth) S360_LAUNCH_K8(S360_MODE_ERP, true); else S360_LAUNCH_K8(S360_MODE_ERP, false); }
 #undef S360_LAUNCH_K8
