@@ -242,9 +242,12 @@ def run_ours(args):
     launches = _lib.launch_count() - l0
     stages = _lib.profile_read(reset=True)
     if graphed is not None:
-        # per-stage times and the launch count of the SAME step run eagerly (outside the timed region): a replayed graph
-        # launches exactly the kernels its capture recorded
+        # per-stage times and the launch count of the SAME steps run eagerly right after the timed region (stage events
+        # cannot be recorded inside a replayed graph; a replay launches exactly the kernels its capture recorded)
+        from splatter360_b200 import rasterizer as R_
         tr = CapacityTracker()
+        mse_grad = lambda c_: 2.0 * (c_ - target) / c_.numel()
+
         def eager(i):
             s_ = GaussianRasterizationSettings(
                 image_height=H, image_width=W, tanfovx=1.0, tanfovy=1.0, bg=bg, scale_modifier=1.0, viewmatrix=cams.view_matrix[i],
@@ -252,8 +255,7 @@ def run_ours(args):
                 projection="erp", capacity_tracker=tr)
             c_, st_ = R_.forward_raw(s_, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), None)
             R_.backward_raw(s_, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), None, st_, mse_grad(c_))
-        from splatter360_b200 import rasterizer as R_
-        mse_grad = lambda c_: 2.0 * (c_ - target) / c_.numel()
+
         for i in range(3):
             eager(Wm + i)
         torch.cuda.synchronize()
@@ -542,31 +544,6 @@ def run_config5(args):
     _lib.profile_enable(False)
     launches = _lib.launch_count() - l0
     stages = _lib.profile_read(reset=True)
-    if graphed is not None:
-        # per-stage times and the launch count of the SAME step run eagerly (outside the timed region): a replayed graph
-        # launches exactly the kernels its capture recorded
-        tr = CapacityTracker()
-        def eager(i):
-            s_ = GaussianRasterizationSettings(
-                image_height=H, image_width=W, tanfovx=1.0, tanfovy=1.0, bg=bg, scale_modifier=1.0, viewmatrix=cams.view_matrix[i],
-                projmatrix=cams.full_projection[i], sh_degree=SH_DEGREE, campos=cams.campos[i], prefiltered=False, debug=False,
-                projection="erp", capacity_tracker=tr)
-            c_, st_ = R_.forward_raw(s_, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), None)
-            R_.backward_raw(s_, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), None, st_, mse_grad(c_))
-        from splatter360_b200 import rasterizer as R_
-        mse_grad = lambda c_: 2.0 * (c_ - target) / c_.numel()
-        for i in range(3):
-            eager(Wm + i)
-        torch.cuda.synchronize()
-        _lib.profile_read(reset=True); _lib.profile_enable(True)
-        l1 = _lib.launch_count()
-        n_e = min(K, 20)
-        for i in range(n_e):
-            eager(Wm + i)
-        torch.cuda.synchronize()
-        _lib.profile_enable(False)
-        launches = (_lib.launch_count() - l1 + n_e) * K // n_e   # + the fused loss kernel of the graphed step
-        stages = _lib.profile_read(reset=True)
     if tracker is not None:
         tracker.flush()
         if tracker.overflowed:
@@ -688,31 +665,6 @@ def run_config4(args):
     _lib.profile_enable(False)
     launches = _lib.launch_count() - l0
     stages = _lib.profile_read(reset=True)
-    if graphed is not None:
-        # per-stage times and the launch count of the SAME step run eagerly (outside the timed region): a replayed graph
-        # launches exactly the kernels its capture recorded
-        tr = CapacityTracker()
-        def eager(i):
-            s_ = GaussianRasterizationSettings(
-                image_height=H, image_width=W, tanfovx=1.0, tanfovy=1.0, bg=bg, scale_modifier=1.0, viewmatrix=cams.view_matrix[i],
-                projmatrix=cams.full_projection[i], sh_degree=SH_DEGREE, campos=cams.campos[i], prefiltered=False, debug=False,
-                projection="erp", capacity_tracker=tr)
-            c_, st_ = R_.forward_raw(s_, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), None)
-            R_.backward_raw(s_, means.detach(), cov6.detach(), opac.detach().reshape(-1), shs.detach(), None, st_, mse_grad(c_))
-        from splatter360_b200 import rasterizer as R_
-        mse_grad = lambda c_: 2.0 * (c_ - target) / c_.numel()
-        for i in range(3):
-            eager(Wm + i)
-        torch.cuda.synchronize()
-        _lib.profile_read(reset=True); _lib.profile_enable(True)
-        l1 = _lib.launch_count()
-        n_e = min(K, 20)
-        for i in range(n_e):
-            eager(Wm + i)
-        torch.cuda.synchronize()
-        _lib.profile_enable(False)
-        launches = (_lib.launch_count() - l1 + n_e) * K // n_e   # + the fused loss kernel of the graphed step
-        stages = _lib.profile_read(reset=True)
     ovf = []
     if dec.capacity_trackers:
         for t in dec.capacity_trackers.values():

@@ -295,136 +295,89 @@ S360_HD constexpr float sh_c4(int i) {
   return t[i];
 }
 
-// basis values for all 25 slots (unused bands are left untouched); returns number of active coeffs
-S360_HD int sh_basis(int deg, float x, float y, float z, float* b) {
-  b[0] = SH_C0;
+// ONE list of the 25 basis polynomials and their partial derivatives w.r.t. (x, y, z) taken as independent variables:
+// f(k, b_k, db_k/dx, db_k/dy, db_k/dz) is called for every active coefficient, in order; returns their number.  Everything
+// below is a thin wrapper (unused values are dead code to the compiler), so no 25-float array needs to be live anywhere.
+template <class F>
+S360_HD int sh_terms(int deg, float x, float y, float z, F&& f) {
+  f(0, SH_C0, 0.f, 0.f, 0.f);
   if (deg < 1) return 1;
-  b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+  f(1, -SH_C1 * y, 0.f, -SH_C1, 0.f);
+  f(2, SH_C1 * z, 0.f, 0.f, SH_C1);
+  f(3, -SH_C1 * x, -SH_C1, 0.f, 0.f);
   if (deg < 2) return 4;
   const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  b[4] = sh_c2(0) * xy; b[5] = sh_c2(1) * yz; b[6] = sh_c2(2) * (2.f * zz - xx - yy);
-  b[7] = sh_c2(3) * xz; b[8] = sh_c2(4) * (xx - yy);
+  f(4, sh_c2(0) * xy, sh_c2(0) * y, sh_c2(0) * x, 0.f);
+  f(5, sh_c2(1) * yz, 0.f, sh_c2(1) * z, sh_c2(1) * y);
+  f(6, sh_c2(2) * (2.f * zz - xx - yy), sh_c2(2) * -2.f * x, sh_c2(2) * -2.f * y, sh_c2(2) * 4.f * z);
+  f(7, sh_c2(3) * xz, sh_c2(3) * z, 0.f, sh_c2(3) * x);
+  f(8, sh_c2(4) * (xx - yy), sh_c2(4) * 2.f * x, sh_c2(4) * -2.f * y, 0.f);
   if (deg < 3) return 9;
-  b[9] = sh_c3(0) * y * (3.f * xx - yy);
-  b[10] = sh_c3(1) * xy * z;
-  b[11] = sh_c3(2) * y * (4.f * zz - xx - yy);
-  b[12] = sh_c3(3) * z * (2.f * zz - 3.f * xx - 3.f * yy);
-  b[13] = sh_c3(4) * x * (4.f * zz - xx - yy);
-  b[14] = sh_c3(5) * z * (xx - yy);
-  b[15] = sh_c3(6) * x * (xx - 3.f * yy);
+  f(9, sh_c3(0) * y * (3.f * xx - yy), sh_c3(0) * 6.f * xy, sh_c3(0) * (3.f * xx - 3.f * yy), 0.f);
+  f(10, sh_c3(1) * xy * z, sh_c3(1) * yz, sh_c3(1) * xz, sh_c3(1) * xy);
+  f(11, sh_c3(2) * y * (4.f * zz - xx - yy), sh_c3(2) * -2.f * xy, sh_c3(2) * (4.f * zz - xx - 3.f * yy), sh_c3(2) * 8.f * yz);
+  f(12, sh_c3(3) * z * (2.f * zz - 3.f * xx - 3.f * yy), sh_c3(3) * -6.f * xz, sh_c3(3) * -6.f * yz,
+    sh_c3(3) * (6.f * zz - 3.f * xx - 3.f * yy));
+  f(13, sh_c3(4) * x * (4.f * zz - xx - yy), sh_c3(4) * (4.f * zz - 3.f * xx - yy), sh_c3(4) * -2.f * xy, sh_c3(4) * 8.f * xz);
+  f(14, sh_c3(5) * z * (xx - yy), sh_c3(5) * 2.f * xz, sh_c3(5) * -2.f * yz, sh_c3(5) * (xx - yy));
+  f(15, sh_c3(6) * x * (xx - 3.f * yy), sh_c3(6) * (3.f * xx - 3.f * yy), sh_c3(6) * -6.f * xy, 0.f);
   if (deg < 4) return 16;
-  b[16] = sh_c4(0) * xy * (xx - yy);
-  b[17] = sh_c4(1) * yz * (3.f * xx - yy);
-  b[18] = sh_c4(2) * xy * (7.f * zz - 1.f);
-  b[19] = sh_c4(3) * yz * (7.f * zz - 3.f);
-  b[20] = sh_c4(4) * (zz * (35.f * zz - 30.f) + 3.f);
-  b[21] = sh_c4(5) * xz * (7.f * zz - 3.f);
-  b[22] = sh_c4(6) * (xx - yy) * (7.f * zz - 1.f);
-  b[23] = sh_c4(7) * xz * (xx - 3.f * yy);
-  b[24] = sh_c4(8) * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy));
+  f(16, sh_c4(0) * xy * (xx - yy), sh_c4(0) * (3.f * xx * y - yy * y), sh_c4(0) * (xx * x - 3.f * x * yy), 0.f);
+  f(17, sh_c4(1) * yz * (3.f * xx - yy), sh_c4(1) * 6.f * xy * z, sh_c4(1) * z * (3.f * xx - 3.f * yy), sh_c4(1) * y * (3.f * xx - yy));
+  f(18, sh_c4(2) * xy * (7.f * zz - 1.f), sh_c4(2) * y * (7.f * zz - 1.f), sh_c4(2) * x * (7.f * zz - 1.f), sh_c4(2) * 14.f * xy * z);
+  f(19, sh_c4(3) * yz * (7.f * zz - 3.f), 0.f, sh_c4(3) * z * (7.f * zz - 3.f), sh_c4(3) * y * (21.f * zz - 3.f));
+  f(20, sh_c4(4) * (zz * (35.f * zz - 30.f) + 3.f), 0.f, 0.f, sh_c4(4) * (140.f * zz * z - 60.f * z));
+  f(21, sh_c4(5) * xz * (7.f * zz - 3.f), sh_c4(5) * z * (7.f * zz - 3.f), 0.f, sh_c4(5) * x * (21.f * zz - 3.f));
+  f(22, sh_c4(6) * (xx - yy) * (7.f * zz - 1.f), sh_c4(6) * 2.f * x * (7.f * zz - 1.f), sh_c4(6) * -2.f * y * (7.f * zz - 1.f),
+    sh_c4(6) * (xx - yy) * 14.f * z);
+  f(23, sh_c4(7) * xz * (xx - 3.f * yy), sh_c4(7) * z * (3.f * xx - 3.f * yy), sh_c4(7) * -6.f * xy * z, sh_c4(7) * x * (xx - 3.f * yy));
+  f(24, sh_c4(8) * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy)), sh_c4(8) * (4.f * xx * x - 12.f * x * yy),
+    sh_c4(8) * (-12.f * xx * y + 4.f * yy * y), 0.f);
   return 25;
+}
+
+// basis values for all 25 slots (unused bands are left untouched); returns number of active coeffs
+S360_HD int sh_basis(int deg, float x, float y, float z, float* b) {
+  return sh_terms(deg, x, y, z, [&](int k, float v, float, float, float) { b[k] = v; });
 }
 
 // partial derivatives of the basis polynomials w.r.t. (x, y, z) taken as independent variables
 S360_HD void sh_basis_grad(int deg, float x, float y, float z, float* bx, float* by, float* bz) {
-  bx[0] = by[0] = bz[0] = 0.f;
-  if (deg < 1) return;
-  bx[1] = 0.f; by[1] = -SH_C1; bz[1] = 0.f;
-  bx[2] = 0.f; by[2] = 0.f; bz[2] = SH_C1;
-  bx[3] = -SH_C1; by[3] = 0.f; bz[3] = 0.f;
-  if (deg < 2) return;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  bx[4] = sh_c2(0) * y; by[4] = sh_c2(0) * x; bz[4] = 0.f;
-  bx[5] = 0.f; by[5] = sh_c2(1) * z; bz[5] = sh_c2(1) * y;
-  bx[6] = sh_c2(2) * -2.f * x; by[6] = sh_c2(2) * -2.f * y; bz[6] = sh_c2(2) * 4.f * z;
-  bx[7] = sh_c2(3) * z; by[7] = 0.f; bz[7] = sh_c2(3) * x;
-  bx[8] = sh_c2(4) * 2.f * x; by[8] = sh_c2(4) * -2.f * y; bz[8] = 0.f;
-  if (deg < 3) return;
-  bx[9] = sh_c3(0) * 6.f * xy; by[9] = sh_c3(0) * (3.f * xx - 3.f * yy); bz[9] = 0.f;
-  bx[10] = sh_c3(1) * yz; by[10] = sh_c3(1) * xz; bz[10] = sh_c3(1) * xy;
-  bx[11] = sh_c3(2) * -2.f * xy; by[11] = sh_c3(2) * (4.f * zz - xx - 3.f * yy); bz[11] = sh_c3(2) * 8.f * yz;
-  bx[12] = sh_c3(3) * -6.f * xz; by[12] = sh_c3(3) * -6.f * yz; bz[12] = sh_c3(3) * (6.f * zz - 3.f * xx - 3.f * yy);
-  bx[13] = sh_c3(4) * (4.f * zz - 3.f * xx - yy); by[13] = sh_c3(4) * -2.f * xy; bz[13] = sh_c3(4) * 8.f * xz;
-  bx[14] = sh_c3(5) * 2.f * xz; by[14] = sh_c3(5) * -2.f * yz; bz[14] = sh_c3(5) * (xx - yy);
-  bx[15] = sh_c3(6) * (3.f * xx - 3.f * yy); by[15] = sh_c3(6) * -6.f * xy; bz[15] = 0.f;
-  if (deg < 4) return;
-  bx[16] = sh_c4(0) * (3.f * xx * y - yy * y); by[16] = sh_c4(0) * (xx * x - 3.f * x * yy); bz[16] = 0.f;
-  bx[17] = sh_c4(1) * 6.f * xy * z; by[17] = sh_c4(1) * z * (3.f * xx - 3.f * yy); bz[17] = sh_c4(1) * y * (3.f * xx - yy);
-  bx[18] = sh_c4(2) * y * (7.f * zz - 1.f); by[18] = sh_c4(2) * x * (7.f * zz - 1.f); bz[18] = sh_c4(2) * 14.f * xy * z;
-  bx[19] = 0.f; by[19] = sh_c4(3) * z * (7.f * zz - 3.f); bz[19] = sh_c4(3) * y * (21.f * zz - 3.f);
-  bx[20] = 0.f; by[20] = 0.f; bz[20] = sh_c4(4) * (140.f * zz * z - 60.f * z);
-  bx[21] = sh_c4(5) * z * (7.f * zz - 3.f); by[21] = 0.f; bz[21] = sh_c4(5) * x * (21.f * zz - 3.f);
-  bx[22] = sh_c4(6) * 2.f * x * (7.f * zz - 1.f); by[22] = sh_c4(6) * -2.f * y * (7.f * zz - 1.f);
-  bz[22] = sh_c4(6) * (xx - yy) * 14.f * z;
-  bx[23] = sh_c4(7) * z * (3.f * xx - 3.f * yy); by[23] = sh_c4(7) * -6.f * xy * z; bz[23] = sh_c4(7) * x * (xx - 3.f * yy);
-  bx[24] = sh_c4(8) * (4.f * xx * x - 12.f * x * yy); by[24] = sh_c4(8) * (-12.f * xx * y + 4.f * yy * y); bz[24] = 0.f;
+  sh_terms(deg, x, y, z, [&](int k, float, float gx, float gy, float gz) { bx[k] = gx; by[k] = gy; bz[k] = gz; });
 }
 
-// f(k, b_k) for every active basis function, one at a time (no 25-float array live); returns the number of coefficients
+// f(k, b_k) for every active basis function, one at a time; returns the number of coefficients
 template <class F>
 S360_HD int sh_basis_each(int deg, float x, float y, float z, F&& f) {
-  f(0, SH_C0);
-  if (deg < 1) return 1;
-  f(1, -SH_C1 * y); f(2, SH_C1 * z); f(3, -SH_C1 * x);
-  if (deg < 2) return 4;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  f(4, sh_c2(0) * xy); f(5, sh_c2(1) * yz); f(6, sh_c2(2) * (2.f * zz - xx - yy)); f(7, sh_c2(3) * xz); f(8, sh_c2(4) * (xx - yy));
-  if (deg < 3) return 9;
-  f(9, sh_c3(0) * y * (3.f * xx - yy)); f(10, sh_c3(1) * xy * z); f(11, sh_c3(2) * y * (4.f * zz - xx - yy));
-  f(12, sh_c3(3) * z * (2.f * zz - 3.f * xx - 3.f * yy)); f(13, sh_c3(4) * x * (4.f * zz - xx - yy));
-  f(14, sh_c3(5) * z * (xx - yy)); f(15, sh_c3(6) * x * (xx - 3.f * yy));
-  if (deg < 4) return 16;
-  f(16, sh_c4(0) * xy * (xx - yy)); f(17, sh_c4(1) * yz * (3.f * xx - yy)); f(18, sh_c4(2) * xy * (7.f * zz - 1.f));
-  f(19, sh_c4(3) * yz * (7.f * zz - 3.f)); f(20, sh_c4(4) * (zz * (35.f * zz - 30.f) + 3.f)); f(21, sh_c4(5) * xz * (7.f * zz - 3.f));
-  f(22, sh_c4(6) * (xx - yy) * (7.f * zz - 1.f)); f(23, sh_c4(7) * xz * (xx - 3.f * yy));
-  f(24, sh_c4(8) * (xx * (xx - 3.f * yy) - yy * (3.f * xx - yy)));
-  return 25;
+  return sh_terms(deg, x, y, z, [&](int k, float v, float, float, float) { f(k, v); });
 }
 
-// d += sum_k grad b_k(x, y, z) * s(k): the direction gradient of an SH colour, term by term, so that no 3 x 25 array of
-// basis derivatives is ever live (the batched K8+K9 kernel spilled on exactly those arrays).  s(k) is a callable.
+// d += sum_k grad b_k(x, y, z) * s(k): the direction gradient of an SH colour; s(k) is a callable
 template <class S>
 S360_HD void sh_grad_dot(int deg, float x, float y, float z, S&& s, float* d) {
-#define S360_T(k, BX, BY, BZ) { const float sk = s(k); d[0] += (BX) * sk; d[1] += (BY) * sk; d[2] += (BZ) * sk; }
-  if (deg < 1) return;
-  S360_T(1, 0.f, -SH_C1, 0.f) S360_T(2, 0.f, 0.f, SH_C1) S360_T(3, -SH_C1, 0.f, 0.f)
-  if (deg < 2) return;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-  S360_T(4, sh_c2(0) * y, sh_c2(0) * x, 0.f)
-  S360_T(5, 0.f, sh_c2(1) * z, sh_c2(1) * y)
-  S360_T(6, sh_c2(2) * -2.f * x, sh_c2(2) * -2.f * y, sh_c2(2) * 4.f * z)
-  S360_T(7, sh_c2(3) * z, 0.f, sh_c2(3) * x)
-  S360_T(8, sh_c2(4) * 2.f * x, sh_c2(4) * -2.f * y, 0.f)
-  if (deg < 3) return;
-  S360_T(9, sh_c3(0) * 6.f * xy, sh_c3(0) * (3.f * xx - 3.f * yy), 0.f)
-  S360_T(10, sh_c3(1) * yz, sh_c3(1) * xz, sh_c3(1) * xy)
-  S360_T(11, sh_c3(2) * -2.f * xy, sh_c3(2) * (4.f * zz - xx - 3.f * yy), sh_c3(2) * 8.f * yz)
-  S360_T(12, sh_c3(3) * -6.f * xz, sh_c3(3) * -6.f * yz, sh_c3(3) * (6.f * zz - 3.f * xx - 3.f * yy))
-  S360_T(13, sh_c3(4) * (4.f * zz - 3.f * xx - yy), sh_c3(4) * -2.f * xy, sh_c3(4) * 8.f * xz)
-  S360_T(14, sh_c3(5) * 2.f * xz, sh_c3(5) * -2.f * yz, sh_c3(5) * (xx - yy))
-  S360_T(15, sh_c3(6) * (3.f * xx - 3.f * yy), sh_c3(6) * -6.f * xy, 0.f)
-  if (deg < 4) return;
-  S360_T(16, sh_c4(0) * (3.f * xx * y - yy * y), sh_c4(0) * (xx * x - 3.f * x * yy), 0.f)
-  S360_T(17, sh_c4(1) * 6.f * xy * z, sh_c4(1) * z * (3.f * xx - 3.f * yy), sh_c4(1) * y * (3.f * xx - yy))
-  S360_T(18, sh_c4(2) * y * (7.f * zz - 1.f), sh_c4(2) * x * (7.f * zz - 1.f), sh_c4(2) * 14.f * xy * z)
-  S360_T(19, 0.f, sh_c4(3) * z * (7.f * zz - 3.f), sh_c4(3) * y * (21.f * zz - 3.f))
-  S360_T(20, 0.f, 0.f, sh_c4(4) * (140.f * zz * z - 60.f * z))
-  S360_T(21, sh_c4(5) * z * (7.f * zz - 3.f), 0.f, sh_c4(5) * x * (21.f * zz - 3.f))
-  S360_T(22, sh_c4(6) * 2.f * x * (7.f * zz - 1.f), sh_c4(6) * -2.f * y * (7.f * zz - 1.f), sh_c4(6) * (xx - yy) * 14.f * z)
-  S360_T(23, sh_c4(7) * z * (3.f * xx - 3.f * yy), sh_c4(7) * -6.f * xy * z, sh_c4(7) * x * (xx - 3.f * yy))
-  S360_T(24, sh_c4(8) * (4.f * xx * x - 12.f * x * yy), sh_c4(8) * (-12.f * xx * y + 4.f * yy * y), 0.f)
-#undef S360_T
+  sh_terms(deg, x, y, z, [&](int k, float, float gx, float gy, float gz) {
+    if (k == 0) return;
+    const float sk = s(k);
+    d[0] += gx * sk; d[1] += gy * sk; d[2] += gz * sk; });
 }
 
-// J[c][a] = sum_k (d b_k / d a) sh(k, c): Jacobian of the three SH colour channels w.r.t. the (unnormalised) view direction;
-// sh(k, c) is a callable.  The three inlined copies share the basis-derivative expressions.
+// colour sums and their Jacobian in ONE pass over the coefficients: rgb[c] = sum_k b_k sh(k, c) (no +0.5, no clamp) and
+// J[c][a] = sum_k (d b_k / d a) sh(k, c), the derivative w.r.t. the (unnormalised) view direction.  sh(k, c) is a callable and
+// is called once per (k, c).
 template <class S>
-S360_HD void sh_colour_jacobian(int deg, float x, float y, float z, S&& sh, float* J /* [3][3] */) {
+S360_HD void sh_colour_and_jacobian(int deg, float x, float y, float z, S&& sh, float* rgb /* [3] */, float* J /* [3][3] */) {
 #pragma unroll
-  for (int c = 0; c < 3; c++) {
-    J[3 * c] = J[3 * c + 1] = J[3 * c + 2] = 0.f;
-    sh_grad_dot(deg, x, y, z, [&](int k) { return sh(k, c); }, J + 3 * c);
-  }
+  for (int i = 0; i < 3; i++) rgb[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; i++) J[i] = 0.f;
+  sh_terms(deg, x, y, z, [&](int k, float v, float gx, float gy, float gz) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float s = sh(k, c);
+      rgb[c] += v * s;
+      J[3 * c] += gx * s; J[3 * c + 1] += gy * s; J[3 * c + 2] += gz * s;
+    }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------

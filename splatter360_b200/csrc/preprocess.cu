@@ -101,15 +101,21 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
         __syncthreads();
       }
       if (want_color) {
+        // colour and d rgb / d direction in one pass over the staged SH row; the Jacobian (36 B) spares the backward
+        // pass the 300-B SH row
         const float* sh = s_sh + threadIdx.x * row;
-        sh_to_rgb(v, sh, mx, my, mz, cam.cam, col, cl);
-        // d rgb / d direction for the backward pass (36 B per Gaussian instead of re-reading the 300-B SH row there)
         float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
         const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
         const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
         float J[9];
-        sh_colour_jacobian(min(v.sh_degree, v.max_sh_degree), ox * inv, oy * inv, oz * inv,
-                           [&](int k, int c) { return sh[ks * k + cs * c]; }, J);
+        sh_colour_and_jacobian(min(v.sh_degree, v.max_sh_degree), ox * inv, oy * inv, oz * inv,
+                               [&](int k, int c) { return sh[ks * k + cs * c]; }, col, J);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {   // as sh_to_rgb: + 0.5, clamp at 0, remember the clamp for the backward pass
+          const float r = col[ch] + 0.5f;
+          if (r < 0.f) cl |= (1 << ch);
+          col[ch] = fmaxf(r, 0.f);
+        }
 #pragma unroll
         for (int k = 0; k < 9; k++) gs.sh_jac[9 * (size_t)idx + k] = J[k];
       }

@@ -115,6 +115,30 @@ __device__ __forceinline__ void load_records(ChunkRegs& c, const float4* __restr
   }
 }
 
+// S360_ASYNC_STAGE=1 (A/B variant, north_star's "async-copy staging of sorted Gaussian attributes into shared memory"):
+// the next chunk's records travel global -> shared by cp.async (LDGSTS, no registers held) while the current chunk is
+// composited, double-buffered per warp; every lane copies and later reads only its own record, so no barrier is needed.
+#ifndef S360_ASYNC_STAGE
+#define S360_ASYNC_STAGE 0
+#endif
+#if S360_ASYNC_STAGE
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void issue_records(float4 (*buf)[32], uint32_t gid, const float4* __restrict__ rec, bool valid, int lane) {
+  if (valid) {
+    cp_async16(&buf[0][lane], rec + 3 * (size_t)gid);
+    cp_async16(&buf[1][lane], rec + 3 * (size_t)gid + 1);
+    cp_async16(&buf[2][lane], rec + 3 * (size_t)gid + 2);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fetch_records(ChunkRegs& c, float4 (*buf)[32], int lane) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  c.r0 = buf[0][lane]; c.r1 = buf[1][lane]; c.r2 = buf[2][lane];
+}
+#endif
+
 template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(RT, S360_FWD_MINB)
 render_forward_kernel(const int W, const int H, const float* __restrict__ bg, const float4* __restrict__ rec,
@@ -153,7 +177,11 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
   nx.r0 = nx.r1 = nx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
   nx.gid = 0;
   if (range.x + lane < range.y) nx.gid = point_list[range.x + lane];
-#if S360_FWD_PREFETCH
+#if S360_ASYNC_STAGE
+  __shared__ float4 s_rec[NWARPS][2][3][32];
+  int rbuf = 0;
+  issue_records(s_rec[warp][0], nx.gid, rec, range.x + lane < range.y, lane);
+#elif S360_FWD_PREFETCH
   load_records(nx, rec, range.x + lane < range.y);
 #endif
   uint32_t gid2 = (range.x + 32 + lane < range.y) ? point_list[range.x + 32 + lane] : 0u;
@@ -165,7 +193,9 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     if (__all_sync(0xffffffffu, amin0 == INF && amin1 == INF)) break;
     const bool valid = base + lane < range.y;
     S360_COUNT(c_chunks, 1); S360_COUNT(c_tests, __popc(__ballot_sync(0xffffffffu, valid)));
-#if !S360_FWD_PREFETCH
+#if S360_ASYNC_STAGE
+    fetch_records(nx, s_rec[warp][rbuf], lane);
+#elif !S360_FWD_PREFETCH
     load_records(nx, rec, valid);
 #endif
     float4 cull, ev, col;
@@ -175,7 +205,10 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
     const float dval = DEPTH ? -depth_value(dspec, nx.r2.w) : 0.f;   // per-Gaussian value of the fused depth channel (negated like rgb)
     // keep the pipeline full: records of the next chunk, ids of the one after
     nx.gid = gid2;
-#if S360_FWD_PREFETCH
+#if S360_ASYNC_STAGE
+    rbuf ^= 1;
+    issue_records(s_rec[warp][rbuf], nx.gid, rec, base + 32 + lane < range.y, lane);
+#elif S360_FWD_PREFETCH
     load_records(nx, rec, base + 32 + lane < range.y);
 #endif
     gid2 = (base + 64 + lane < range.y) ? point_list[base + 64 + lane] : 0u;
@@ -390,10 +423,16 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
   nx.r0 = nx.r1 = nx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
   nx.gid = 0;
   uint32_t gid2 = 0;
+#if S360_ASYNC_STAGE
+  __shared__ float4 s_rec[NWARPS][2][3][32];
+  int rbuf = 0;
+#endif
   if (nchunks > 0) {
     const uint32_t p = (uint32_t)(nchunks - 1) * 32u + lane;
     if (p < todo) nx.gid = point_list[range.x + p];
-#if S360_BWD_PREFETCH
+#if S360_ASYNC_STAGE
+    issue_records(s_rec[warp][0], nx.gid, rec, p < todo, lane);
+#elif S360_BWD_PREFETCH
     load_records(nx, rec, p < todo);
 #endif
     if (nchunks > 1) gid2 = point_list[range.x + p - 32u];
@@ -405,7 +444,9 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     const uint32_t pos0 = (uint32_t)ci * 32u;
     const bool valid = pos0 + lane < todo;
     S360_COUNT(c_chunks, 1); S360_COUNT(c_tests, __popc(__ballot_sync(0xffffffffu, valid)));
-#if !S360_BWD_PREFETCH
+#if S360_ASYNC_STAGE
+    fetch_records(nx, s_rec[warp][rbuf], lane);
+#elif !S360_BWD_PREFETCH
     load_records(nx, rec, valid);
 #endif
     float4 cull, ev, col;
@@ -415,7 +456,10 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
     col.w = __uint_as_float(nx.gid);
     const float nx_depth = nx.r2.w;      // sort depth of this lane's instance (fused depth channel)
     nx.gid = gid2;                       // chunks below the last one are always full
-#if S360_BWD_PREFETCH
+#if S360_ASYNC_STAGE
+    rbuf ^= 1;
+    issue_records(s_rec[warp][rbuf], nx.gid, rec, ci > 0, lane);
+#elif S360_BWD_PREFETCH
     load_records(nx, rec, ci > 0);
 #endif
     gid2 = (ci > 1) ? point_list[range.x + pos0 - 64u + lane] : 0u;
