@@ -24,8 +24,8 @@ struct GeomState {
   float4* rec;        // [P*3]
   uint2* rect;        // [P] packed tile rect: x = (x0 & 0xffff) | nx << 16 ; y = y0 | ny << 16
   uint8_t* clamped;   // [P] bits 0..2 SH clamp per channel, bit 3 = jacobian clamp x, bit 4 = clamp y
-  float* sh_jac;      // [P*9] d rgb_c / d dir_a of the SH colour (single-view path; NULL in the batched path): K1 has the SH
-                      // block in shared memory anyway, and with these 36 B the backward never reads the 300-B SH row again
+  float* sh_jac;      // [P*9] d rgb_c / d dir_a of the SH colour (per pair in the batched path): K1 has the SH block in shared
+                      // memory anyway, and with these 36 B the backward never reads the 300-B SH row again
 };
 
 struct ImageState {
@@ -89,10 +89,13 @@ inline GeomState carve_geom_multi(void* buf, int P, int64_t cap, PairState* ps) 
   char* p = (char*)buf + geom_base_bytes((int)cap);
   ps->base = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
   ps->mask = (uint32_t*)p; p += align_up((size_t)P * 4, 256);
-  ps->count = (uint32_t*)p;
+  ps->count = (uint32_t*)p; p += 256;
+  g.sh_jac = (float*)p;   // [cap*9] per PAIR
   return g;
 }
-inline size_t geom_multi_bytes(int P, int64_t cap) { return geom_base_bytes((int)cap) + 2 * align_up((size_t)P * 4, 256) + 256; }
+inline size_t geom_multi_bytes(int P, int64_t cap) {
+  return geom_base_bytes((int)cap) + 2 * align_up((size_t)P * 4, 256) + 256 + align_up((size_t)cap * 9 * sizeof(float), 256);
+}
 
 // V views are laid out as one stacked image: pixel state [V][H][W], tiles [V][gy][gx] (V = 1: the single view)
 inline ImageState carve_image(void* buf, int H, int W, int V = 1) {

@@ -191,31 +191,28 @@ S360_HD float view_frobenius2(const float* V) {
          V[10] * V[10];
 }
 
-// SH -> RGB for one Gaussian (row `sh` of the staged block) seen from `campos`; sets the clamp bits 0..2 of cl
-S360_HD void sh_to_rgb(const S360View& v, const float* sh, float mx, float my, float mz,
-                                          const float* campos, float* col, uint8_t& cl) {
+// SH -> RGB for one Gaussian (row `sh` of the staged block) seen from `campos`, together with J[c][a] = d rgb_c / d dir_a
+// (w.r.t. the unnormalised view direction, before the +0.5 and the clamp); sets the clamp bits 0..2 of cl.  The ONE colour
+// routine of every kernel (single-view K1, batched K1c): identical expressions with identical uses, so a Gaussian gets
+// bit-identical colours whichever path renders it.  The 36-B Jacobian spares the backward pass the 300-B SH row.
+S360_HD void sh_to_rgb_jac(const S360View& v, const float* sh, float mx, float my, float mz, const float* campos,
+                           float* col, uint8_t& cl, float* J) {
   float dx = mx - campos[0], dy = my - campos[1], dz = mz - campos[2];
   const float inv = 1.f / sqrtf(dx * dx + dy * dy + dz * dz);
   dx *= inv; dy *= inv; dz *= inv;
-  float b[25];
-  const int deg = min(v.sh_degree, v.max_sh_degree);
-  const int n = sh_basis(deg, dx, dy, dz, b);
   const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;   // [P,M,3] or the reference's [P,3,M]
-  float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int k = 0; k < 25; k++) {
-    if (k < n) {
-      acc[0] += b[k] * sh[ks * k];
-      acc[1] += b[k] * sh[ks * k + cs];
-      acc[2] += b[k] * sh[ks * k + 2 * cs];
-    }
-  }
+  sh_colour_and_jacobian(min(v.sh_degree, v.max_sh_degree), dx, dy, dz, [&](int k, int c) { return sh[ks * k + cs * c]; }, col, J);
 #pragma unroll
   for (int ch = 0; ch < 3; ch++) {
-    const float r = acc[ch] + 0.5f;
+    const float r = col[ch] + 0.5f;
     if (r < 0.f) cl |= (1 << ch);
     col[ch] = fmaxf(r, 0.f);
   }
+}
+S360_HD void sh_to_rgb(const S360View& v, const float* sh, float mx, float my, float mz, const float* campos, float* col,
+                       uint8_t& cl) {
+  float J[9];
+  sh_to_rgb_jac(v, sh, mx, my, mz, campos, col, cl, J);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -223,7 +220,9 @@ S360_HD void sh_to_rgb(const S360View& v, const float* sh, float mx, float my, f
 // dL/d(mean3D) through the projection and the Jacobian, dL/d(cov3D), screen-space gradient dm2 (NDC units).
 // a0 = {dL/dr, dL/dg, dL/db, sum q dx}, a1 = {sum q dy, sum q dx^2, sum q dxdy, sum q dy^2}, q = G dL/dalpha.
 // Shared by the single-view and the batched kernel; the SH part (direction gradient) is added by the caller.
-template <int MODE, bool DEPTH = false>
+// ACCUM: add to dm / dcov instead of overwriting them (the batched kernel folds several views into one gradient set and
+// has no registers to spare for per-view temporaries).
+template <int MODE, bool DEPTH = false, bool ACCUM = false>
 S360_HD void view_backward(const S360View& v, const float* V, const float* PM, float mx, float my,
                                               float mz, const float* cv, float op, const float4& a0, const float4& a1,
                                               float* dm, float* dm2, float* dcov, const DepthSpec& ds, float dl_dd) {
@@ -249,12 +248,12 @@ S360_HD void view_backward(const S360View& v, const float* V, const float* PM, f
   const float dc = inv2 * (-g.a * g.a * gC + g.a * g.b * gB + (denom - g.a * g.c) * gA);
   const float db = inv2 * (2.f * g.b * g.c * gA - (denom + 2.f * g.b * g.b) * gB + 2.f * g.a * g.b * gC);
   const float(*Mm)[3] = g.Mm;
-  dcov[0] = Mm[0][0] * Mm[0][0] * da + Mm[0][0] * Mm[1][0] * db + Mm[1][0] * Mm[1][0] * dc;
-  dcov[3] = Mm[0][1] * Mm[0][1] * da + Mm[0][1] * Mm[1][1] * db + Mm[1][1] * Mm[1][1] * dc;
-  dcov[5] = Mm[0][2] * Mm[0][2] * da + Mm[0][2] * Mm[1][2] * db + Mm[1][2] * Mm[1][2] * dc;
-  dcov[1] = 2.f * Mm[0][0] * Mm[0][1] * da + (Mm[0][0] * Mm[1][1] + Mm[0][1] * Mm[1][0]) * db + 2.f * Mm[1][0] * Mm[1][1] * dc;
-  dcov[2] = 2.f * Mm[0][0] * Mm[0][2] * da + (Mm[0][0] * Mm[1][2] + Mm[0][2] * Mm[1][0]) * db + 2.f * Mm[1][0] * Mm[1][2] * dc;
-  dcov[4] = 2.f * Mm[0][2] * Mm[0][1] * da + (Mm[0][1] * Mm[1][2] + Mm[0][2] * Mm[1][1]) * db + 2.f * Mm[1][1] * Mm[1][2] * dc;
+  dcov[0] = (ACCUM ? dcov[0] : 0.f) + (Mm[0][0] * Mm[0][0] * da + Mm[0][0] * Mm[1][0] * db + Mm[1][0] * Mm[1][0] * dc);
+  dcov[3] = (ACCUM ? dcov[3] : 0.f) + (Mm[0][1] * Mm[0][1] * da + Mm[0][1] * Mm[1][1] * db + Mm[1][1] * Mm[1][1] * dc);
+  dcov[5] = (ACCUM ? dcov[5] : 0.f) + (Mm[0][2] * Mm[0][2] * da + Mm[0][2] * Mm[1][2] * db + Mm[1][2] * Mm[1][2] * dc);
+  dcov[1] = (ACCUM ? dcov[1] : 0.f) + (2.f * Mm[0][0] * Mm[0][1] * da + (Mm[0][0] * Mm[1][1] + Mm[0][1] * Mm[1][0]) * db + 2.f * Mm[1][0] * Mm[1][1] * dc);
+  dcov[2] = (ACCUM ? dcov[2] : 0.f) + (2.f * Mm[0][0] * Mm[0][2] * da + (Mm[0][0] * Mm[1][2] + Mm[0][2] * Mm[1][0]) * db + 2.f * Mm[1][0] * Mm[1][2] * dc);
+  dcov[4] = (ACCUM ? dcov[4] : 0.f) + (2.f * Mm[0][2] * Mm[0][1] * da + (Mm[0][1] * Mm[1][2] + Mm[0][2] * Mm[1][1]) * db + 2.f * Mm[1][1] * Mm[1][2] * dc);
   const float S[3][3] = {{cv[0], cv[1], cv[2]}, {cv[1], cv[3], cv[4]}, {cv[2], cv[4], cv[5]}};
   float dM[2][3];
 #pragma unroll
@@ -271,7 +270,7 @@ S360_HD void view_backward(const S360View& v, const float* V, const float* PM, f
 #pragma unroll
     for (int k = 0; k < 3; k++) dJ[r][k] = V[k] * dM[r][0] + V[4 + k] * dM[r][1] + V[8 + k] * dM[r][2];
   float dt[3] = {0.f, 0.f, 0.f};
-  dm[0] = dm[1] = dm[2] = 0.f;
+  if (!ACCUM) dm[0] = dm[1] = dm[2] = 0.f;
   if (MODE == S360_MODE_PINHOLE) {
     const float fx = (float)W / (2.f * v.tanfovx), fy = (float)H / (2.f * v.tanfovy);
     const float tz = 1.f / g.tc[2], tz2 = tz * tz, tz3 = tz2 * tz;
@@ -284,9 +283,9 @@ S360_HD void view_backward(const S360View& v, const float* V, const float* PM, f
     const float mw = 1.f / (hw + 0.0000001f);
     const float mul1 = (PM[0] * mx + PM[4] * my + PM[8] * mz + PM[12]) * mw * mw;
     const float mul2 = (PM[1] * mx + PM[5] * my + PM[9] * mz + PM[13]) * mw * mw;
-    dm[0] = (PM[0] * mw - PM[3] * mul1) * dm2[0] + (PM[1] * mw - PM[3] * mul2) * dm2[1];
-    dm[1] = (PM[4] * mw - PM[7] * mul1) * dm2[0] + (PM[5] * mw - PM[7] * mul2) * dm2[1];
-    dm[2] = (PM[8] * mw - PM[11] * mul1) * dm2[0] + (PM[9] * mw - PM[11] * mul2) * dm2[1];
+    dm[0] += (PM[0] * mw - PM[3] * mul1) * dm2[0] + (PM[1] * mw - PM[3] * mul2) * dm2[1];
+    dm[1] += (PM[4] * mw - PM[7] * mul1) * dm2[0] + (PM[5] * mw - PM[7] * mul2) * dm2[1];
+    dm[2] += (PM[8] * mw - PM[11] * mul1) * dm2[0] + (PM[9] * mw - PM[11] * mul2) * dm2[1];
   } else {
     const float su = -(float)W / (2.f * PI_F), sv = -(float)H / PI_F;
     const float x = g.tc[0], y = g.tc[1], z = g.tc[2];

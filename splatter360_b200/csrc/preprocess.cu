@@ -101,21 +101,8 @@ preprocess_kernel(const S360View v, const float* __restrict__ means, const float
         __syncthreads();
       }
       if (want_color) {
-        // colour and d rgb / d direction in one pass over the staged SH row; the Jacobian (36 B) spares the backward
-        // pass the 300-B SH row
-        const float* sh = s_sh + threadIdx.x * row;
-        float ox = mx - cam.cam[0], oy = my - cam.cam[1], oz = mz - cam.cam[2];
-        const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
-        const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
         float J[9];
-        sh_colour_and_jacobian(min(v.sh_degree, v.max_sh_degree), ox * inv, oy * inv, oz * inv,
-                               [&](int k, int c) { return sh[ks * k + cs * c]; }, col, J);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {   // as sh_to_rgb: + 0.5, clamp at 0, remember the clamp for the backward pass
-          const float r = col[ch] + 0.5f;
-          if (r < 0.f) cl |= (1 << ch);
-          col[ch] = fmaxf(r, 0.f);
-        }
+        sh_to_rgb_jac(v, s_sh + threadIdx.x * row, mx, my, mz, cam.cam, col, cl, J);
 #pragma unroll
         for (int k = 0; k < 9; k++) gs.sh_jac[9 * (size_t)idx + k] = J[k];
       }
@@ -457,6 +444,7 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
   ps.base[idx] = slot;
   uint32_t kept = mask;
   float col[3] = {0.f, 0.f, 0.f};
+  float J[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   uint8_t clc = 0;
   int col_view = -1;
   for (uint32_t m = mask; m; m &= m - 1, slot++) {
@@ -469,7 +457,9 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
       // same camera centre as the last evaluated view (cube faces): same direction, same colour
       const bool same = col_view >= 0 && s_cam[col_view][32] == cam[32] && s_cam[col_view][33] == cam[33] &&
                         s_cam[col_view][34] == cam[34];
-      if (!same) { clc = 0; sh_to_rgb(v, s_sh + threadIdx.x * row, mx, my, mz, cam + 32, col, clc); col_view = view; }
+      if (!same) { clc = 0; sh_to_rgb_jac(v, s_sh + threadIdx.x * row, mx, my, mz, cam + 32, col, clc, J); col_view = view; }
+#pragma unroll
+      for (int k = 0; k < 9; k++) gs.sh_jac[9 * (size_t)slot + k] = J[k];   // per pair: the backward reads no SH
     } else if (col_view < 0) {
       col[0] = colors[3 * idx]; col[1] = colors[3 * idx + 1]; col[2] = colors[3 * idx + 2];
       col_view = view;
@@ -527,17 +517,16 @@ int launch_zero_acc(float* acc, const uint32_t* n_dev, int64_t cap, cudaStream_t
   return (int)cudaGetLastError();
 }
 
-// direction part of the SH backward for one view: dL/d(mean) through the normalised view direction
-__device__ __forceinline__ void sh_dir_backward(const S360View& v, const float* sh, float mx, float my, float mz,
+// direction part of the SH backward for one pair: dL/d(mean) through the normalised view direction, from the Jacobian
+// J[c][a] = d rgb_c / d dir_a that K1c stored for the pair
+__device__ __forceinline__ void sh_dir_backward(const float* __restrict__ J, float mx, float my, float mz,
                                                 const float* campos, const float* drgb, float* dm) {
   const float ox = mx - campos[0], oy = my - campos[1], oz = mz - campos[2];
   const float inv = 1.f / sqrtf(ox * ox + oy * oy + oz * oz);
   const float dx = ox * inv, dy = oy * inv, dz = oz * inv;
-  const int deg = min(v.sh_degree, v.max_sh_degree);
-  const int ks = v.sh_layout ? 1 : 3, cs = v.sh_layout ? v.M : 1;
-  float ddir[3] = {0.f, 0.f, 0.f};
-  sh_grad_dot(deg, dx, dy, dz,
-              [&](int k) { return sh[ks * k] * drgb[0] + sh[ks * k + cs] * drgb[1] + sh[ks * k + 2 * cs] * drgb[2]; }, ddir);
+  float ddir[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) ddir[a] = J[a] * drgb[0] + J[3 + a] * drgb[1] + J[6 + a] * drgb[2];
   const float dot = dx * ddir[0] + dy * ddir[1] + dz * ddir[2];
   dm[0] += (ddir[0] - dx * dot) * inv;
   dm[1] += (ddir[1] - dy * dot) * inv;
@@ -562,52 +551,40 @@ __device__ __forceinline__ void sh_coeff_backward(const S360View& v, float* sh, 
 }
 
 // Batched K8 + K9: one thread per Gaussian folds the moments of all its pairs into ONE set of gradients
-// (the reference gets the same sum from autograd over V separate rasterizer calls).
+// (the reference gets the same sum from autograd over V separate rasterizer calls).  No SH coefficient is read: the
+// direction gradient uses the per-pair Jacobians of K1c, dL/dSH = sum_v basis(dir_v) x dL/drgb_v is assembled in shared
+// memory (one basis evaluation when all views share the camera centre) and leaves by one TMA bulk store.
 template <int MODE, bool DEPTH>
 __global__ void __launch_bounds__(PRE_THREADS, S360_MV_BWD_MINB)
 preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __restrict__ means,
                                  const float* __restrict__ cov3D, const float* __restrict__ opac,
-                                 const float* __restrict__ shs, GeomState gs, PairState ps,
+                                 const bool has_sh, GeomState gs, PairState ps,
                                  const float* __restrict__ acc, float* __restrict__ d_means,
                                  float* __restrict__ d_cov, float* __restrict__ d_opac, float* __restrict__ d_shs,
                                  float* __restrict__ d_colors, const DepthSpec dspec) {
-  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: SH in, dL/dSH out (in place)
-  __shared__ uint64_t s_bar;
+  extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: dL/dSH of this CTA
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
   __shared__ int s_same;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = v.P;
   const int row = v.M * 3;
   const int rows = min(PRE_THREADS, P - blockIdx.x * PRE_THREADS);
-  const float* sh_src = shs ? shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
-  float* dsh_dst = shs ? d_shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
+  float* dsh_dst = has_sh ? d_shs + (size_t)blockIdx.x * PRE_THREADS * row : nullptr;
   const uint32_t sh_bytes = (uint32_t)rows * row * 4u;
-  const bool bulk_ok = shs && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(sh_src) & 15u) == 0u) &&
-                       ((reinterpret_cast<uintptr_t>(dsh_dst) & 15u) == 0u);
+  const bool bulk_ok = has_sh && (sh_bytes % 16u == 0u) && ((reinterpret_cast<uintptr_t>(dsh_dst) & 15u) == 0u);
   const uint32_t mask = idx < P ? ps.mask[idx] : 0u;
   const uint32_t slot0 = idx < P ? ps.base[idx] : 0u;   // loaded with the mask: one dependent global load less before acc
   const bool vis = mask != 0u;
   stage_cameras(v, NV, MODE == S360_MODE_PINHOLE, s_cam);
   if (threadIdx.x == 0) {
-    if (shs) mbar_init(&s_bar, 1);
-    int same = 1;   // all views share one camera centre (cube faces): one SH evaluation serves every view
+    int same = 1;   // all views share one camera centre (cube faces): one basis evaluation serves every view
     for (int k = 1; k < NV; k++)
       for (int j = 0; j < 3; j++) same &= (__ldg(v.campos + 3 * k + j) == __ldg(v.campos + j)) ? 1 : 0;
     s_same = same;
   }
   const bool need = __syncthreads_or(vis) != 0;
-  if (shs) {
-    if (need) {
-      if (bulk_ok) {
-        if (threadIdx.x == 0) { mbar_expect_tx(&s_bar, sh_bytes); bulk_load(s_sh, sh_src, sh_bytes, &s_bar); }
-      } else {
-        for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) s_sh[i] = sh_src[i];
-        __syncthreads();
-      }
-    } else {
-      for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) dsh_dst[i] = 0.f;
-    }
-  }
+  if (has_sh && !need)
+    for (int i = threadIdx.x; i < rows * row; i += PRE_THREADS) dsh_dst[i] = 0.f;
   const bool same_cam = s_same != 0;
   float dm[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float dop = 0.f, dcol[3] = {0.f, 0.f, 0.f};
@@ -618,9 +595,9 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
     load_cov6(v, cov3D, idx, cv);
     const float op = opac[idx];
     float* sh = s_sh + threadIdx.x * row;
-    if (shs != nullptr && bulk_ok) mbar_wait(&s_bar, 0);
     uint32_t slot = slot0;
     int first_view = -1;
+#pragma unroll 1
     for (uint32_t m = mask; m; m &= m - 1, slot++) {
       const int view = __ffs(m) - 1;
       if (first_view < 0) first_view = view;
@@ -632,48 +609,31 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
 #else
       dop += acc[(size_t)slot * ACC_STRIDE + 8];
 #endif
-      float dmv[3], dm2v[2], dcv[6];
-      view_backward<MODE, DEPTH>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dmv, dm2v, dcv, dspec,
-                                 DEPTH ? acc[(size_t)slot * ACC_STRIDE + 9] : 0.f);
-#pragma unroll
-      for (int k = 0; k < 3; k++) dm[k] += dmv[k];
-#pragma unroll
-      for (int k = 0; k < 6; k++) dcov[k] += dcv[k];
-      if (shs != nullptr) {
+      float dm2v[2];
+      view_backward<MODE, DEPTH, true>(v, cam, cam + 16, mx, my, mz, cv, op, a0, a1, dm, dm2v, dcov, dspec,
+                                       DEPTH ? acc[(size_t)slot * ACC_STRIDE + 9] : 0.f);
+      if (has_sh) {
         const uint8_t cl = gs.clamped[slot];
         const float drgb[3] = {(cl & 1) ? 0.f : a0.x, (cl & 2) ? 0.f : a0.y, (cl & 4) ? 0.f : a0.z};
-        if (same_cam) { dcol[0] += drgb[0]; dcol[1] += drgb[1]; dcol[2] += drgb[2]; }
-        else sh_dir_backward(v, sh, mx, my, mz, cam + 32, drgb, dm);
+        if (same_cam) { dcol[0] += drgb[0]; dcol[1] += drgb[1]; dcol[2] += drgb[2]; }   // same direction, same Jacobian
+        else {
+          sh_dir_backward(gs.sh_jac + 9 * (size_t)slot, mx, my, mz, cam + 32, drgb, dm);
+          sh_coeff_backward(v, sh, mx, my, mz, cam + 32, drgb, view == first_view);
+        }
       } else {
         dcol[0] += a0.x; dcol[1] += a0.y; dcol[2] += a0.z;
       }
     }
-    if (shs != nullptr) {
-      if (same_cam) {
-        sh_dir_backward(v, sh, mx, my, mz, s_cam[first_view] + 32, dcol, dm);
-        sh_coeff_backward(v, sh, mx, my, mz, s_cam[first_view] + 32, dcol, true);
-      } else {
-        // second sweep: every SH value has been read, the row can now take the gradient
-        slot = slot0;
-        bool first = true;
-        for (uint32_t m = mask; m; m &= m - 1, slot++) {
-          const int view = __ffs(m) - 1;
-          const float4 a0 = *reinterpret_cast<const float4*>(acc + (size_t)slot * ACC_STRIDE);
-          const uint8_t cl = gs.clamped[slot];
-          const float drgb[3] = {(cl & 1) ? 0.f : a0.x, (cl & 2) ? 0.f : a0.y, (cl & 4) ? 0.f : a0.z};
-          sh_coeff_backward(v, sh, mx, my, mz, s_cam[view] + 32, drgb, first);
-          first = false;
-        }
-      }
+    if (has_sh && same_cam) {
+      sh_dir_backward(gs.sh_jac + 9 * (size_t)slot0, mx, my, mz, s_cam[first_view] + 32, dcol, dm);
+      sh_coeff_backward(v, sh, mx, my, mz, s_cam[first_view] + 32, dcol, true);
     }
-  } else if (shs != nullptr && need && idx < P) {
-    if (bulk_ok) mbar_wait(&s_bar, 0);
+  } else if (has_sh && need && idx < P) {
     float* sh = s_sh + threadIdx.x * row;
     for (int k = 0; k < row; k++) sh[k] = 0.f;
   }
-  if (shs != nullptr && need) {
+  if (has_sh && need) {
     if (bulk_ok) {
-      if (idx >= P) mbar_wait(&s_bar, 0);
       fence_async_smem();
       __syncthreads();
       if (threadIdx.x == 0) { bulk_store(dsh_dst, s_sh, sh_bytes); bulk_store_wait_read(); }
@@ -689,7 +649,7 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
   store_dcov(v, d_cov, idx, dcov, gsc * gsc);
   d_opac[idx] = dop;
   if (d_colors != nullptr) {
-    const bool pre = shs == nullptr;
+    const bool pre = !has_sh;
 #pragma unroll
     for (int k = 0; k < 3; k++) d_colors[3 * idx + k] = pre ? dcol[k] : 0.f;
   }
@@ -707,7 +667,7 @@ int launch_preprocess_multi_backward(const S360View& v, int NV, const float* mea
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
 #define S360_LAUNCH_MK8(MODE_, DEPTH_) do { \
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    preprocess_multi_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
+    preprocess_multi_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs != nullptr, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
   if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_MK8(S360_MODE_PINHOLE, true); else S360_LAUNCH_MK8(S360_MODE_PINHOLE, false); }
   else { if (has_depth) S360_LAUNCH_MK8(S360_MODE_ERP, true); else S360_LAUNCH_MK8(S360_MODE_ERP, false); }
 #undef S360_LAUNCH_MK8

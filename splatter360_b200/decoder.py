@@ -223,6 +223,24 @@ def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image
 # batched multi-view path: every view of a batch item in ONE rasterizer pass
 MAX_VIEWS_PER_PASS = 12   # two sets of cube faces; the pair buffers grow with views x Gaussians
 
+# The rasterizer settings carry tan(fov/2), the 1/near scale, near and far as HOST floats (as upstream's do), so a decoder
+# call has to read them back from the intrinsics / near / far tensors: one device -> host wait per call, which stalls a
+# render loop that is otherwise asynchronous.  The same tensor objects (same storage, same in-place version counter) give
+# the same host values, so those are remembered; the cache holds the tensors, which keeps their storage from being reused.
+_HOST_SCALARS: dict = {}
+
+
+def _host_scalars(key_tensors, flag, compute):
+    key = (flag,) + tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in key_tensors)
+    hit = _HOST_SCALARS.get(key)
+    if hit is not None:
+        return hit[1]
+    val = compute()
+    if len(_HOST_SCALARS) >= 16:
+        _HOST_SCALARS.pop(next(iter(_HOST_SCALARS)))
+    _HOST_SCALARS[key] = (tuple(key_tensors), val)
+    return val
+
 
 def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
                      gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh, projection,
@@ -273,11 +291,12 @@ def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     once over all views (six cube faces of a panorama: one pass instead of six)."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b, v = extrinsics.shape[:2]
-    scale = torch.ones_like(near)
     if scale_invariant:
         scale = 1 / near
         extrinsics = extrinsics.clone()
         extrinsics[..., :3, 3] = extrinsics[..., :3, 3] * scale[..., None]
+    else:
+        scale = torch.ones_like(near)
     near_s, far_s = near * scale, far * scale
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
@@ -286,8 +305,8 @@ def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     view_matrix = extrinsics.reshape(b * v, 4, 4).inverse().transpose(1, 2)
     full_projection = (view_matrix @ projection_matrix).reshape(b, v, 4, 4)
     view_matrix = view_matrix.reshape(b, v, 4, 4)
-    host = torch.stack(((0.5 * fov_x).tan().reshape(b, v), (0.5 * fov_y).tan().reshape(b, v), scale, near, far), -1).tolist()
-    host = [[tuple(x) for x in row] for row in host]
+    host = _host_scalars((intrinsics, near, far), bool(scale_invariant), lambda: [[tuple(x) for x in row] for row in torch.stack(
+        ((0.5 * fov_x).tan().reshape(b, v), (0.5 * fov_y).tan().reshape(b, v), scale, near, far), -1).tolist()])
     return _rasterize_views(extrinsics, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
                             gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
                             "pinhole", fused_depth_mode, max_views_per_pass, capacity_trackers)
