@@ -20,9 +20,16 @@ import torch
 from torch import Tensor
 
 
+def inverse(m: Tensor) -> Tensor:
+    """``m.inverse()`` without the host round trip: torch's ``inverse`` reads the LU status back from the device to raise on
+    singular input, which stalls an otherwise asynchronous render loop once per call; ``linalg.inv_ex`` computes the same
+    inverse and leaves the status on the device (camera matrices are never singular)."""
+    return torch.linalg.inv_ex(m).inverse
+
+
 def get_fov(intrinsics: Tensor) -> Tensor:
     """Field of view [b,2] (x, y) from normalised intrinsics [b,3,3] via the edge-ray angle."""
-    inv = intrinsics.inverse()
+    inv = inverse(intrinsics)
 
     def ray(v):
         v = torch.tensor(v, dtype=torch.float32, device=intrinsics.device)
@@ -69,14 +76,14 @@ def pinhole_camera(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Te
     """cuda_splatting.py:80-87.  ``extrinsics`` is camera-to-world (OpenCV), already rescaled."""
     fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
     proj = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
-    view = extrinsics.inverse().transpose(1, 2)
+    view = inverse(extrinsics).transpose(1, 2)
     return Camera(view, view @ proj, (0.5 * fov_x).tan(), (0.5 * fov_y).tan(), extrinsics[:, :3, 3])
 
 
 def erp_camera(extrinsics_sphere: Tensor) -> Camera:
     """Native ERP camera: only the view matrix and campos are meaningful; the projection slot
     carries the view matrix (unused by the erp kernels) and tan_fov is 1."""
-    view = extrinsics_sphere.inverse().transpose(1, 2)
+    view = inverse(extrinsics_sphere).transpose(1, 2)
     b = extrinsics_sphere.shape[0]
     one = torch.ones(b, dtype=torch.float32, device=extrinsics_sphere.device)
     return Camera(view, view.clone(), one, one, extrinsics_sphere[:, :3, 3])

@@ -35,10 +35,17 @@ S360_HD void ad_quat_to_matrix(const float* q, float eps, float* R) {
 
 // unit ray of ERP pixel (row, col) in the sphere-camera frame, hm3d convention (utils360.py:93-104, 148-153)
 S360_HD void ad_pixel_dir(int row, int col, int H, int W, float* d) {
-  const float theta = (0.5f - ((float)col + 0.5f) / (float)W) * (2.f * PI_F);
-  const float phi = -(((float)row + 0.5f) / (float)H - 0.5f) * PI_F;
-  const float cp = cosf(phi);
-  d[0] = cp * sinf(theta); d[1] = sinf(phi); d[2] = cp * cosf(theta);
+  // theta = 2 pi tu, phi = pi tv; on the device sincospif takes the angle in units of pi (exact argument reduction, no
+  // local-memory slow path)
+  const float tu = 0.5f - ((float)col + 0.5f) / (float)W, tv = -(((float)row + 0.5f) / (float)H - 0.5f);
+  float st, ct, sp, cp;
+#ifdef __CUDA_ARCH__
+  sincospif(2.f * tu, &st, &ct);
+  sincospif(tv, &sp, &cp);
+#else
+  st = sinf(tu * (2.f * PI_F)); ct = cosf(tu * (2.f * PI_F)); sp = sinf(tv * PI_F); cp = cosf(tv * PI_F);
+#endif
+  d[0] = cp * st; d[1] = sp; d[2] = cp * ct;
 }
 
 struct AdapterFwd {

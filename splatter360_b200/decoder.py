@@ -21,7 +21,7 @@ from typing import Literal, Optional
 import torch
 from torch import Tensor, nn
 
-from .camera import erp_camera, get_fov, get_projection_matrix
+from .camera import erp_camera, get_fov, get_projection_matrix, inverse
 from .rasterizer import CapacityTracker, GaussianRasterizationSettings, GaussianRasterizer, rasterize_views
 
 DepthRenderingMode = Literal["depth", "disparity", "relative_disparity", "log"]
@@ -33,6 +33,25 @@ def depth_to_relative_disparity(depth: Tensor, near: Tensor, far: Tensor, eps: f
     disp_far = 1 / (far + eps)
     disp = 1 / (depth + eps)
     return 1 - (disp - disp_far) / (disp_near - disp_far + eps)
+
+
+# The rasterizer settings carry tan(fov/2), the 1/near scale, near and far as HOST floats (as upstream's do), so a decoder
+# call has to read them back from the intrinsics / near / far tensors: one device -> host wait per call, which stalls a
+# render loop that is otherwise asynchronous.  The same tensor objects (same storage, same in-place version counter) give
+# the same host values, so those are remembered; the cache holds the tensors, which keeps their storage from being reused.
+_HOST_SCALARS: dict = {}
+
+
+def _host_scalars(key_tensors, flag, compute):
+    key = (flag,) + tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in key_tensors)
+    hit = _HOST_SCALARS.get(key)
+    if hit is not None:
+        return hit[1]
+    val = compute()
+    if len(_HOST_SCALARS) >= 16:
+        _HOST_SCALARS.pop(next(iter(_HOST_SCALARS)))
+    _HOST_SCALARS[key] = (tuple(key_tensors), val)
+    return val
 
 
 def _triu6(cov: Tensor) -> Tensor:
@@ -92,7 +111,7 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
     ``rasterizer.CapacityTracker`` (or one per batch item) -- sync-free sizing of the instance buffers in a render loop."""
     assert use_sh or gaussian_sh_coefficients.shape[-1] == 1
     b = extrinsics.shape[0]
-    depth = None if fused_depth_mode is None else (fused_depth_mode, near.tolist(), far.tolist())
+    near0, far0 = near, far
     scale = torch.ones_like(near)
     if scale_invariant:
         scale = 1 / near
@@ -103,9 +122,12 @@ def render_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far: Tenso
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
     fov_x, fov_y = get_fov(intrinsics).unbind(dim=-1)
-    host = torch.stack(((0.5 * fov_x).tan(), (0.5 * fov_y).tan(), scale)).tolist()   # one device read for all scalars
+    # one device read for all scalars (tan fov x / y, scale, unscaled near / far), remembered per input tensors
+    host = _host_scalars((intrinsics, near0, far0), bool(scale_invariant),
+                         lambda: torch.stack(((0.5 * fov_x).tan(), (0.5 * fov_y).tan(), scale, near0, far0)).tolist())
+    depth = None if fused_depth_mode is None else (fused_depth_mode, host[3], host[4])
     projection_matrix = get_projection_matrix(near, far, fov_x, fov_y).transpose(1, 2)
-    view_matrix = extrinsics.inverse().transpose(1, 2)
+    view_matrix = inverse(extrinsics).transpose(1, 2)
     full_projection = view_matrix @ projection_matrix
     return _rasterize_batch(extrinsics, view_matrix, full_projection, host[0], host[1], image_shape,
                             background_color, gaussian_means, gaussian_covariances, gaussian_sh_coefficients,
@@ -136,7 +158,7 @@ def render_cuda_orthographic(extrinsics: Tensor, width: Tensor, height: Tensor, 
     if dump is not None:
         dump.update(extrinsics=extrinsics, fov_x=fov_x, fov_y=fov_y, near=near, far=far)
     projection_matrix = get_projection_matrix(near, far, fov_x.expand(b), fov_y).transpose(1, 2)
-    view_matrix = extrinsics.inverse().transpose(1, 2)
+    view_matrix = inverse(extrinsics).transpose(1, 2)
     full_projection = view_matrix @ projection_matrix
     return _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x.expand(b).tolist(),
                             tan_fov_y.expand(b).tolist(), image_shape, background_color, gaussian_means,
@@ -159,7 +181,7 @@ def render_depth_cuda(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
                       gaussian_opacities: Tensor, scale_invariant: bool = True,
                       mode: DepthRenderingMode = "depth") -> Tensor:
     """Depth-as-colour render [b,h,w] (cuda_splatting.py:226-269)."""
-    w2c = extrinsics.inverse()
+    w2c = inverse(extrinsics)
     cam = torch.einsum("bij,bgj->bgi", w2c[:, :3, :3], gaussian_means) + w2c[:, None, :3, 3]
     fake_color = _depth_colors(cam[..., 2], near, far, mode)
     b = fake_color.shape[0]
@@ -207,7 +229,7 @@ def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image
                      scale_invariant: bool = True, mode: DepthRenderingMode = "depth") -> Tensor:
     """Radial-distance-as-colour equirectangular render [b,h,w] -- the quantity the reference converts its
     cube-face z-depth to before stitching (/root/reference/src/model/model_wrapper_erp.py:447-457)."""
-    w2c = extrinsics_sphere.inverse()
+    w2c = inverse(extrinsics_sphere)
     cam = torch.einsum("bij,bgj->bgi", w2c[:, :3, :3], gaussian_means) + w2c[:, None, :3, 3]
     fake_color = _depth_colors(cam.norm(dim=-1), near, far, mode)
     b = fake_color.shape[0]
@@ -222,25 +244,6 @@ def render_depth_erp(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image
 # ------------------------------------------------------------------------------------------------
 # batched multi-view path: every view of a batch item in ONE rasterizer pass
 MAX_VIEWS_PER_PASS = 12   # two sets of cube faces; the pair buffers grow with views x Gaussians
-
-# The rasterizer settings carry tan(fov/2), the 1/near scale, near and far as HOST floats (as upstream's do), so a decoder
-# call has to read them back from the intrinsics / near / far tensors: one device -> host wait per call, which stalls a
-# render loop that is otherwise asynchronous.  The same tensor objects (same storage, same in-place version counter) give
-# the same host values, so those are remembered; the cache holds the tensors, which keeps their storage from being reused.
-_HOST_SCALARS: dict = {}
-
-
-def _host_scalars(key_tensors, flag, compute):
-    key = (flag,) + tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in key_tensors)
-    hit = _HOST_SCALARS.get(key)
-    if hit is not None:
-        return hit[1]
-    val = compute()
-    if len(_HOST_SCALARS) >= 16:
-        _HOST_SCALARS.pop(next(iter(_HOST_SCALARS)))
-    _HOST_SCALARS[key] = (tuple(key_tensors), val)
-    return val
-
 
 def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
                      gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh, projection,
@@ -302,7 +305,7 @@ def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     degree = isqrt(n) - 1
     fov_x, fov_y = get_fov(intrinsics.reshape(b * v, 3, 3)).unbind(dim=-1)
     projection_matrix = get_projection_matrix(near_s.reshape(-1), far_s.reshape(-1), fov_x, fov_y).transpose(1, 2)
-    view_matrix = extrinsics.reshape(b * v, 4, 4).inverse().transpose(1, 2)
+    view_matrix = inverse(extrinsics.reshape(b * v, 4, 4)).transpose(1, 2)
     full_projection = (view_matrix @ projection_matrix).reshape(b, v, 4, 4)
     view_matrix = view_matrix.reshape(b, v, 4, 4)
     host = _host_scalars((intrinsics, near, far), bool(scale_invariant), lambda: [[tuple(x) for x in row] for row in torch.stack(
@@ -327,7 +330,7 @@ def render_erp_views(extrinsics_sphere: Tensor, near: Tensor, far: Tensor, image
         extrinsics_sphere[..., :3, 3] = extrinsics_sphere[..., :3, 3] * scale[..., None]
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    view_matrix = extrinsics_sphere.reshape(b * v, 4, 4).inverse().transpose(1, 2).reshape(b, v, 4, 4)
+    view_matrix = inverse(extrinsics_sphere.reshape(b * v, 4, 4)).transpose(1, 2).reshape(b, v, 4, 4)
     host = torch.stack((torch.ones_like(near), torch.ones_like(near), scale, near, far), -1).tolist()
     host = [[tuple(x) for x in row] for row in host]
     return _rasterize_views(extrinsics_sphere, view_matrix, view_matrix, host, image_shape, background_color,
