@@ -116,20 +116,22 @@ def build_scene(device, seed):
 
 
 def algorithmic_bytes(P, P_vis, N):
-    """Per-view algorithmic HBM bytes per stage (SURVEY.md sec. 8d adapted to the 48-B
-    geometry record and the depth-sort + tile-sort split)."""
+    """Per-view algorithmic HBM bytes per stage (SURVEY.md sec. 8d adapted to the 48-B geometry record,
+    the 36-B SH Jacobian and matrix binning).  Stage names are the library's timer slots: in the matrix-binning path
+    "emit" = count matrix (mb_count), "scan" = column scan (mb_colscan), "tile_sort" = ranked scatter (mb_scatter)."""
     npix = H * W
     tiles = (H // 16) * (W // 16)
+    chunks = (P + 2047) // 2048
     return {
-        "preprocess": 340 * P + 48 * P_vis + (4 + 8 + 1 + 8) * P,          # inputs; geom record; radii+rect+clamp+key/id
-        "depth_sort": 4 * (4 + 8 + 8) * P + 4 * P,                          # 4 passes x (hist read 4 + scatter r/w 16) + order copy
-        "scan": (4 + 8) * 2 * P + 4 * P,                                    # two gathers of (id, rect) + offsets write
-        "emit": (4 + 8 + 4) * P + 8 * N,                                    # id, rect, offset in; (tile, id) out
-        "tile_sort": 2 * (4 + 8 + 8) * N,                                   # 2 passes over 11-bit tile ids
-        "tile_ranges": 4 * N + 8 * tiles,
+        "preprocess": 340 * P + (48 + 36) * P_vis + (4 + 8 + 1 + 8) * P,     # inputs; geom record + SH Jacobian; radii+rect+clamp+key/id
+        "depth_sort": 4 * (4 + 8 + 8) * P + 4 * P,                          # hist read + 4 passes x scatter r/w 16 B
+        "scan": 2 * 4 * chunks * tiles,                                     # count matrix read + prefix write
+        "emit": (4 + 8) * P + 4 * chunks * tiles,                           # id + rect gather; count matrix row out
+        "tile_sort": (4 + 8) * P + 4 * chunks * tiles + 8 * tiles + 4 * N,  # id + rect, prefix row, ranges; 4 B per instance out
+        "tile_ranges": 4 * tiles + 8 * tiles + 8 * tiles,
         "render_fwd": (4 + 48) * N + 20 * npix,                             # id + record per instance; colour + T + n_contrib out
         "render_bwd": 20 * npix + (4 + 48) * N + 72 * N,                    # pixel grads, T, n_contrib; instance refetch; 36-B grad record r-m-w
-        "preprocess_bwd": 48 * P + (340 + 48) * P_vis + 352 * P,            # accumulator (zero fill + read), inputs again, all gradient writes
+        "preprocess_bwd": 2 * 48 * P + (12 + 24 + 4 + 36 + 1 + 4) * P_vis + 352 * P,   # accumulator zero-fill + read; inputs + Jacobian; all gradient writes
     }
 
 
@@ -385,10 +387,10 @@ def run_ours(args):
         import re
         kname = {"render_bwd": "render_backward_kernel", "render_fwd": "render_forward_kernel",
                  "preprocess": "preprocess_kernel", "preprocess_bwd": "preprocess_backward_kernel"}.get(dom)
-        txt = open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.txt")).read()
+        txt = open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.txt")).read()
         blk = next(b for b in txt.split("== ")[1:] if kname and kname in b.split("\n")[0])
         pick = lambda key: float(re.search(key + r"\s+([\d.]+)", blk).group(1))
-        ncu_note = {"source": "profiles/r01_ncu_full_summary.txt (ncu --set full of this command)",
+        ncu_note = {"source": "profiles/r02_ncu_full_summary.txt (ncu --set full of this command)",
                     "issue_slot_utilisation_pct": pick("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                     "fma_pipe_utilisation_pct": pick("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
                     "dram_utilisation_pct": pick("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")}

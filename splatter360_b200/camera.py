@@ -27,19 +27,27 @@ def inverse(m: Tensor) -> Tensor:
     return torch.linalg.inv_ex(m).inverse
 
 
+_EDGE_RAYS: dict = {}
+
+
+def _edge_rays(device) -> Tensor:
+    """[4, 3] image-plane points (left, right, top, bottom) on ``device``, built once: ``torch.tensor(list, device=cuda)`` is a
+    blocking pageable-memory upload, and the reference's ``get_fov`` does four of them per call."""
+    key = str(device)
+    t = _EDGE_RAYS.get(key)
+    if t is None:
+        t = torch.tensor([[0, 0.5, 1], [1, 0.5, 1], [0.5, 0, 1], [0.5, 1, 1]], dtype=torch.float32).to(device)
+        _EDGE_RAYS[key] = t
+    return t
+
+
 def get_fov(intrinsics: Tensor) -> Tensor:
     """Field of view [b,2] (x, y) from normalised intrinsics [b,3,3] via the edge-ray angle."""
     inv = inverse(intrinsics)
-
-    def ray(v):
-        v = torch.tensor(v, dtype=torch.float32, device=intrinsics.device)
-        v = torch.einsum("bij,j->bi", inv, v)
-        return v / v.norm(dim=-1, keepdim=True)
-
-    left, right = ray([0, 0.5, 1]), ray([1, 0.5, 1])
-    top, bottom = ray([0.5, 0, 1]), ray([0.5, 1, 1])
-    fov_x = (left * right).sum(dim=-1).acos()
-    fov_y = (top * bottom).sum(dim=-1).acos()
+    rays = torch.einsum("bij,kj->bki", inv, _edge_rays(intrinsics.device))      # [b, 4, 3]
+    rays = rays / rays.norm(dim=-1, keepdim=True)
+    fov_x = (rays[:, 0] * rays[:, 1]).sum(dim=-1).acos()
+    fov_y = (rays[:, 2] * rays[:, 3]).sum(dim=-1).acos()
     return torch.stack((fov_x, fov_y), dim=-1)
 
 

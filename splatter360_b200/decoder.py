@@ -303,13 +303,19 @@ def render_cuda_views(extrinsics: Tensor, intrinsics: Tensor, near: Tensor, far:
     near_s, far_s = near * scale, far * scale
     n = gaussian_sh_coefficients.shape[-1]
     degree = isqrt(n) - 1
-    fov_x, fov_y = get_fov(intrinsics.reshape(b * v, 3, 3)).unbind(dim=-1)
-    projection_matrix = get_projection_matrix(near_s.reshape(-1), far_s.reshape(-1), fov_x, fov_y).transpose(1, 2)
+    def intrinsic_block():
+        # everything that depends only on (intrinsics, near, far): the projection matrices on the device and the host
+        # scalars of the settings -- remembered per input tensors, so a render loop over poses pays for them once
+        fov_x, fov_y = get_fov(intrinsics.reshape(b * v, 3, 3)).unbind(dim=-1)
+        proj = get_projection_matrix(near_s.reshape(-1), far_s.reshape(-1), fov_x, fov_y).transpose(1, 2)
+        hs = [[tuple(x) for x in row] for row in torch.stack(
+            ((0.5 * fov_x).tan().reshape(b, v), (0.5 * fov_y).tan().reshape(b, v), scale, near, far), -1).tolist()]
+        return hs, proj
+
+    host, projection_matrix = _host_scalars((intrinsics, near, far), bool(scale_invariant), intrinsic_block)
     view_matrix = inverse(extrinsics.reshape(b * v, 4, 4)).transpose(1, 2)
     full_projection = (view_matrix @ projection_matrix).reshape(b, v, 4, 4)
     view_matrix = view_matrix.reshape(b, v, 4, 4)
-    host = _host_scalars((intrinsics, near, far), bool(scale_invariant), lambda: [[tuple(x) for x in row] for row in torch.stack(
-        ((0.5 * fov_x).tan().reshape(b, v), (0.5 * fov_y).tan().reshape(b, v), scale, near, far), -1).tolist()])
     return _rasterize_views(extrinsics, view_matrix, full_projection, host, image_shape, background_color, gaussian_means,
                             gaussian_covariances, gaussian_sh_coefficients, gaussian_opacities, degree, use_sh,
                             "pinhole", fused_depth_mode, max_views_per_pass, capacity_trackers)

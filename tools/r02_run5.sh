@@ -19,4 +19,4 @@ try:
   print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, 'e2e', d['e2e'] and {k:d['e2e'][k] for k in ('value','ms_per_step')})
 except Exception as e: print('ERR', e)
 "; done
-tail -3 gpurun_out/r02e_c5_n$N.err gpurun_out/r02e_c4_n$N.err gpurun_out/r02e_c3_n$N.err
+tail -n 3 gpurun_out/r02e_c5_n$N.err gpurun_out/r02e_c4_n$N.err gpurun_out/r02e_c3_n$N.err
