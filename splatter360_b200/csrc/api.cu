@@ -70,7 +70,9 @@ static bool force_radix() {
 }
 static int64_t tiles_of(int H, int W, int V = 1) { return (int64_t)V * ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE); }
 // n_items: Gaussians (or pair capacity) the binning stage walks
-static bool use_matrix(int64_t n_items, int H, int W, int V = 1) { return !force_radix() && matrix_binning_ok(n_items, tiles_of(H, W, V)); }
+static bool use_matrix(int64_t n_items, int H, int W, int V = 1) {
+  return !force_radix() && matrix_binning_ok(n_items, tiles_of(H, W, V), (W + TILE - 1) / TILE);
+}
 
 static size_t bin_scratch_carve(void* buf, int64_t cap, int H, int W, BinScratch* out, int V = 1) {
   char* p = (char*)buf;

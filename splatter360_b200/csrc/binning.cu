@@ -454,13 +454,11 @@ emit_instances_kernel(int P_cap, const uint32_t* __restrict__ n_dev, int gx, int
 // to emit + two stable radix passes, with 4 B written per instance instead of 8 B emitted + 2 x 16 B sorted, and no
 // scan of per-Gaussian offsets at all.  Used whenever tiles <= MB_MAX_TILES and the matrix stays small.
 constexpr int MB_CHUNK = 2048;
-constexpr int MB_MAX_TILES = 8192;
-#ifndef S360_MB_BALLOT_MATCH
-#define S360_MB_BALLOT_MATCH 0
-#endif
+constexpr int MB_MAX_TILES = 8192;    // shared-memory tile histogram of the count kernel: 32 KB
+constexpr int MB_BAND_TILES = 2048;   // tiles per band of the scatter kernel (and the widest supported tile row)
 
-bool matrix_binning_ok(int64_t n_items, int64_t tiles) {
-  if (tiles <= 0 || tiles > MB_MAX_TILES || n_items <= 0) return false;
+bool matrix_binning_ok(int64_t n_items, int64_t tiles, int gx) {
+  if (tiles <= 0 || tiles > MB_MAX_TILES || gx > MB_BAND_TILES || n_items <= 0) return false;
   const int64_t chunks = (n_items + MB_CHUNK - 1) / MB_CHUNK;
   return chunks * tiles * 4 <= (256ll << 20);
 }
@@ -625,17 +623,23 @@ mb_colscan_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int ntiles, uin
   }
 }
 
+// blockIdx.y = band of tile rows [band * band_rows, (band + 1) * band_rows): every Gaussian's rectangle is clipped to the
+// band, so the per-warp counters cover band_rows * gx <= MB_BAND_TILES tiles whatever the image size (instances of
+// different tiles never interact, so bands are independent); small images have one band.
 template <int NW>
 __global__ void __launch_bounds__(NW * 32)
-mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int ntiles, int tbits, int mode,
+mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy, int band_rows, int ntiles, int mode,
                   const uint2* __restrict__ rect, const uint32_t* __restrict__ order, const uint32_t* __restrict__ prefix,
                   const uint2* __restrict__ ranges, int64_t capacity, uint32_t* __restrict__ point_list,
                   S360Counters* counters) {
   extern __shared__ uint32_t s_mem[];
   constexpr int ROUNDS = MB_CHUNK / (NW * 32);
-  const int half = (ntiles + 1) >> 1;            // u16 counters, two per word
-  uint32_t* s_base = s_mem;                      // [ntiles]  first slot of this chunk's instances of the tile
-  uint32_t* s_cnt32 = s_mem + ntiles;            // [NW][half] per-warp counters -> exclusive prefixes over the warps
+  const int y_lo = (int)blockIdx.y * band_rows, y_hi = min(y_lo + band_rows, gy);
+  const int btiles = (y_hi - y_lo) * gx;         // tiles of this band
+  const uint32_t tile0 = (uint32_t)(y_lo * gx);  // first global tile id of the band
+  const int half = (band_rows * gx + 1) >> 1;    // u16 counters, two per word
+  uint32_t* s_base = s_mem;                      // [band tiles]  first slot of this chunk's instances of the tile
+  uint32_t* s_cnt32 = s_mem + band_rows * gx;    // [NW][half] per-warp counters -> exclusive prefixes over the warps
   const int n = (int)effective_n(n_cap, n_dev);
   const int base = (int)blockIdx.x * MB_CHUNK;
   if (base >= n) return;
@@ -651,11 +655,17 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int nti
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++) {
     const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
-    rc[r] = i < n ? rect[gid[r]] : make_uint2(0u, 0u);
+    uint2 q = i < n ? rect[gid[r]] : make_uint2(0u, 0u);
+    if (gridDim.y > 1) {   // clip the rows to the band (an empty intersection has no cells)
+      const int r0 = (int)(q.y & 0xffffu), r1 = r0 + (int)(q.y >> 16);
+      const int c0 = max(r0, y_lo), c1 = min(r1, y_hi);
+      q.y = c1 > c0 ? ((uint32_t)c0 | ((uint32_t)(c1 - c0) << 16)) : 0u;
+    }
+    rc[r] = q;
   }
   {
-    const uint32_t* prow = prefix + (size_t)blockIdx.x * ntiles;
-    for (int t = threadIdx.x; t < ntiles; t += NW * 32) s_base[t] = ranges[t].x + prow[t];
+    const uint32_t* prow = prefix + (size_t)blockIdx.x * ntiles + tile0;
+    for (int t = threadIdx.x; t < btiles; t += NW * 32) s_base[t] = ranges[tile0 + t].x + prow[t];
   }
   __syncthreads();
   // pass 1: instances per (warp, tile); packed u16 pairs take native 32-bit shared-memory adds
@@ -663,7 +673,7 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int nti
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
     expand_unordered(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
-                     [&](uint32_t tile) { atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
+                     [&](uint32_t tile) { tile -= tile0; atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
   __syncthreads();
   // exclusive prefix over the warps, both halves of a word at once (a chunk has at most MB_CHUNK instances per tile)
   for (int j = threadIdx.x; j < half; j += NW * 32) {
@@ -672,25 +682,17 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int nti
     for (int w = 0; w < NW; w++) { const uint32_t c = s_cnt32[w * half + j]; s_cnt32[w * half + j] = run; run += c; }
   }
   __syncthreads();
-  // pass 2: in-order ranking.  Lanes of one batch that hit the same tile are found with MATCH.ANY (S360_MB_BALLOT_MATCH=1:
-  // one ballot per tile-id bit instead -- measured 3x more instructions per batch); all of them read the warp's counter of
-  // that tile (shared-memory broadcast), the lowest one then advances it by the size of the group.
+  // pass 2: in-order ranking.  Lanes of one batch that hit the same tile are found with MATCH.ANY (eleven ballots, one per
+  // tile-id bit, measured the same: the kernel is latency-bound); all of them read the warp's counter of that tile
+  // (shared-memory broadcast), the lowest one then advances it by the size of the group.
   unsigned short* my16 = reinterpret_cast<unsigned short*>(my32);
   const unsigned lt_mask = (1u << lane) - 1u;
   bool overflow = false;
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
     expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode, [&](uint32_t tile, uint32_t g, bool valid) {
-#if S360_MB_BALLOT_MATCH
-      unsigned peers = __ballot_sync(0xffffffffu, valid);
-      for (int b = 0; b < tbits; b++) {
-        const bool bit = (tile >> b) & 1u;
-        const unsigned bal = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? bal : ~bal;
-      }
-#else
-      const unsigned peers = __match_any_sync(0xffffffffu, tile);   // lanes past the end carry 0xffffffff and match each other
-#endif
+      tile -= tile0;   // lanes past the end carry 0xffffffff - tile0: still equal to each other, never dereferenced
+      const unsigned peers = __match_any_sync(0xffffffffu, tile);
       uint32_t old = 0;
       if (valid) old = my16[tile];
       __syncwarp();
@@ -704,7 +706,6 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int nti
   if (overflow) atomicOr(&counters->overflow, 1u);
 }
 
-static int mb_tile_bits(int ntiles) { int b = 0; while ((1 << b) < ntiles) b++; return b; }
 
 // scratch: [matrix chunks x tiles][tile totals]; the three launchers below run in this order with the tile scan
 // (launch_tile_scan with copies = 1 on mb_tile_totals) between the column scan and the scatter
@@ -743,16 +744,16 @@ int launch_mb_scatter(const S360View& v, int NV, int64_t n_items, const uint32_t
   const int ntiles = gx * gy;
   const int chunks = (int)((n_items + MB_CHUNK - 1) / MB_CHUNK);
   if (chunks == 0) return 0;
-  // warps per chunk: as many as the per-warp tile counters (u16 x tiles each) allow within ~100 KB of shared memory
-  const int nw = ntiles <= 2048 ? 16 : ntiles <= 4096 ? 8 : 4;
-  const size_t smem = (size_t)ntiles * 4 + (size_t)nw * ((ntiles + 1) / 2) * 4;
+  // 16 warps per chunk; tile rows are cut into bands of at most MB_BAND_TILES tiles so that the per-warp u16 counters stay
+  // at 4 KB per warp (72 KB per CTA, three CTAs per SM) whatever the image size -- 1024x2048 (8192 tiles) = four bands
+  const int band_rows = max(1, MB_BAND_TILES / gx);
+  const int bands = (gy + band_rows - 1) / band_rows;
+  const int btiles = band_rows * gx;
+  const size_t smem = (size_t)btiles * 4 + (size_t)16 * ((btiles + 1) / 2) * 4;
   const uint32_t* prefix = (const uint32_t*)scratch;
-#define S360_SCATTER(NW_) do { \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    mb_scatter_kernel<NW_><<<chunks, NW_ * 32, smem, st>>>((int)n_items, n_dev, gx, ntiles, mb_tile_bits(ntiles), v.mode, g.rect, \
-                                                         depth_order, prefix, ranges, capacity, point_list, counters); } while (0)
-  if (nw == 16) S360_SCATTER(16); else if (nw == 8) S360_SCATTER(8); else S360_SCATTER(4);
-#undef S360_SCATTER
+  if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mb_scatter_kernel<16><<<dim3(chunks, bands), 512, smem, st>>>((int)n_items, n_dev, gx, gy, band_rows, ntiles, v.mode, g.rect,
+                                                               depth_order, prefix, ranges, capacity, point_list, counters);
   count_launch();
   return (int)cudaGetLastError();
 }

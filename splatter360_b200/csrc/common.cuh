@@ -426,7 +426,7 @@ int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, int 
                      uint32_t* order, uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st);
 // matrix binning (binning.cu): depth order -> point_list sorted by (tile, depth, id) + tile ranges + schedule, without
 // materialising (tile, id) keys; usable when matrix_binning_ok(items, tiles)
-bool matrix_binning_ok(int64_t n_items, int64_t tiles);
+bool matrix_binning_ok(int64_t n_items, int64_t tiles, int gx);
 size_t matrix_scratch_bytes(int64_t n_items, int64_t tiles);
 uint32_t* mb_tile_totals(void* scratch, int64_t n_items, int ntiles);
 int launch_mb_count(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, GeomState g,
