@@ -404,6 +404,12 @@ def run_ours(args):
         "whole_step": {"algorithmic_bytes": whole, "achieved": whole / (ms_per_step * 1e-3) / 1e9,
                        "frac": whole / (ms_per_step * 1e-3) / 1e9 / peak},
         "stages_ms": stage_ms,
+        "stage_timing": ("CUDA events recorded by the library around every stage on the launching stream; the timed region itself is "
+                         "ONE graph launch per step (events cannot be recorded inside a replayed graph), so the per-stage events come from "
+                         "an eager pass over the same steps right after it (bench.py --no-graph has them inside the timed region: same numbers)"
+                         if graphed is not None else "CUDA events recorded by the library around every stage on the launching stream, inside the timed region"),
+        "stage_kernels": {"emit": "mb_count_kernel", "scan": "mb_colscan_kernel", "tile_ranges": "tile_scan_kernel", "tile_sort": "mb_scatter_kernel",
+                          "depth_sort": "rs_global_hist_kernel + 4 x rs_onesweep_kernel"},
         "stages_GBps": {k: (alg[k] / (stage_ms[k] * 1e-3) / 1e9 if stage_ms[k] > 0 else None) for k in alg},
         "instances": {"P": P, "P_visible": P_vis, "N": N},
         "ncu": ncu_note,

@@ -625,8 +625,10 @@ mb_colscan_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int ntiles, uin
 
 // blockIdx.y = band of tile rows [band * band_rows, (band + 1) * band_rows): every Gaussian's rectangle is clipped to the
 // band, so the per-warp counters cover band_rows * gx <= MB_BAND_TILES tiles whatever the image size (instances of
-// different tiles never interact, so bands are independent); small images have one band.
-template <int NW>
+// different tiles never interact, so bands are independent); small images have one band (BANDED = false).  With bands,
+// every warp first compacts its 128 Gaussians to those that reach the band (order preserved, staged in shared memory):
+// the rounds of the two passes then run over the survivors only, not over four times as many mostly empty rounds.
+template <int NW, bool BANDED>
 __global__ void __launch_bounds__(NW * 32)
 mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy, int band_rows, int ntiles, int mode,
                   const uint2* __restrict__ rect, const uint32_t* __restrict__ order, const uint32_t* __restrict__ prefix,
@@ -640,6 +642,7 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy,
   const int half = (band_rows * gx + 1) >> 1;    // u16 counters, two per word
   uint32_t* s_base = s_mem;                      // [band tiles]  first slot of this chunk's instances of the tile
   uint32_t* s_cnt32 = s_mem + band_rows * gx;    // [NW][half] per-warp counters -> exclusive prefixes over the warps
+  uint32_t* s_list = s_cnt32 + NW * half;        // BANDED: [NW][ROUNDS * 32][3] compacted (gid, rect.x, rect.y) per warp
   const int n = (int)effective_n(n_cap, n_dev);
   const int base = (int)blockIdx.x * MB_CHUNK;
   if (base >= n) return;
@@ -652,16 +655,39 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy,
     const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
     gid[r] = i < n ? order[i] : 0u;
   }
+  int nrounds = ROUNDS;
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++) {
     const int i = base + warp * (ROUNDS * 32) + r * 32 + lane;
-    uint2 q = i < n ? rect[gid[r]] : make_uint2(0u, 0u);
-    if (gridDim.y > 1) {   // clip the rows to the band (an empty intersection has no cells)
+    rc[r] = i < n ? rect[gid[r]] : make_uint2(0u, 0u);
+  }
+  if (BANDED) {
+    uint32_t* my_list = s_list + warp * (ROUNDS * 32 * 3);
+    int kept = 0;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      // clip the rows to the band (an empty intersection has no cells)
+      const uint2 q = rc[r];
       const int r0 = (int)(q.y & 0xffffu), r1 = r0 + (int)(q.y >> 16);
       const int c0 = max(r0, y_lo), c1 = min(r1, y_hi);
-      q.y = c1 > c0 ? ((uint32_t)c0 | ((uint32_t)(c1 - c0) << 16)) : 0u;
+      const bool keep = c1 > c0 && (q.x >> 16) != 0u;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        uint32_t* e = my_list + 3 * (kept + __popc(m & ((1u << lane) - 1u)));
+        e[0] = gid[r]; e[1] = q.x; e[2] = (uint32_t)c0 | ((uint32_t)(c1 - c0) << 16);
+      }
+      kept += __popc(m);
     }
-    rc[r] = q;
+    nrounds = (kept + 31) >> 5;
+    __syncwarp();
+    // re-read as rounds of 32 survivors (the tail of the last round has no cells)
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+      const int k = r * 32 + lane;
+      const bool in = k < kept;
+      gid[r] = in ? my_list[3 * k] : 0u;
+      rc[r] = in ? make_uint2(my_list[3 * k + 1], my_list[3 * k + 2]) : make_uint2(0u, 0u);
+    }
   }
   {
     const uint32_t* prow = prefix + (size_t)blockIdx.x * ntiles + tile0;
@@ -672,8 +698,9 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy,
   uint32_t* my32 = s_cnt32 + warp * half;
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
-    expand_unordered(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
-                     [&](uint32_t tile) { tile -= tile0; atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
+    if (r < nrounds)
+      expand_unordered(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode,
+                       [&](uint32_t tile) { tile -= tile0; atomicAdd(&my32[tile >> 1], 1u << ((tile & 1u) * 16u)); });
   __syncthreads();
   // exclusive prefix over the warps, both halves of a word at once (a chunk has at most MB_CHUNK instances per tile)
   for (int j = threadIdx.x; j < half; j += NW * 32) {
@@ -690,22 +717,22 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy,
   bool overflow = false;
 #pragma unroll
   for (int r = 0; r < ROUNDS; r++)
-    expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode, [&](uint32_t tile, uint32_t g, bool valid) {
-      tile -= tile0;   // lanes past the end carry 0xffffffff - tile0: still equal to each other, never dereferenced
-      const unsigned peers = __match_any_sync(0xffffffffu, tile);
-      uint32_t old = 0;
-      if (valid) old = my16[tile];
-      __syncwarp();
-      if (valid && (peers & lt_mask) == 0u) my16[tile] = (unsigned short)(old + (uint32_t)__popc(peers));
-      __syncwarp();
-      if (valid) {
-        const uint32_t dst = s_base[tile] + old + (uint32_t)__popc(peers & lt_mask);
-        if ((int64_t)dst < capacity) point_list[dst] = g; else overflow = true;
-      }
-    });
+    if (r < nrounds)
+      expand_group(gid[r], rc[r], rect_tiles(rc[r]), lane, gx, mode, [&](uint32_t tile, uint32_t g, bool valid) {
+        tile -= tile0;   // lanes past the end carry 0xffffffff - tile0: still equal to each other, never dereferenced
+        const unsigned peers = __match_any_sync(0xffffffffu, tile);
+        uint32_t old = 0;
+        if (valid) old = my16[tile];
+        __syncwarp();
+        if (valid && (peers & lt_mask) == 0u) my16[tile] = (unsigned short)(old + (uint32_t)__popc(peers));
+        __syncwarp();
+        if (valid) {
+          const uint32_t dst = s_base[tile] + old + (uint32_t)__popc(peers & lt_mask);
+          if ((int64_t)dst < capacity) point_list[dst] = g; else overflow = true;
+        }
+      });
   if (overflow) atomicOr(&counters->overflow, 1u);
 }
-
 
 // scratch: [matrix chunks x tiles][tile totals]; the three launchers below run in this order with the tile scan
 // (launch_tile_scan with copies = 1 on mb_tile_totals) between the column scan and the scatter
@@ -749,11 +776,14 @@ int launch_mb_scatter(const S360View& v, int NV, int64_t n_items, const uint32_t
   const int band_rows = max(1, MB_BAND_TILES / gx);
   const int bands = (gy + band_rows - 1) / band_rows;
   const int btiles = band_rows * gx;
-  const size_t smem = (size_t)btiles * 4 + (size_t)16 * ((btiles + 1) / 2) * 4;
+  const size_t smem = (size_t)btiles * 4 + (size_t)16 * ((btiles + 1) / 2) * 4 + (bands > 1 ? (size_t)MB_CHUNK * 3 * 4 : 0);
   const uint32_t* prefix = (const uint32_t*)scratch;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mb_scatter_kernel<16><<<dim3(chunks, bands), 512, smem, st>>>((int)n_items, n_dev, gx, gy, band_rows, ntiles, v.mode, g.rect,
-                                                               depth_order, prefix, ranges, capacity, point_list, counters);
+#define S360_SCATTER(BANDED_) do { \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<16, BANDED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    mb_scatter_kernel<16, BANDED_><<<dim3(chunks, bands), 512, smem, st>>>((int)n_items, n_dev, gx, gy, band_rows, ntiles, v.mode, \
+        g.rect, depth_order, prefix, ranges, capacity, point_list, counters); } while (0)
+  if (bands > 1) S360_SCATTER(true); else S360_SCATTER(false);
+#undef S360_SCATTER
   count_launch();
   return (int)cudaGetLastError();
 }
