@@ -124,6 +124,35 @@ def broadcast_scene(tensors: Sequence[Tensor], src: int = 0) -> None:
         dist.broadcast(t, src=src)
 
 
+def upload_and_broadcast_scene(host: Optional[Sequence[Tensor]], bufs: Sequence[Tensor], src: int = 0,
+                               chunk_bytes: int = 64 << 20, copy_stream: Optional["torch.cuda.Stream"] = None) -> None:
+    """Replicated-scene upload: rank ``src`` holds the scene in (pinned) host tensors ``host``; every rank ends up with it in
+    its device buffers ``bufs`` (same shapes).  The tensors are cut into chunks of ``chunk_bytes``: rank ``src`` uploads chunk
+    k+1 over PCIe on a copy stream while chunk k is being broadcast over NVLink / NVSwitch (NCCL), so the broadcast costs
+    (almost) nothing on top of the single upload.  Stream-ordered on the current stream; other ranks pass ``host=None``."""
+    rank, ws = world()
+    cur = torch.cuda.current_stream(bufs[0].device)
+    if rank == src:
+        if host is None:
+            raise ValueError("the source rank needs the host tensors")
+        side = copy_stream if copy_stream is not None else torch.cuda.Stream(device=bufs[0].device)
+        side.wait_stream(cur)   # the buffers may still be read by earlier work on the current stream
+    for i, b in enumerate(bufs):
+        flat = b.view(-1)
+        per = max(1, chunk_bytes // flat.element_size())
+        hflat = host[i].view(-1) if rank == src else None
+        for o in range(0, flat.numel(), per):
+            piece = flat[o:o + per]
+            if rank == src:
+                with torch.cuda.stream(side):
+                    piece.copy_(hflat[o:o + per], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                cur.wait_event(ev)
+            if ws > 1:
+                dist.broadcast(piece, src=src)
+
+
 def gather_views(local: Tensor, num_views: int) -> Tensor:
     """Reassemble the [num_views, ...] stack from the round-robin shards ``local`` [len(shard), ...] held by each
     rank (evaluation / video paths that need every frame on every rank)."""

@@ -4,6 +4,8 @@
      views rendered by ONE GPU (SURVEY.md sec. 4b "8-rank view sharding reproduces the single-GPU images bit-for-bit").
   2. per-rank gradients of the per-view losses + parallel.all_reduce_gradients == the single-GPU sum over all views.
   3. parallel.broadcast_scene: the scene built on rank 0 only arrives bit-identical on every rank.
+  4. parallel.upload_and_broadcast_scene: the same from pinned host tensors on rank 0, uploaded in small chunks that are
+     broadcast while the next chunk uploads.
 Prints 'MULTIRANK OK <world>' on rank 0; any mismatch raises."""
 import os
 import sys
@@ -34,6 +36,11 @@ def main():
     parallel.broadcast_scene(tensors, src=0)
     for a, b in zip(tensors, ref):
         assert torch.equal(a, b), "broadcast_scene changed the scene"
+    host = [t.cpu().pin_memory() for t in ref] if rank == 0 else None
+    bufs = [torch.zeros_like(t) for t in ref]
+    parallel.upload_and_broadcast_scene(host, bufs, src=0, chunk_bytes=100_000)   # many ragged chunks
+    for a, b in zip(bufs, ref):
+        assert torch.equal(a, b), "upload_and_broadcast_scene changed the scene"
     means, cov6, opac, shs = tensors
     cams = camera.erp_camera(synthetic.trajectory(V, seed=5).to(dev))
     dL = torch.randn(V, 3, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(9))
