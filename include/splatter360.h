@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define S360_ABI_VERSION 5
+#define S360_ABI_VERSION 6
 
 #define S360_MODE_PINHOLE 0 /* upstream semantics                     */
 #define S360_MODE_ERP 1     /* native equirectangular splatting      */
@@ -223,6 +223,12 @@ int s360_multi_backward(const S360View* view, int32_t V, int64_t pair_capacity, 
                         const float* dL_ddepth /* [V,H,W] or NULL */, int32_t depth_mode, float depth_near,
                         float depth_far, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dopacity, float* dL_dshs,
                         float* dL_dcolors, void* scratch, void* stream);
+
+/* ---- camera-to-world -> view matrix: batched inverse of n row-major 4x4 matrices (in != out).  Replaces
+ * `extrinsics.inverse()` of /root/reference/src/model/decoder/cuda_splatting.py:84, :176, :262 (a batched LU with a host
+ * status read-back) by one launch; partial pivoting, double-precision arithmetic rounded once to float; no singularity
+ * status (like torch.linalg.inv_ex). */
+int s360_invert4x4(const float* in, float* out, int64_t n, void* stream);
 
 /* ---- visibility mask (replaces upstream _C.mark_visible) ------------------------------------ */
 int s360_mark_visible(const S360View* view, const float* means3D, uint8_t* present, void* stream);

@@ -27,9 +27,9 @@ EXPORTS = [
     "s360_multi_image_bytes", "s360_multi_backward_scratch_bytes",
     "s360_multi_forward_project", "s360_multi_forward_order", "s360_multi_forward_render", "s360_multi_backward",
     "s360_debug_unpack_pairs", "s360_cube2equirec_forward", "s360_cube2equirec_backward", "s360_debug_counters",
-    "s360_adapter_forward", "s360_adapter_backward",
+    "s360_adapter_forward", "s360_adapter_backward", "s360_invert4x4",
 ]
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_VIEWS = 32
 
 STAGES = ["preprocess", "depth_sort", "scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "render_bwd",
@@ -97,6 +97,8 @@ def load() -> ctypes.CDLL:
     lib.s360_debug_unpack_geom.argtypes = [c_int32] + [vp] * 8
     lib.s360_debug_unpack_image.restype = c_int
     lib.s360_debug_unpack_image.argtypes = [c_int32, c_int32] + [vp] * 5
+    lib.s360_invert4x4.restype = c_int
+    lib.s360_invert4x4.argtypes = [vp, vp, c_int64, vp]
     lib.s360_mse_loss_grad.restype = c_int
     lib.s360_mse_loss_grad.argtypes = [vp, vp, c_int64, c_float, vp, vp, vp]
     lib.s360_profile_enable.restype = c_int

@@ -21,9 +21,24 @@ from torch import Tensor
 
 
 def inverse(m: Tensor) -> Tensor:
-    """``m.inverse()`` without the host round trip: torch's ``inverse`` reads the LU status back from the device to raise on
-    singular input, which stalls an otherwise asynchronous render loop once per call; ``linalg.inv_ex`` computes the same
+    """``m.inverse()`` of [..., 4, 4] camera matrices (the reference: cuda_splatting.py:84, :176, :262) without the host round
+    trip: torch's ``inverse`` is a batched LU over several launches that reads its status back from the device to raise on
+    singular input, which stalls an otherwise asynchronous render loop once per call.  CUDA float32 4x4 matrices that need
+    no gradient go through one launch of ``s360_invert4x4`` (also capturable in a CUDA graph); everything else (CPU tensors
+    of the argument-capture tests, 3x3 intrinsics, differentiable poses) through ``linalg.inv_ex``, which computes the same
     inverse and leaves the status on the device (camera matrices are never singular)."""
+    if (m.is_cuda and m.dtype == torch.float32 and m.shape[-2:] == (4, 4) and m.numel() > 0
+            and not (m.requires_grad and torch.is_grad_enabled())):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        src = m.detach().contiguous()
+        out = torch.empty_like(src)
+        with torch.cuda.device(m.device):
+            _lib.check(lib.s360_invert4x4(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                          ctypes.c_int64(src.numel() // 16),
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
     return torch.linalg.inv_ex(m).inverse
 
 

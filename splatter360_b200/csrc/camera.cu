@@ -1,0 +1,61 @@
+// camera.cu -- batched inverse of 4x4 camera matrices on the device.
+// The reference turns every camera-to-world pose into the rasterizer's view matrix with `extrinsics.inverse()`
+// (/root/reference/src/model/decoder/cuda_splatting.py:84, :176, :262): per call a cuSOLVER/cuBLAS batched LU (several
+// launches, pointer arrays uploaded from the host, a status read-back) for a handful of 4x4 matrices.  One thread per
+// matrix here: Gauss-Jordan with partial pivoting in double precision, rounded once to float -- within half an ulp of the
+// exact inverse, one launch, nothing on the host, capturable in a CUDA graph.  Singular input yields inf/nan like
+// `torch.linalg.inv_ex` (no status).
+#include "common.cuh"
+
+namespace s360 {
+
+__global__ void __launch_bounds__(64)
+invert4x4_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      a[r][c] = (double)in[i * 16 + r * 4 + c];
+      a[r][4 + c] = r == c ? 1.0 : 0.0;
+    }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    // partial pivoting: bring the largest |a[r][k]|, r >= k, to row k (conditional swaps keep everything in registers)
+#pragma unroll
+    for (int r = k + 1; r < 4; r++) {
+      if (fabs(a[r][k]) > fabs(a[k][k])) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) { const double t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t; }
+      }
+    }
+    const double inv = 1.0 / a[k][k];
+#pragma unroll
+    for (int c = 0; c < 8; c++) a[k][c] *= inv;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (r == k) continue;
+      const double f = a[r][k];
+#pragma unroll
+      for (int c = 0; c < 8; c++) a[r][c] -= f * a[k][c];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) out[i * 16 + r * 4 + c] = (float)a[r][4 + c];
+}
+
+}  // namespace s360
+
+using namespace s360;
+
+extern "C" int s360_invert4x4(const float* in, float* out, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (!in || !out))) return S360_ERR_BAD_ARGUMENT;
+  if (n == 0) return 0;
+  invert4x4_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(in, out, n);
+  count_launch();
+  return (int)cudaGetLastError();
+}

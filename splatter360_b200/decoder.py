@@ -54,6 +54,13 @@ def _host_scalars(key_tensors, flag, compute):
     return val
 
 
+def _batch_items(t: Tensor):
+    """The batch items of ``t`` [b, ...] as views whose backward costs nothing for b == 1 (the reference's batch size per GPU):
+    ``t[i]`` differentiates to a zero-filled [b, ...] tensor plus a copy of the item's gradient -- for the 300-B-per-Gaussian
+    harmonics of a 1M scene that is 0.6 GB of traffic per step, more than the rasterizer's own backward kernels."""
+    return (t.squeeze(0),) if t.shape[0] == 1 else t.unbind(0)
+
+
 def _triu6(cov: Tensor) -> Tensor:
     row, col = torch.triu_indices(3, 3)
     return cov[..., row, col]
@@ -69,8 +76,10 @@ def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fo
     b = extrinsics.shape[0]
     h, w = image_shape
     images, depths = [], []
+    means_b, opac_b, cov_b, sh_b = (_batch_items(t) for t in (gaussian_means, gaussian_opacities, gaussian_covariances,
+                                                              gaussian_sh_coefficients))
     for i in range(b):
-        mean_gradients = torch.zeros_like(gaussian_means[i], requires_grad=True)
+        mean_gradients = torch.zeros_like(means_b[i], requires_grad=True)
         try:
             mean_gradients.retain_grad()
         except Exception:
@@ -87,11 +96,11 @@ def _rasterize_batch(extrinsics, view_matrix, full_projection, tan_fov_x, tan_fo
             depth_near=0.0 if depth is None else float(depth[1][i]), depth_far=0.0 if depth is None else float(depth[2][i]),
             capacity_tracker=capacity_tracker[i] if isinstance(capacity_tracker, (list, tuple)) else capacity_tracker)
         out = GaussianRasterizer(settings)(
-            means3D=gaussian_means[i], means2D=mean_gradients,
-            shs=gaussian_sh_coefficients[i] if use_sh else None,
-            colors_precomp=None if use_sh else gaussian_sh_coefficients[i, :, :, 0],
-            opacities=gaussian_opacities[i, ..., None],
-            cov3D_precomp=gaussian_covariances[i])
+            means3D=means_b[i], means2D=mean_gradients,
+            shs=sh_b[i] if use_sh else None,
+            colors_precomp=None if use_sh else sh_b[i][:, :, 0],
+            opacities=opac_b[i][..., None],
+            cov3D_precomp=cov_b[i])
         images.append(out[0])
         if depth is not None:
             depths.append(out[2])
@@ -256,6 +265,8 @@ def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, b
     h, w = image_shape
     colors = torch.empty((b, v, 3, h, w), dtype=torch.float32, device=view_matrix.device)
     depths = torch.empty((b, v, h, w), dtype=torch.float32, device=view_matrix.device) if depth_mode is not None else None
+    means_b, opac_b, cov_b, sh_b = (_batch_items(t) for t in (gaussian_means, gaussian_opacities, gaussian_covariances,
+                                                              gaussian_sh_coefficients))
     for i in range(b):
         j = 0
         while j < v:
@@ -270,9 +281,9 @@ def _rasterize_views(cam_ext, view_matrix, full_projection, host, image_shape, b
                 scene_scale=scale, sh_layout=1, cov_layout=1, depth_mode=depth_mode, depth_near=near, depth_far=far,
                 capacity_tracker=None if capacity_trackers is None else capacity_trackers.setdefault((i, j), CapacityTracker()))
             out = rasterize_views(
-                gaussian_means[i], gaussian_opacities[i], gaussian_covariances[i], settings,
-                shs=gaussian_sh_coefficients[i] if use_sh else None,
-                colors_precomp=None if use_sh else gaussian_sh_coefficients[i, :, :, 0])
+                means_b[i], opac_b[i], cov_b[i], settings,
+                shs=sh_b[i] if use_sh else None,
+                colors_precomp=None if use_sh else sh_b[i][:, :, 0])
             if depth_mode is not None:
                 colors[i, j:k], depths[i, j:k] = out
             else:

@@ -243,7 +243,11 @@ class CapacityTracker:
 
     Until the first count has arrived the settings are returned unchanged (exact path).  An overflow can only be
     detected after the fact: ``overflowed`` lists the steps whose buffers were too small (their images / gradients are
-    incomplete and should be redone -- with the grown capacity the retry succeeds)."""
+    incomplete and should be redone -- with the grown capacity the retry succeeds).
+
+    ``freeze()`` pins the capacities for CUDA-graph capture (graph.GraphedAutogradStep): no polling, no asynchronous
+    copies; the tracker only remembers the device counters of the captured call, and ``frozen_overflowed()`` reads them
+    (one sync) whenever the caller wants to know whether the last replay fitted."""
 
     def __init__(self, margin: float = 1.25, min_capacity: int = 4096) -> None:
         self.margin, self.min_capacity = float(margin), int(min_capacity)
@@ -254,9 +258,26 @@ class CapacityTracker:
         self.overflowed: list = []
         self._pending: list = []
         self._step = 0
+        self.frozen = False
+        self._static_counters = None
+
+    def freeze(self) -> None:
+        self.flush()
+        if self.capacity is None:
+            raise RuntimeError("CapacityTracker.freeze: no count has been observed yet (run the call at least once)")
+        self.frozen = True
+
+    def unfreeze(self) -> None:
+        self.frozen, self._static_counters = False, None
+
+    def frozen_overflowed(self) -> bool:
+        """Did the last captured / replayed call need more than the frozen capacities?  Synchronises."""
+        c = self._static_counters
+        return c is not None and bool(int(c[1].item()) & 3)
 
     def settings(self, s: GaussianRasterizationSettings, pairs: bool = False) -> GaussianRasterizationSettings:
-        self.poll()
+        if not self.frozen:
+            self.poll()
         if self.capacity is None:
             return s
         if pairs:
@@ -266,6 +287,9 @@ class CapacityTracker:
     def observe(self, counters) -> None:
         """``counters``: the device int32[4] of a forward call (ForwardState.counters) or the state itself."""
         c = getattr(counters, "counters", counters)
+        if self.frozen:
+            self._static_counters = c
+            return
         host = torch.empty(4, dtype=torch.int32).pin_memory()
         host.copy_(c, non_blocking=True)
         ev = torch.cuda.Event()

@@ -49,3 +49,18 @@ torch.cuda.synchronize()
 s = io.StringIO()
 pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
 print(s.getvalue()[:6000])
+
+# device side: every kernel / memset / memcpy of the step by total time (torch.profiler, 10 steps)
+try:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(10):
+            step(5 + i)
+        torch.cuda.synchronize()
+    rows = sorted(((e.key, e.device_time_total / 10, e.count / 10) for e in prof.key_averages() if e.device_time_total > 0),
+                  key=lambda r: -r[1])
+    print(f"device time per step by kernel (us), total {sum(r[1] for r in rows):.1f} us over {sum(r[2] for r in rows):.0f} launches")
+    for k, us, n in rows[:45]:
+        print(f"{us:9.1f} us  x{n:4.1f}  {k[:110]}")
+except Exception as e:  # CUPTI may be unavailable on the box
+    print("torch.profiler unavailable:", e)
