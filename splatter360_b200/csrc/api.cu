@@ -10,6 +10,10 @@
 namespace s360 {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("S360_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 // ---- optional per-stage CUDA-event timing (off by default; bench.py turns it on) -------------
 static std::atomic<int> g_profile{0};

@@ -37,6 +37,7 @@ __device__ __forceinline__ int64_t effective_n(int64_t n_cap, const uint32_t* n_
 __global__ void __launch_bounds__(RS_THREADS)
 rs_global_hist_kernel(const uint32_t* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ n_dev, int npasses,
                       uint32_t* __restrict__ hist) {
+  pdl_enter();
   __shared__ uint32_t s_hist[4][RS_BINS];
   const int64_t n = effective_n(n_cap, n_dev);
   for (int i = threadIdx.x; i < 4 * RS_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
@@ -71,6 +72,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
                    const uint32_t* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
                    uint32_t* status, uint32_t* counter) {
+  pdl_enter();
   __shared__ uint32_t s_cnt[RS_WARPS][RS_BINS];   // per-warp digit counters -> exclusive warp prefixes
   __shared__ uint32_t s_keys[RS_TILE];
   __shared__ uint32_t s_vals[RS_TILE];
@@ -261,8 +263,8 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   for (int p = 0; p < passes; p++) {
     uint32_t* vdst = (vals_final != nullptr && p == passes - 1) ? vals_final : vo;   // last pass may write elsewhere
-    rs_onesweep_kernel<<<nblocks, RS_THREADS, 0, st>>>(ki, vi, ko, vdst, n, n_dev, 8 * p, hist + p * RS_BINS,
-                                                       status + (size_t)p * nblocks * RS_BINS, counters + p);
+    launch_pdl(rs_onesweep_kernel, dim3(nblocks), dim3(RS_THREADS), 0, st, ki, vi, ko, vdst, n, n_dev, 8 * p, hist + p * RS_BINS,
+               status + (size_t)p * nblocks * RS_BINS, counters + p);
     count_launch();
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
@@ -550,6 +552,7 @@ template <int NW>
 __global__ void __launch_bounds__(NW * 32)
 mb_count_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int ntiles, int mode,
                 const uint2* __restrict__ rect, const uint32_t* __restrict__ order, uint32_t* __restrict__ matrix) {
+  pdl_enter();
   extern __shared__ uint32_t s_cnt[];   // [ntiles]
   constexpr int ROUNDS = MB_CHUNK / (NW * 32);
   const int n = (int)effective_n(n_cap, n_dev);
@@ -581,6 +584,7 @@ mb_count_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int ntile
 // exclusive prefix over the chunks for every tile (in place) + instances per tile.  Block = 32 tiles x 32 chunk segments.
 __global__ void __launch_bounds__(1024)
 mb_colscan_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int ntiles, uint32_t* matrix, uint32_t* __restrict__ tile_total) {
+  pdl_enter();
   __shared__ uint32_t s_seg[32][33];
   const int n = (int)effective_n(n_cap, n_dev);
   const int n_chunks = (n + MB_CHUNK - 1) / MB_CHUNK;
@@ -634,6 +638,7 @@ mb_scatter_kernel(int n_cap, const uint32_t* __restrict__ n_dev, int gx, int gy,
                   const uint2* __restrict__ rect, const uint32_t* __restrict__ order, const uint32_t* __restrict__ prefix,
                   const uint2* __restrict__ ranges, int64_t capacity, uint32_t* __restrict__ point_list,
                   S360Counters* counters) {
+  pdl_enter();
   extern __shared__ uint32_t s_mem[];
   constexpr int ROUNDS = MB_CHUNK / (NW * 32);
   const int y_lo = (int)blockIdx.y * band_rows, y_hi = min(y_lo + band_rows, gy);
@@ -749,8 +754,8 @@ int launch_mb_count(const S360View& v, int NV, int64_t n_items, const uint32_t* 
   if (chunks == 0) return 0;
   // 16 warps per chunk: the per-warp work (rounds of 32 Gaussians, each a chain of shuffles and shared-memory atomics) is
   // latency-bound, so more and shorter chains win (8 warps: 25 us, measured)
-  mb_count_kernel<16><<<chunks, 512, (size_t)ntiles * 4, st>>>((int)n_items, n_dev, gx, ntiles, v.mode, g.rect, depth_order,
-                                                               (uint32_t*)scratch);
+  launch_pdl(mb_count_kernel<16>, dim3(chunks), dim3(512), (size_t)ntiles * 4, st, (int)n_items, n_dev, gx, ntiles, v.mode, g.rect,
+             depth_order, (uint32_t*)scratch);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -758,8 +763,8 @@ int launch_mb_count(const S360View& v, int NV, int64_t n_items, const uint32_t* 
 int launch_mb_colscan(const S360View& v, int NV, int64_t n_items, const uint32_t* n_dev, void* scratch, cudaStream_t st) {
   const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
   const int ntiles = gx * gy;
-  mb_colscan_kernel<<<(ntiles + 31) / 32, 1024, 0, st>>>((int)n_items, n_dev, ntiles, (uint32_t*)scratch,
-                                                         mb_tile_totals(scratch, n_items, ntiles));
+  launch_pdl(mb_colscan_kernel, dim3((ntiles + 31) / 32), dim3(1024), 0, st, (int)n_items, n_dev, ntiles, (uint32_t*)scratch,
+             mb_tile_totals(scratch, n_items, ntiles));
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -780,8 +785,8 @@ int launch_mb_scatter(const S360View& v, int NV, int64_t n_items, const uint32_t
   const uint32_t* prefix = (const uint32_t*)scratch;
 #define S360_SCATTER(BANDED_) do { \
     if (smem > 48 * 1024) cudaFuncSetAttribute(mb_scatter_kernel<16, BANDED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    mb_scatter_kernel<16, BANDED_><<<dim3(chunks, bands), 512, smem, st>>>((int)n_items, n_dev, gx, gy, band_rows, ntiles, v.mode, \
-        g.rect, depth_order, prefix, ranges, capacity, point_list, counters); } while (0)
+    launch_pdl(mb_scatter_kernel<16, BANDED_>, dim3(chunks, bands), dim3(512), smem, st, (int)n_items, n_dev, gx, gy, band_rows, ntiles, \
+               v.mode, g.rect, depth_order, prefix, ranges, capacity, point_list, counters); } while (0)
   if (bands > 1) S360_SCATTER(true); else S360_SCATTER(false);
 #undef S360_SCATTER
   count_launch();
@@ -797,6 +802,7 @@ int tile_hist_copies() { return TILE_HIST_COPIES; }
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, int copies, uint32_t capacity, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ order, uint32_t* __restrict__ work, uint32_t* __restrict__ hist, int npasses) {
+  pdl_enter();
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_hist[3][RS_BINS];
@@ -868,6 +874,7 @@ tile_scan_kernel(int ntiles, const uint32_t* __restrict__ tile_count, int copies
 // longest-first schedule of the backward pass from the work the forward pass measured per tile
 __global__ void __launch_bounds__(1024)
 tile_order_kernel(int ntiles, const uint32_t* __restrict__ work, uint32_t* __restrict__ order) {
+  pdl_enter();
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_bucket[1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -897,7 +904,7 @@ tile_order_kernel(int ntiles, const uint32_t* __restrict__ work, uint32_t* __res
 
 int launch_tile_order(const S360View& v, int NV, const uint32_t* work, uint32_t* order, cudaStream_t st) {
   const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
-  tile_order_kernel<<<1, 1024, 0, st>>>(gx * gy, work, order);
+  launch_pdl(tile_order_kernel, dim3(1), dim3(1024), 0, st, gx * gy, work, order);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -918,7 +925,7 @@ int launch_tile_scan(const S360View& v, int NV, const uint32_t* tile_count, int 
                      uint32_t* order, uint32_t* work, uint32_t* hist, int npasses, cudaStream_t st) {
   const int gx = (v.image_width + TILE - 1) / TILE, gy = NV * ((v.image_height + TILE - 1) / TILE);
   const uint32_t cap = (uint32_t)(capacity < 0xffffffffll ? capacity : 0xffffffffll);
-  tile_scan_kernel<<<1, 1024, 0, st>>>(gx * gy, tile_count, copies, cap, ranges, order, work, hist, npasses);
+  launch_pdl(tile_scan_kernel, dim3(1), dim3(1024), 0, st, gx * gy, tile_count, copies, cap, ranges, order, work, hist, npasses);
   count_launch();
   return (int)cudaGetLastError();
 }

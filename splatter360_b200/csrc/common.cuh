@@ -153,6 +153,31 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 void count_launch(int n = 1);
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled while its predecessor on the
+// stream is still draining -- its CTAs become resident as the predecessor's retire and park at pdl_enter() until the
+// predecessor's grid has completed and its writes are visible -- so the launch ramp of every kernel in the latency-bound
+// sort / binning chain overlaps the tail of the kernel before it (also inside a captured CUDA graph).  Rules kept here:
+// (1) pdl_enter() is the FIRST statement of every kernel launched through launch_pdl(), executed by all threads, so that
+// "this grid completed" always implies "everything before it completed"; (2) a kernel never touches global memory before
+// it.  pdl_enter() also releases the kernel's own dependents (they park the same way).  Launched normally, both
+// instructions are no-ops.  S360_PDL=0 in the environment turns the launch attribute off.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused depth channel: what the reference renders in a second full pass by feeding
 // per-Gaussian depth as colour (cuda_splatting.py:226-269).  The geometry record stores the sort depth of the
 // rescaled scene (camera z for pinhole, radial distance for erp); dividing by scene_scale recovers the value the

@@ -152,6 +152,7 @@ preprocess_backward_kernel(const S360View v, const float* __restrict__ means, co
                            const float* __restrict__ acc, float* __restrict__ d_means,
                            float* __restrict__ d_means2D, float* __restrict__ d_cov, float* __restrict__ d_opac,
                            float* __restrict__ d_shs, float* __restrict__ d_colors, const DepthSpec dspec) {
+  pdl_enter();
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: dL/dSH of this CTA
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = v.P;
@@ -255,7 +256,7 @@ int launch_preprocess_backward(const S360View& v, const float* means, const floa
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
 #define S360_LAUNCH_K8(MODE_, DEPTH_) do { \
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    preprocess_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, means, cov, opac, shs != nullptr, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
+    launch_pdl(preprocess_backward_kernel<MODE_, DEPTH_>, dim3(grid), dim3(PRE_THREADS), smem, st, v, means, cov, opac, shs != nullptr, g, radii, acc, d_means, d_means2D, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
   if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_K8(S360_MODE_PINHOLE, true); else S360_LAUNCH_K8(S360_MODE_PINHOLE, false); }
   else { if (has_depth) S360_LAUNCH_K8(S360_MODE_ERP, true); else S360_LAUNCH_K8(S360_MODE_ERP, false); }
 #undef S360_LAUNCH_K8
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(PRE_THREADS)
 multi_count_kernel(const S360View v, const int NV, const float* __restrict__ means, const float* __restrict__ cov3D,
                    const float* __restrict__ opac, PairState ps, int32_t* __restrict__ radii,
                    uint32_t* __restrict__ block_count, S360Counters* counters) {
+  pdl_enter();
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
   __shared__ uint32_t s_cnt[2];
   if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
@@ -348,6 +350,7 @@ multi_count_kernel(const S360View v, const int NV, const float* __restrict__ mea
 // order through the stable sorts exactly like separate per-view calls.
 __global__ void __launch_bounds__(1024)
 multi_scan_kernel(int nblocks, uint32_t* __restrict__ block_count, uint32_t cap, PairState ps, S360Counters* counters) {
+  pdl_enter();
   __shared__ uint32_t s_w[32];
   __shared__ uint32_t s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -389,6 +392,7 @@ multi_write_kernel(const S360View v, const int NV, const uint32_t cap, const flo
                    const float* __restrict__ colors, GeomState gs, PairState ps,
                    const uint32_t* __restrict__ block_base, uint32_t* __restrict__ depth_keys,
                    uint32_t* __restrict__ ids) {
+  pdl_enter();
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3] SH block of this CTA
   __shared__ uint64_t s_bar;
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
@@ -491,13 +495,13 @@ int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, co
     multi_count_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, 0, st>>>(v, NV, means, cov, opac, ps, radii, block_count, counters);
   else
     multi_count_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, 0, st>>>(v, NV, means, cov, opac, ps, radii, block_count, counters);
-  multi_scan_kernel<<<1, 1024, 0, st>>>(grid, block_count, cap, ps, counters);
+  launch_pdl(multi_scan_kernel, dim3(1), dim3(1024), 0, st, grid, block_count, cap, ps, counters);
   if (v.mode == S360_MODE_PINHOLE) {
     if (smem > 32 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_PINHOLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    multi_write_kernel<S360_MODE_PINHOLE><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
+    launch_pdl(multi_write_kernel<S360_MODE_PINHOLE>, dim3(grid), dim3(PRE_THREADS), smem, st, v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
   } else {
     if (smem > 32 * 1024) cudaFuncSetAttribute(multi_write_kernel<S360_MODE_ERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    multi_write_kernel<S360_MODE_ERP><<<grid, PRE_THREADS, smem, st>>>(v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
+    launch_pdl(multi_write_kernel<S360_MODE_ERP>, dim3(grid), dim3(PRE_THREADS), smem, st, v, NV, cap, means, cov, opac, shs, colors, g, ps, block_count, depth_keys, ids);
   }
   count_launch(3);
   return (int)cudaGetLastError();
@@ -505,6 +509,7 @@ int launch_preprocess_multi(const S360View& v, int NV, int64_t pair_capacity, co
 
 // zero the first min(*n_dev, cap) pair accumulators (the pair buffers are sized for the worst case V * P)
 __global__ void zero_acc_kernel(float4* __restrict__ acc, const uint32_t* __restrict__ n_dev, int64_t cap) {
+  pdl_enter();
   int64_t n = (int64_t)(*n_dev);
   if (n > cap) n = cap;
   n *= ACC_STRIDE / 4;
@@ -562,6 +567,7 @@ preprocess_multi_backward_kernel(const S360View v, const int NV, const float* __
                                  const float* __restrict__ acc, float* __restrict__ d_means,
                                  float* __restrict__ d_cov, float* __restrict__ d_opac, float* __restrict__ d_shs,
                                  float* __restrict__ d_colors, const DepthSpec dspec) {
+  pdl_enter();
   extern __shared__ __align__(128) float s_sh[];   // [PRE_THREADS][M*3]: dL/dSH of this CTA
   __shared__ float s_cam[S360_MAX_VIEWS][CAM_F];
   __shared__ int s_same;
@@ -667,7 +673,7 @@ int launch_preprocess_multi_backward(const S360View& v, int NV, const float* mea
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
 #define S360_LAUNCH_MK8(MODE_, DEPTH_) do { \
     if (smem > 40 * 1024) cudaFuncSetAttribute(preprocess_multi_backward_kernel<MODE_, DEPTH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    preprocess_multi_backward_kernel<MODE_, DEPTH_><<<grid, PRE_THREADS, smem, st>>>(v, NV, means, cov, opac, shs != nullptr, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
+    launch_pdl(preprocess_multi_backward_kernel<MODE_, DEPTH_>, dim3(grid), dim3(PRE_THREADS), smem, st, v, NV, means, cov, opac, shs != nullptr, g, ps, acc, d_means, d_cov, d_opac, d_shs, d_colors, ds); } while (0)
   if (v.mode == S360_MODE_PINHOLE) { if (has_depth) S360_LAUNCH_MK8(S360_MODE_PINHOLE, true); else S360_LAUNCH_MK8(S360_MODE_PINHOLE, false); }
   else { if (has_depth) S360_LAUNCH_MK8(S360_MODE_ERP, true); else S360_LAUNCH_MK8(S360_MODE_ERP, false); }
 #undef S360_LAUNCH_MK8

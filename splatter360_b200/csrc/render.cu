@@ -146,6 +146,7 @@ render_forward_kernel(const int W, const int H, const float* __restrict__ bg, co
                       const uint32_t* __restrict__ order, uint32_t* __restrict__ work,
                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color,
                       float* __restrict__ out_depth, const DepthSpec dspec) {
+  pdl_enter();
   // survivors of the current chunk, compacted in list order: [0] = A', B', C' (log2-scaled conic), log2(opacity);
   // [1] = -r, -g, -b, -depth value; [2] = centre relative to the warp block (x, y), wide flag, position in the tile list
   __shared__ float4 s_sv[NWARPS][3][32];
@@ -306,7 +307,7 @@ int launch_render_forward(const S360View& v, int NV, GeomState g, const uint32_t
   if (tiles == 0) return 0;
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
-#define S360_LAUNCH_FWD(MODE_, DEPTH_) render_forward_kernel<MODE_, DEPTH_><<<tiles, RT, 0, st>>>( \
+#define S360_LAUNCH_FWD(MODE_, DEPTH_) launch_pdl(render_forward_kernel<MODE_, DEPTH_>, dim3(tiles), dim3(RT), 0, st, \
       W, H, v.bg, g.rec, point_list, img.ranges, img.order, img.work, img.final_T, img.n_contrib, out_color, out_depth, ds)
   if (v.mode == S360_MODE_PINHOLE) { if (out_depth) S360_LAUNCH_FWD(S360_MODE_PINHOLE, true); else S360_LAUNCH_FWD(S360_MODE_PINHOLE, false); }
   else { if (out_depth) S360_LAUNCH_FWD(S360_MODE_ERP, true); else S360_LAUNCH_FWD(S360_MODE_ERP, false); }
@@ -380,6 +381,7 @@ render_backward_kernel(const int W, const int H, const float* __restrict__ bg, c
                        const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth, const DepthSpec dspec,
                        float* __restrict__ acc) {
+  pdl_enter();
   // survivors of the current chunk, compacted back-to-front: [0] = A', B', C', log2(opacity); [1] = r, g, b, bits of the
   // Gaussian id; [2] = centre relative to the warp block (x, y), wide flag, position in the tile list
   __shared__ float4 s_sv[NWARPS][3][32];
@@ -566,7 +568,7 @@ int launch_render_backward(const S360View& v, int NV, GeomState g, const uint32_
   if (tiles == 0) return 0;
   DepthSpec ds;
   ds.mode = depth_mode; ds.inv_scale = 1.f / v.scene_scale; ds.near = depth_near; ds.far = depth_far;
-#define S360_LAUNCH_BWD(MODE_, DEPTH_) render_backward_kernel<MODE_, DEPTH_><<<tiles, RT, 0, st>>>( \
+#define S360_LAUNCH_BWD(MODE_, DEPTH_) launch_pdl(render_backward_kernel<MODE_, DEPTH_>, dim3(tiles), dim3(RT), 0, st, \
       W, H, v.bg, g.rec, point_list, img.ranges, img.order_bwd, img.final_T, img.n_contrib, dL_dcolor, dL_ddepth, ds, acc)
   if (v.mode == S360_MODE_PINHOLE) { if (dL_ddepth) S360_LAUNCH_BWD(S360_MODE_PINHOLE, true); else S360_LAUNCH_BWD(S360_MODE_PINHOLE, false); }
   else { if (dL_ddepth) S360_LAUNCH_BWD(S360_MODE_ERP, true); else S360_LAUNCH_BWD(S360_MODE_ERP, false); }
