@@ -345,7 +345,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item()) / Ke
         e2e = {"value": P * world / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": e2e_ms, "steps": Ke,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4, "numa_bind": _NUMA["bind"],
                "api": "splatter360_b200.io.HostSceneFeeder (pinned host -> device, upload of step i+1 overlaps step i) + "
                       "splatter360_b200.decoder.render_erp fwd + bwd + loss D2H; every step's H2D copy is inside the timed region"}
 
@@ -470,9 +470,16 @@ def _dist_setup(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if not getattr(args, "no_numa_bind", False):
+        # pinned host buffers of the e2e legs land on the NUMA node this rank's GPU hangs off
+        from splatter360_b200.io import bind_to_gpu_numa_node
+        _NUMA["bind"] = bind_to_gpu_numa_node(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     return rank, world, local_rank, dev
+
+
+_NUMA = {"bind": None}
 
 
 def _timed(fn, K, Wm, world, dev):
@@ -595,7 +602,7 @@ def run_config5(args):
         e2e = {"value": Pv * n_frames / (e2e_ms * 1e-3), "unit": "Gaussians/s", "ms_per_step": e2e_ms, "steps": Ke,
                "frames_per_s": n_frames / (e2e_ms * 1e-3),
                "h2d_bytes_per_step": int(scene_bytes), "d2h_bytes_per_step": int(n_frames * 3 * Hv * Wv * 4),
-               "broadcast_bytes_per_rank": int(scene_bytes) if world > 1 else 0,
+               "broadcast_bytes_per_rank": int(scene_bytes) if world > 1 else 0, "numa_bind": _NUMA["bind"],
                "api": "pinned host scene on rank 0 -> parallel.upload_and_broadcast_scene (one H2D upload in 64-MB chunks, each chunk "
                       "broadcast by NCCL over NVLink while the next one uploads) -> rasterizer.forward_raw per frame -> every frame to "
                       "pinned host on a copy stream while the next one renders; all inside the timed region"}
@@ -919,6 +926,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the process's CPU affinity alone (default: the CPUs of the GPU's NUMA node)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cube6", action="store_true")
     ap.add_argument("--exact-counts", action="store_true", help="read the instance count back every view (no CapacityTracker)")

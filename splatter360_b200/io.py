@@ -7,10 +7,47 @@ that with pinned source buffers, a small ring of reusable device buffers and str
 """
 from __future__ import annotations
 
-from typing import Dict, NamedTuple
+import os
+from typing import Dict, NamedTuple, Optional
 
 import torch
 from torch import Tensor
+
+
+def gpu_numa_node(device) -> Optional[int]:
+    """NUMA node the GPU's PCIe root hangs off (sysfs), or None when the platform does not say."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa_node(device) -> Optional[dict]:
+    """Pin the calling process to the CPUs of the GPU's NUMA node BEFORE it allocates pinned host buffers: pinned pages are
+    placed on the node of the allocating thread, and an upload from the other socket crosses the inter-socket link on top of
+    PCIe.  One process per GPU (the torchrun shape) makes this a per-rank decision.  Returns {"node", "cpus"} or None when
+    the topology is not exposed (then nothing is changed)."""
+    node = gpu_numa_node(device)
+    if node is None:
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)          # never widen what the launcher / container allows
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
 
 
 class Ticket(NamedTuple):
