@@ -241,3 +241,33 @@ def test_shard_view_groups_keeps_cube_faces_together():
     assert sorted(sum(parts, [])) == list(range(14)) and parts[2] == [12, 13] and parts[3] == []
     with pytest.raises(ValueError):
         shard_view_groups(6, 0, 0, 1)
+
+
+def test_frozen_capacity_tracker_and_numa_helpers_without_a_gpu():
+    """CapacityTracker.freeze (what graph.GraphedAutogradStep relies on): fixed capacities, no polling, the counters of the
+    captured call are only remembered; the NUMA helpers change nothing when the topology is not exposed."""
+    import os
+    from splatter360_b200 import io
+    from splatter360_b200 import rasterizer as R
+    t = R.CapacityTracker(margin=1.25)
+    with pytest.raises(RuntimeError):
+        t.freeze()                                   # nothing observed yet
+    t._take(0, torch.tensor([1000, 0, 300, 0], dtype=torch.int32))
+    assert t.capacity == max(t.min_capacity, 1251) and t.pair_capacity == max(t.min_capacity, 376)
+    t.freeze()
+    s = R.GaussianRasterizationSettings(
+        image_height=16, image_width=16, tanfovx=1.0, tanfovy=1.0, bg=torch.zeros(3), scale_modifier=1.0,
+        viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3), prefiltered=False, debug=False)
+    assert t.settings(s).instance_capacity == t.capacity and t.settings(s).pair_capacity is None
+    both = t.settings(s, pairs=True)
+    assert (both.instance_capacity, both.pair_capacity) == (t.capacity, t.pair_capacity)
+    t.observe(torch.tensor([5000, 1, 10, 0], dtype=torch.int32))     # frozen: remembered, not copied, capacity untouched
+    assert t.frozen_overflowed() and t.capacity == max(t.min_capacity, 1251) and not t._pending
+    t.observe(torch.tensor([900, 0, 10, 0], dtype=torch.int32))
+    assert not t.frozen_overflowed()
+    t.unfreeze()
+    assert not t.frozen and not t.frozen_overflowed()
+    before = os.sched_getaffinity(0)
+    assert io.gpu_numa_node("cuda:0") is None or isinstance(io.gpu_numa_node("cuda:0"), int)
+    if not torch.cuda.is_available():
+        assert io.bind_to_gpu_numa_node("cuda:0") is None and os.sched_getaffinity(0) == before
