@@ -16,14 +16,21 @@ namespace s360 {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-#ifndef S360_RS_ITEMS
-#define S360_RS_ITEMS 12
-#endif
 #ifndef S360_RS_MINB
 #define S360_RS_MINB 3
 #endif
-constexpr int RS_ITEMS = S360_RS_ITEMS;           // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;    // 2048 keys per block
+// keys per thread of a onesweep pass: 12 (3072 per CTA) in general; 10 (2560 per CTA) while all CTAs of a pass are still
+// resident at once (148 SMs x 3 CTAs): more, shorter CTAs finish a latency-bound pass sooner (1M keys: 18.6 -> 17.5 us per
+// pass; with 3M keys -- several waves either way -- the smaller tile is 2 % slower).  -DS360_RS_ITEMS_FORCE=10 or 12 pins one of the two (A/B).
+constexpr int RS_ITEMS_SMALL = 10, RS_ITEMS_LARGE = 12;
+constexpr int64_t RS_SMALL_MAX_KEYS = (int64_t)148 * 3 * RS_THREADS * RS_ITEMS_SMALL;
+static inline int rs_items(int64_t n) {
+#ifdef S360_RS_ITEMS_FORCE
+  (void)n; return S360_RS_ITEMS_FORCE;
+#else
+  return n <= RS_SMALL_MAX_KEYS ? RS_ITEMS_SMALL : RS_ITEMS_LARGE;
+#endif
+}
 constexpr int RS_BINS = 256;
 constexpr uint32_t ST_AGG = 1u << 30, ST_PREFIX = 2u << 30, ST_MASK = (1u << 30) - 1u;
 
@@ -67,15 +74,17 @@ rs_global_hist_kernel(const uint32_t* __restrict__ keys, int64_t n_cap, const ui
 // ---- one radix pass: rank in block, look back for the cross-block prefix, exchange, scatter ---
 // hist: this pass's global digit counts [256].  status: [nblocks][256], zero on entry.
 // counter: zero on entry; hands out block ids in scheduling order so that look-back cannot deadlock.
+template <int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, S360_RS_MINB)
 rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
                    const uint32_t* __restrict__ n_dev, int shift, const uint32_t* __restrict__ hist,
                    uint32_t* status, uint32_t* counter) {
   pdl_enter();
+  constexpr int TILE = RS_THREADS * ITEMS;
   __shared__ uint32_t s_cnt[RS_WARPS][RS_BINS];   // per-warp digit counters -> exclusive warp prefixes
-  __shared__ uint32_t s_keys[RS_TILE];
-  __shared__ uint32_t s_vals[RS_TILE];
+  __shared__ uint32_t s_keys[TILE];
+  __shared__ uint32_t s_vals[TILE];
   __shared__ int64_t s_gbase[RS_BINS];            // global destination of local sorted slot 0 of each digit
   __shared__ uint32_t s_scan[RS_WARPS];
   __shared__ uint32_t s_scan2[RS_WARPS];
@@ -86,16 +95,16 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   for (int w = 0; w < RS_WARPS; w++) s_cnt[w][threadIdx.x] = 0;
   __syncthreads();
   const uint32_t bid = s_bid;
-  const int64_t base = (int64_t)bid * RS_TILE;
+  const int64_t base = (int64_t)bid * TILE;
   if (base >= n) return;   // every later block is out of range too: nobody will look back at this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // warp w owns the contiguous items [w*256, w*256+256) of this block, 8 rounds of 32
-  uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+  uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; r++) {
-    const int64_t j = base + warp * (RS_ITEMS * 32) + r * 32 + lane;
+  for (int r = 0; r < ITEMS; r++) {
+    const int64_t j = base + warp * (ITEMS * 32) + r * 32 + lane;
     key[r] = 0; val[r] = 0;
     if (j < n) { key[r] = keys_in[j]; val[r] = vals_in[j]; }
   }
@@ -103,10 +112,10 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   // lanes with the same digit, from eight ballots (one per digit bit) instead of MATCH.ANY: the match instruction's
   // latency grows with the number of distinct values in the warp (~30 of 256 digits here) and every round waits for it;
   // the ballots of all rounds are independent and are issued back to back before the serial counter updates
-  unsigned peer_mask[RS_ITEMS];
+  unsigned peer_mask[ITEMS];
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; r++) {
-    const int64_t j = base + warp * (RS_ITEMS * 32) + r * 32 + lane;
+  for (int r = 0; r < ITEMS; r++) {
+    const int64_t j = base + warp * (ITEMS * 32) + r * 32 + lane;
     const uint32_t d = (key[r] >> shift) & 0xffu;
     unsigned m = __ballot_sync(0xffffffffu, j < n);
 #pragma unroll
@@ -119,8 +128,8 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   }
 #endif
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; r++) {
-    const int64_t j = base + warp * (RS_ITEMS * 32) + r * 32 + lane;
+  for (int r = 0; r < ITEMS; r++) {
+    const int64_t j = base + warp * (ITEMS * 32) + r * 32 + lane;
     const bool valid = j < n;
     const uint32_t d = valid ? ((key[r] >> shift) & 0xffu) : (0x100u | lane);
 #ifdef S360_RS_MATCH
@@ -212,8 +221,8 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   __syncthreads();
 
 #pragma unroll
-  for (int r = 0; r < RS_ITEMS; r++) {
-    const int64_t j = base + warp * (RS_ITEMS * 32) + r * 32 + lane;
+  for (int r = 0; r < ITEMS; r++) {
+    const int64_t j = base + warp * (ITEMS * 32) + r * 32 + lane;
     if (j < n) {
       const uint32_t dg = (key[r] >> shift) & 0xffu;
       const uint32_t slot = s_cnt[warp][dg] + rank[r];
@@ -222,9 +231,9 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
     }
   }
   __syncthreads();
-  const int nvalid = (int)((n - base) < (int64_t)RS_TILE ? (n - base) : (int64_t)RS_TILE);
+  const int nvalid = (int)((n - base) < (int64_t)TILE ? (n - base) : (int64_t)TILE);
 #pragma unroll
-  for (int i = 0; i < RS_ITEMS; i++) {
+  for (int i = 0; i < ITEMS; i++) {
     const int slot = i * RS_THREADS + threadIdx.x;
     if (slot < nvalid) {
       const uint32_t k = s_keys[slot];
@@ -235,7 +244,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   }
 }
 
-static inline int rs_blocks(int64_t n) { return (int)((n + RS_TILE - 1) / RS_TILE); }
+static inline int rs_blocks(int64_t n) { const int tile = RS_THREADS * rs_items(n); return (int)((n + tile - 1) / tile); }
 
 // scratch: [hist 4*256][counters 4 (padded)][status passes*nblocks*256]
 static inline size_t rs_status_words(int64_t n, int passes) { return (size_t)passes * rs_blocks(n > 0 ? n : 1) * RS_BINS; }
@@ -263,8 +272,12 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
   uint32_t *ki = keys_a, *vi = vals_a, *ko = keys_b, *vo = vals_b;
   for (int p = 0; p < passes; p++) {
     uint32_t* vdst = (vals_final != nullptr && p == passes - 1) ? vals_final : vo;   // last pass may write elsewhere
-    launch_pdl(rs_onesweep_kernel, dim3(nblocks), dim3(RS_THREADS), 0, st, ki, vi, ko, vdst, n, n_dev, 8 * p, hist + p * RS_BINS,
-               status + (size_t)p * nblocks * RS_BINS, counters + p);
+    if (rs_items(n) == RS_ITEMS_SMALL)
+      launch_pdl(rs_onesweep_kernel<RS_ITEMS_SMALL>, dim3(nblocks), dim3(RS_THREADS), 0, st, ki, vi, ko, vdst, n, n_dev, 8 * p,
+                 hist + p * RS_BINS, status + (size_t)p * nblocks * RS_BINS, counters + p);
+    else
+      launch_pdl(rs_onesweep_kernel<RS_ITEMS_LARGE>, dim3(nblocks), dim3(RS_THREADS), 0, st, ki, vi, ko, vdst, n, n_dev, 8 * p,
+                 hist + p * RS_BINS, status + (size_t)p * nblocks * RS_BINS, counters + p);
     count_launch();
     uint32_t* t = ki; ki = ko; ko = t;
     t = vi; vi = vo; vo = t;
@@ -455,7 +468,11 @@ emit_instances_kernel(int P_cap, const uint32_t* __restrict__ n_dev, int gx, int
 // straight to  ranges[tile].x + prefix[chunk][tile] + rank.  Result: point_list sorted by (tile, depth, id), bit-identical
 // to emit + two stable radix passes, with 4 B written per instance instead of 8 B emitted + 2 x 16 B sorted, and no
 // scan of per-Gaussian offsets at all.  Used whenever tiles <= MB_MAX_TILES and the matrix stays small.
-constexpr int MB_CHUNK = 2048;
+#ifndef S360_MB_CHUNK
+#define S360_MB_CHUNK 2048
+#endif
+constexpr int MB_CHUNK = S360_MB_CHUNK;   // a multiple of 512 (16 warps x 32 Gaussians per round)
+static_assert(MB_CHUNK % 512 == 0 && MB_CHUNK >= 512 && MB_CHUNK <= 8192, "MB_CHUNK: whole rounds of 16 warps, u16 counters");
 constexpr int MB_MAX_TILES = 8192;    // shared-memory tile histogram of the count kernel: 32 KB
 constexpr int MB_BAND_TILES = 2048;   // tiles per band of the scatter kernel (and the widest supported tile row)
 
