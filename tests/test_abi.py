@@ -85,3 +85,25 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     "-l:libsplatter360.so", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == _lib.ABI_VERSION and int(out[1]) > 6 * 256 * 256 * 8
+
+
+def test_every_kernel_launched_with_programmatic_dependent_launch_waits_first():
+    """common.cuh's rule for launch_pdl(): the kernel's FIRST statement is pdl_enter() (griddepcontrol.wait before anything
+    touches global memory, executed by every thread) -- otherwise "this grid completed" would no longer imply "everything
+    before it completed" for the kernels further down the stream.  Checked on the sources, no GPU needed."""
+    import glob
+    import re
+    src = {p: open(p).read() for p in glob.glob(os.path.join(ROOT, "splatter360_b200", "csrc", "*.cu"))}
+    launched = set()
+    for text in src.values():
+        launched |= set(re.findall(r"launch_pdl\(\s*([A-Za-z_0-9]+)\s*[<,]", text))
+    assert len(launched) >= 10, launched
+    for name in sorted(launched):
+        bodies = []
+        for text in src.values():
+            for m in re.finditer(r"__global__[^;{]*?\b" + name + r"\s*\(", text, flags=re.S):
+                brace = text.index(") {", m.end())
+                bodies.append(text[brace + 3:brace + 80].strip())
+        assert bodies, f"definition of {name} not found"
+        for b in bodies:
+            assert b.startswith("pdl_enter();"), f"{name}: first statement is {b[:40]!r}"
