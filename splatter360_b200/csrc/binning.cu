@@ -3,7 +3,9 @@
 // Upstream sorts N (tile<<32 | depth) 64-bit keys with CUB (6 passes over every instance).  Here the
 // order (tile, depth, id) is produced in two cheaper steps with identical result:
 //   1. sort the P Gaussians once by (depth bits, id)              -- 4 passes over P pairs
-//   2. emit instances in that order, then STABLE-sort them by tile -- ceil(log2(tiles)/8) passes over N
+//   2. bucket the instances by tile in that order, stably: "matrix binning" (count matrix [chunk][tile] -> column scan ->
+//      ranked scatter, further down) whenever the tile count allows it; otherwise emit (tile, id) and STABLE-sort by tile
+//      -- ceil(log2(tiles)/8) passes over N
 // Each pass is ONE kernel (onesweep: per-block digit counts are published to a status array and the
 // exclusive prefix over preceding blocks is obtained by decoupled look-back), the digit histograms of
 // all passes come from a single read of the keys (depth) or from the per-tile instance histogram that
@@ -100,7 +102,7 @@ rs_onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  // warp w owns the contiguous items [w*256, w*256+256) of this block, 8 rounds of 32
+  // warp w owns the contiguous items [w * 32 * ITEMS, (w + 1) * 32 * ITEMS) of this block: ITEMS rounds of 32
   uint32_t key[ITEMS], val[ITEMS], rank[ITEMS];
 #pragma unroll
   for (int r = 0; r < ITEMS; r++) {
