@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "render.cu", "loss.cu", "cubemap.cu", "adapter.cu", "camera.cu"]
-HEADERS = ["common.cuh", "persplat.cuh", "render_cull.cuh", "adapter_math.cuh", os.path.join("..", "..", "include", "splatter360.h")]
+HEADERS = ["common.cuh", "persplat.cuh", "render_cull.cuh", "adapter_math.cuh", "camera_math.cuh", os.path.join("..", "..", "include", "splatter360.h")]
 OUT = os.path.join(PKG, "libsplatter360.so")
 
 NVCC_FLAGS = [

@@ -5,7 +5,7 @@
 // matrix here: Gauss-Jordan with partial pivoting in double precision, rounded once to float -- within half an ulp of the
 // exact inverse, one launch, nothing on the host, capturable in a CUDA graph.  Singular input yields inf/nan like
 // `torch.linalg.inv_ex` (no status).
-#include "common.cuh"
+#include "camera_math.cuh"
 
 namespace s360 {
 
@@ -13,39 +13,7 @@ __global__ void __launch_bounds__(64)
 invert4x4_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double a[4][8];
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      a[r][c] = (double)in[i * 16 + r * 4 + c];
-      a[r][4 + c] = r == c ? 1.0 : 0.0;
-    }
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    // partial pivoting: bring the largest |a[r][k]|, r >= k, to row k (conditional swaps keep everything in registers)
-#pragma unroll
-    for (int r = k + 1; r < 4; r++) {
-      if (fabs(a[r][k]) > fabs(a[k][k])) {
-#pragma unroll
-        for (int c = 0; c < 8; c++) { const double t = a[k][c]; a[k][c] = a[r][c]; a[r][c] = t; }
-      }
-    }
-    const double inv = 1.0 / a[k][k];
-#pragma unroll
-    for (int c = 0; c < 8; c++) a[k][c] *= inv;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      if (r == k) continue;
-      const double f = a[r][k];
-#pragma unroll
-      for (int c = 0; c < 8; c++) a[r][c] -= f * a[k][c];
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-#pragma unroll
-    for (int c = 0; c < 4; c++) out[i * 16 + r * 4 + c] = (float)a[r][4 + c];
+  invert4x4(in + i * 16, out + i * 16);
 }
 
 }  // namespace s360

@@ -1,9 +1,10 @@
 // harness.cu -- TEST INFRASTRUCTURE.  Compiles the per-Gaussian math the kernels inline (splatter360_b200/csrc/persplat.cuh:
-// project_view, sh_to_rgb, view_backward, depth_value) for the HOST, so that tests/test_host_math.py can check the very
+// project_view, sh_to_rgb, view_backward, depth_value; camera_math.cuh: invert4x4) for the HOST, so that tests/test_host_math.py can check the very
 // code the GPU runs against the CPU oracle without a GPU.  Plain C entry points, host pointers everywhere.
 #include "../../splatter360_b200/csrc/persplat.cuh"
 #include "../../splatter360_b200/csrc/render_cull.cuh"
 #include "../../splatter360_b200/csrc/adapter_math.cuh"
+#include "../../splatter360_b200/csrc/camera_math.cuh"
 
 using namespace s360;
 
@@ -111,6 +112,12 @@ int s360h_adapter(int views, int H, int W, int sh_degree, float smin, float smax
       }
     }
   }
+  return 0;
+}
+
+// batched 4x4 inverse exactly as camera.cu's kernel computes it, one matrix after the other
+int s360h_invert4x4(const float* in, float* out, int64_t n) {
+  for (int64_t i = 0; i < n; i++) invert4x4(in + i * 16, out + i * 16);
   return 0;
 }
 

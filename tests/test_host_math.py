@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not (os.path.exists(NVCC) or shutil.which("nvcc"
 def harness():
     src = os.path.join(HERE, "host_harness", "harness.cu")
     out = os.path.join(HERE, "host_harness", "libharness.so")
-    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh", "render_cull.cuh", "adapter_math.cuh")]
+    deps = [src] + [os.path.join(HERE, "..", "splatter360_b200", "csrc", f) for f in ("persplat.cuh", "common.cuh", "render_cull.cuh", "adapter_math.cuh", "camera_math.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         nvcc = NVCC if os.path.exists(NVCC) else shutil.which("nvcc")
         subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
@@ -237,3 +237,23 @@ def test_frustum_reject_never_drops_a_visible_gaussian_on_cube_faces(harness):
         assert np.array_equal(c["tiles_touched"], o["tiles_touched"]), k
         seen += int((o["radii"] > 0).sum())
     assert seen > n          # most Gaussians are seen by more than one face at this size
+
+
+def test_invert4x4_on_the_host_matches_the_float64_inverse(harness):
+    """camera_math.cuh (the body of s360_invert4x4's kernel): rigid poses, general matrices that need pivoting, a zero
+    leading pivot -- within float rounding of numpy's float64 inverse; singular input yields non-finite values, no crash."""
+    from splatter360_b200 import synthetic
+    rng = np.random.default_rng(3)
+    poses = synthetic.trajectory(40, seed=2).numpy().astype(np.float32)
+    general = (rng.standard_normal((60, 4, 4)) + 2 * np.eye(4)).astype(np.float32)
+    general[7, 0, 0] = 0.0
+    perm = np.eye(4, dtype=np.float32)[[2, 0, 3, 1]][None]                    # every pivot needs a row swap
+    m = np.ascontiguousarray(np.concatenate([poses, general, perm]))
+    out = np.empty_like(m)
+    assert harness.s360h_invert4x4(_p(m), _p(out), ctypes.c_int64(m.shape[0])) == 0
+    want = np.linalg.inv(m.astype(np.float64))
+    err = np.abs(out - want).max(axis=(1, 2)) / np.abs(want).max(axis=(1, 2))
+    assert err.max() < 2e-7, err.max()
+    assert np.array_equal(out[-1], perm[0].T)
+    sing = np.zeros((1, 4, 4), np.float32); o2 = np.empty_like(sing)
+    assert harness.s360h_invert4x4(_p(sing), _p(o2), ctypes.c_int64(1)) == 0 and not np.isfinite(o2).all()
